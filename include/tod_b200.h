@@ -1,0 +1,212 @@
+/*
+ * tod_b200.h — C-ABI of libtod_b200.so: the B200 (sm_100a) implementation of TOD's detection hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one piece of the reference's two ecto cells
+ * (reference = wg-perception/tod 0.5.6; file:line below are relative to the reference tree):
+ *
+ *   tod::DescriptorMatcher   src/detection/DescriptorMatcher.cpp:58-270   -> tod_matcher_*
+ *   tod::GuessGenerator      src/detection/GuessGenerator.cpp:69-276      -> tod_guess_*
+ *   tod::AdjacencyRansac     src/common/adjacency_ransac.{h,cpp}          -> tod_fill_adjacency, tod_score_hypotheses,
+ *                                                                            tod_guess_process
+ *
+ * Conventions: plain pointers and sizes only, caller-owned buffers, int status returns (TOD_OK == 0),
+ * thread-local tod_last_error(), no exceptions cross the ABI.  A handle is NOT thread-safe — the reference's
+ * scheduler calls the cells serially on one thread.  There is no CPU fallback: every compute entry
+ * point fails with TOD_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef TOD_B200_H_
+#define TOD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOD_B200_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------------------------------------------- */
+enum {
+  TOD_OK = 0,
+  TOD_ERR_INVALID = 1,   /* bad argument (null pointer, negative size, k out of range, ...) */
+  TOD_ERR_STATE = 2,     /* call order violated (knn before train, ...) */
+  TOD_ERR_CUDA = 3,      /* CUDA runtime error or no usable device */
+  TOD_ERR_LIMIT = 4,     /* a documented capacity limit was exceeded */
+  TOD_ERR_PARSE = 5      /* malformed JSON parameter string */
+};
+
+/* Message of the last failing call on this thread ("" if none). Never NULL. */
+const char *tod_last_error(void);
+int tod_abi_version(void);
+/* Number of kernels launched by this library in this process so far (bench.py reports it as gpu_launches). */
+uint64_t tod_kernel_launch_count(void);
+
+/* ---- POD mirrors of the OpenCV / ORK types that cross the cell boundary -------------------- */
+
+/* cv::DMatch {int queryIdx; int trainIdx; int imgIdx; float distance;}  — 16 bytes, same field order. */
+typedef struct tod_match {
+  int32_t queryIdx;
+  int32_t trainIdx; /* row inside the object's descriptor matrix */
+  int32_t imgIdx;   /* object index (order of tod_matcher_add_object calls) */
+  float distance;   /* Hamming distance, an exact integer in [0,256] */
+} tod_match;
+
+/* cv::KeyPoint {Point2f pt; float size; float angle; float response; int octave; int class_id;} — 28 bytes. */
+typedef struct tod_keypoint {
+  float x, y;
+  float size, angle, response;
+  int32_t octave, class_id;
+} tod_keypoint;
+
+/* object_recognition_core::common::PoseResult as filled at GuessGenerator.cpp:224-228 (R, T, object id). */
+typedef struct tod_pose {
+  float R[9];            /* row-major 3x3, object -> camera (adjacency_ransac.cpp:304) */
+  float T[3];            /* metres (adjacency_ransac.cpp:305) */
+  int32_t object_index;  /* index into the matcher's object_ids (GuessGenerator.cpp:175-176) */
+  int32_t n_inliers;     /* number of distinct inlier keypoints (query_inliers.size(), GuessGenerator.cpp:202) */
+} tod_pose;
+
+/* ================================================================================================================
+ * DescriptorMatcher  (DescriptorMatcher.cpp)
+ * ============================================================================================================== */
+
+typedef struct tod_matcher tod_matcher;
+
+enum { TOD_SEARCH_EXACT = 0, TOD_SEARCH_LSH = 1 /* accepted for .ork compatibility; runs the exact search */ };
+enum { TOD_KERNEL_AUTO = 0, TOD_KERNEL_POPC = 1, TOD_KERNEL_MMA = 2 };
+#define TOD_MAX_K 8
+
+typedef struct tod_matcher_params {
+  int32_t k;            /* neighbours per query, 1..TOD_MAX_K. The reference hard-codes 5 (DescriptorMatcher.cpp:211) */
+  uint32_t radius;      /* keep matches with distance <= radius; 0 = no radius cut.
+                           unsigned int like DescriptorMatcher.cpp:257 */
+  int32_t search_type;  /* TOD_SEARCH_* (DescriptorMatcher.cpp:175) */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t shard_rank;   /* this handle holds rows [rank*ceil(N/count), ...) of the concatenated DB */
+  int32_t shard_count;  /* 1 = whole DB on this GPU */
+  int32_t kernel;       /* TOD_KERNEL_* : which K1 formulation to run */
+  int32_t reserved;
+} tod_matcher_params;
+
+void tod_matcher_default_params(tod_matcher_params *p); /* k=5, radius=0, exact, device 0, 1 shard, auto */
+
+/* configure(): parses the reference's "search_json_params" string — fields type, radius, ratio, n_tables, key_size,
+ * multi_probe_level (DescriptorMatcher.cpp:159-181) — into *p (k stays 5, as hard-coded in the reference).
+ * type "LSH" is accepted and mapped to the exact search; unknown types fail with TOD_ERR_INVALID instead of the
+ * reference's bare `throw;` -> std::terminate (:182-186). */
+int tod_matcher_params_from_json(const char *search_json_params, tod_matcher_params *p);
+
+int tod_matcher_create(const tod_matcher_params *p, tod_matcher **out);
+void tod_matcher_destroy(tod_matcher *m);
+
+/* parameter_callback(), one DB document per call (DescriptorMatcher.cpp:70-123): descriptors = n x 32 u8 row-major
+ * (training.cpp:157), points = n x 3 f32 (the 1 x N CV_32FC3 "points" attachment, training.cpp:158). Data is copied.
+ * The object's span (:106-121) is computed here.  imgIdx = order of calls. */
+int tod_matcher_add_object(tod_matcher *m, const char *object_id, const uint8_t *descriptors, const float *points,
+                           int32_t n);
+/* matcher_->clear() (:127) */
+int tod_matcher_clear(tod_matcher *m);
+/* matcher_->add(descriptors_db_) + (lazy) train (:128): concatenates objects in imgIdx order, selects this handle's
+ * shard, uploads descriptors (sharded) and points/object table (replicated) to HBM. */
+int tod_matcher_train(tod_matcher *m);
+
+int32_t tod_matcher_num_objects(const tod_matcher *m);
+int64_t tod_matcher_num_descriptors(const tod_matcher *m);       /* whole DB */
+int64_t tod_matcher_shard_rows(const tod_matcher *m);            /* rows resident on this GPU */
+const char *tod_matcher_object_id(const tod_matcher *m, int32_t object_index); /* outputs["object_ids"] (:248) */
+float tod_matcher_span(const tod_matcher *m, int32_t object_index);            /* outputs["spans"] (:249) */
+int32_t tod_matcher_k(const tod_matcher *m);
+
+/* process() (DescriptorMatcher.cpp:195-252) with HOST buffers: knnMatch(k) -> radius cut -> matches_3d gather.
+ *   descriptors: nq x 32 u8.   matches: nq x k (row q holds counts[q] valid entries, sorted by
+ *   (distance, imgIdx, trainIdx) exactly like cv::BFMatcher(NORM_HAMMING).knnMatch).  counts: nq.
+ *   points3d: nq x k x 3 f32 (matches_3d), may be NULL.  Only valid with shard_count == 1. */
+int tod_matcher_knn(tod_matcher *m, const uint8_t *descriptors, int32_t nq, tod_match *matches, int32_t *counts,
+                    float *points3d);
+
+/* Device-resident stages of the same call, for the sharded (one process per GPU) path. All pointers are device
+ * pointers on the handle's device; `stream` is a cudaStream_t (NULL = the handle's own stream).
+ *   knn_keys: this shard's top-k per query as packed keys (distance << 23 | global_row), ascending, padded with
+ *             0xFFFFFFFF.  d_keys: nq x k u32.  min() over keys == the (distance, imgIdx, trainIdx) order.
+ *   merge:    d_keys_all = n_src x nq x k gathered keys (e.g. after an NCCL all-gather) -> final matches.
+ */
+int tod_matcher_knn_keys_device(tod_matcher *m, const void *d_descriptors, int32_t nq, uint32_t *d_keys, void *stream);
+int tod_matcher_merge_device(tod_matcher *m, const uint32_t *d_keys_all, int32_t n_src, int32_t nq,
+                             tod_match *d_matches, int32_t *d_counts, float *d_points3d, void *stream);
+/* Device time (ms, CUDA events on the launch stream) of the K1 kernel alone in the last knn call; <0 if unknown. */
+float tod_matcher_last_k1_ms(const tod_matcher *m);
+/* Name of the K1 formulation actually used by the last call ("popc" | "mma"). */
+const char *tod_matcher_last_kernel(const tod_matcher *m);
+
+/* ================================================================================================================
+ * Geometry stages (adjacency_ransac.cpp, sac_model_registration_graph.h) — exposed for parity tests and reuse
+ * ============================================================================================================== */
+
+/* Words (u32) per bit-matrix row for a cluster of n correspondences: ceil(n/32) rounded up to a multiple of 4. */
+int32_t tod_adjacency_row_words(int32_t n);
+
+/* K2 — AdjacencyRansac::FillAdjacency (adjacency_ransac.cpp:127-172) for a batch of clusters, HOST buffers.
+ *   cluster c owns correspondences [offsets[c], offsets[c+1]).
+ *   query_pts/train_pts: N x 3 f32; pixels: N x 2 f32 (keypoints[query_indices_[i]].pt); spans: per cluster.
+ *   physical/sample: per cluster a full symmetric n_c x row_words(n_c) u32 bit-matrix, clusters concatenated in
+ *   order (bit j of row i set <=> the reference's neighbors(i) contains j).  matrix_offsets (n_clusters+1, in u32
+ *   words, out) may be NULL. */
+int tod_fill_adjacency(int32_t device, int32_t n_clusters, const int32_t *offsets, const float *query_pts,
+                       const float *train_pts, const float *pixels, const float *spans, float sensor_error,
+                       uint32_t *physical, uint32_t *sample, int64_t *matrix_offsets);
+
+/* K3 — one RANSAC iteration body for a batch of hypotheses of ONE cluster, HOST buffers:
+ * computeModelCoefficients (sac_model_registration_graph.h:271-288 -> :304-347) + the candidate/inlier part of
+ * selectWithinDistance (:171-200), i.e. the PRE-gate inlier count.
+ *   physical: n x row_words(n) bit-matrix; valid: row_words(n) bit-vector of still-valid correspondences;
+ *   triples: H x 3 sample indices; threshold: the RANSAC distance threshold, +inf (or >= 1e150) reproduces the
+ *   reference's never-set DBL_MAX (sac.h:70).
+ *   counts: H (|candidates passing| incl. the 3 samples).  R: H x 9, T: H x 3 (query -> training frame), may be NULL. */
+int tod_score_hypotheses(int32_t device, int32_t n, const float *query_pts, const float *train_pts,
+                         const uint32_t *physical, const uint32_t *valid, int32_t n_hyp, const uint32_t *triples,
+                         double threshold, int32_t *counts, float *R, float *T);
+
+/* ================================================================================================================
+ * GuessGenerator  (GuessGenerator.cpp)
+ * ============================================================================================================== */
+
+typedef struct tod_guess tod_guess;
+
+typedef struct tod_guess_params {
+  uint32_t min_inliers;          /* default 15 (GuessGenerator.cpp:74) */
+  uint32_t n_ransac_iterations;  /* default 1000 (:75-76) */
+  float sensor_error;            /* default 0.01 (:77) */
+  int32_t device;
+  double ransac_threshold;       /* +inf = reference-faithful (sac.h:70, quirk Q3) */
+  uint64_t seed;                 /* sampler stream seed; stream is re-seeded per (object, round), see DESIGN.md */
+} tod_guess_params;
+
+void tod_guess_default_params(tod_guess_params *p);
+int tod_guess_create(const tod_guess_params *p, tod_guess **out);
+void tod_guess_destroy(tod_guess *g);
+
+/* process() (GuessGenerator.cpp:127-250) with HOST buffers.
+ *   keypoints: n_kp; cloud: H x W x 3 f32 ("points3d"), NaN where invalid;
+ *   matches/counts/points3d: outputs of tod_matcher_knn for the same n_kp queries (row stride k);
+ *   spans: per object index (n_objects).  poses: capacity max_poses; *n_poses = number produced (in the
+ *   reference's emission order: ascending object index, then RANSAC round).
+ *   inlier_keypoints (optional, may be NULL): concatenated sorted inlier keypoint indices of each pose, capacity
+ *   max_inlier_total; pose p owns n_inliers entries in order. */
+int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp, const float *cloud, int32_t height,
+                      int32_t width, const tod_match *matches, const int32_t *counts, int32_t k,
+                      const float *points3d, const float *spans, int32_t n_objects, tod_pose *poses,
+                      int32_t max_poses, int32_t *n_poses, int32_t *inlier_keypoints, int32_t max_inlier_total);
+
+/* Sampler stream used by tod_guess_process (public so a test harness can drive the reference's rand() with the
+ * same numbers): state = tod_rng_seed(seed, object_index, round); tod_rng_next(&state) in [0, 2^31). */
+uint64_t tod_rng_seed(uint64_t seed, uint32_t object_index, uint32_t round);
+int32_t tod_rng_next(uint64_t *state);
+
+/* Device time (ms) spent in K2 / K3 kernels and number of K3 hypotheses scored during the last process call. */
+void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_t *n_hypotheses, int32_t *n_rounds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOD_B200_H_ */

@@ -1,0 +1,81 @@
+"""CPU: the C-ABI library loads and exports every symbol include/tod_b200.h declares; host-only entry points work."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from tod_b200 import capi
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "tod_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tod_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert header_functions() == sorted(n for n, _, _ in capi.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", capi.LIB_PATH], text=True)
+    exported = set(l.split()[-1] for l in out.splitlines() if " T " in l)
+    missing = [f for f in header_functions() if f not in exported]
+    assert not missing, missing
+    for f in header_functions():
+        assert getattr(lib, f) is not None
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_host_only_entry_points(lib):
+    assert lib.tod_abi_version() == 1
+    assert isinstance(lib.tod_last_error(), bytes)
+    p = capi.MatcherParams()
+    lib.tod_matcher_default_params(ctypes.byref(p))
+    assert (p.k, p.radius, p.shard_count) == (5, 0, 1)
+    # conf/detection.ork `search:` subtree as ORK core would serialise it
+    js = b'{"type": "LSH", "module": "ecto_opencv.features2d", "key_size": 16, "multi_probe_level": 1, ' \
+         b'"n_tables": 10, "radius": 35, "ratio": 0.8}'
+    assert lib.tod_matcher_params_from_json(js, ctypes.byref(p)) == capi.TOD_OK
+    assert (p.radius, p.search_type, p.k) == (35, capi.TOD_SEARCH_LSH, 5)
+    # unknown type: the reference does a bare `throw;` (DescriptorMatcher.cpp:182-186); here a status code
+    assert lib.tod_matcher_params_from_json(b'{"type": "KDTREE", "radius": 1, "ratio": 0}', ctypes.byref(p)) \
+        == capi.TOD_ERR_INVALID
+    assert b"KDTREE" in lib.tod_last_error()
+    assert lib.tod_matcher_params_from_json(b'{not json', ctypes.byref(p)) == capi.TOD_ERR_PARSE
+    g = capi.GuessParams()
+    lib.tod_guess_default_params(ctypes.byref(g))
+    assert (g.min_inliers, g.n_ransac_iterations) == (15, 1000) and abs(g.sensor_error - 0.01) < 1e-9
+    assert lib.tod_adjacency_row_words(1) == 4 and lib.tod_adjacency_row_words(129) == 8
+    assert lib.tod_adjacency_row_words(0) == 0
+
+
+def test_rng_stream_matches_oracle_restatement(lib):
+    from oracle import geometry as og
+    for seed, o, r in ((0, 0, 0), (12345, 7, 3), (2 ** 63 + 5, 99, 12)):
+        s = lib.tod_rng_seed(seed, o, r)
+        assert s == og.rng_seed(seed, o, r)
+        st = ctypes.c_uint64(s)
+        rr = og.Rng(s)
+        for _ in range(50):
+            assert lib.tod_rng_next(ctypes.byref(st)) == rr.rand()
+
+
+def test_no_gpu_means_loud_failure(lib):
+    """Without a usable B200 the compute entry points must fail with TOD_ERR_CUDA, never fall back to the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = capi.MatcherParams()
+    lib.tod_matcher_default_params(ctypes.byref(p))
+    h = ctypes.c_void_p()
+    assert lib.tod_matcher_create(ctypes.byref(p), ctypes.byref(h)) == capi.TOD_ERR_CUDA
+    assert b"no CPU fallback" in lib.tod_last_error()

@@ -1,0 +1,130 @@
+"""GPU: K1 (exact k-NN Hamming) through the C-ABI, bit-exact against the cv2 golden vectors and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import assert_matches_equal, golden_names, load_golden
+from oracle import hamming_knn as hk
+from tod_b200 import DescriptorMatcher, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def run_matcher(query, descs, points, k, radius, **kw):
+    m = DescriptorMatcher(k=k, radius=radius, **kw)
+    for i, (d, p) in enumerate(zip(descs, points)):
+        m.add_object("obj%d" % i, d, p)
+    m.train()
+    out = m.process(query)
+    out["kernel"] = m.last_kernel
+    out["span_idx"] = m.spans_by_index
+    m.close()
+    return out
+
+
+def check_against_oracle(query, descs, points, k, radius):
+    out = run_matcher(query, descs, points, k, radius)
+    em, ec = hk.knn_c(query, descs, k, radius)
+    assert_matches_equal(out["matches"], out["counts"], em["trainIdx"], em["imgIdx"], em["distance"], ec)
+    e3 = hk.gather_points3d(em, ec, points)
+    mask = np.arange(k)[None, :] < ec[:, None]
+    assert (out["matches_3d"][mask] == e3[mask]).all()
+    for i, p in enumerate(points):
+        assert out["span_idx"][i] == hk.object_span(p)
+    return out
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cv2_golden_vectors(name):
+    g, objs = load_golden(name)
+    pts = [np.zeros((o.shape[0], 3), np.float32) for o in objs]
+    out = run_matcher(g["query"], objs, pts, int(g["k"]), int(g["radius"]))
+    assert_matches_equal(out["matches"], out["counts"], g["trainIdx"], g["imgIdx"], g["distance"], g["counts"])
+    assert out["kernel"] in ("popc", "mma")
+
+
+@pytest.mark.parametrize("nq", [1, 31, 255, 256, 257, 513, 1025, 2000])
+def test_ragged_query_counts(nq):
+    descs, points = synth.make_db(3, [700, 1300, 555], seed=11)
+    q, _, _ = synth.make_queries(descs, nq, seed=nq)
+    check_against_oracle(q, descs, points, 5, 0)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_every_k(k):
+    descs, points = synth.make_db(4, 2500, seed=21)
+    q, _, _ = synth.make_queries(descs, 300, seed=22)
+    check_against_oracle(q, descs, points, k, 0)
+
+
+def test_tie_heavy_descriptors():
+    rng = np.random.default_rng(3)
+    descs = [np.zeros((n, 32), np.uint8) for n in (3000, 2000, 4100)]
+    for d in descs:
+        d[:, 5] = rng.integers(0, 8, d.shape[0])       # only 3 significant bits: thousands of exact ties
+    points = [rng.random((d.shape[0], 3)).astype(np.float32) for d in descs]
+    q = np.zeros((200, 32), np.uint8)
+    q[:, 5] = rng.integers(0, 8, 200)
+    check_against_oracle(q, descs, points, 5, 0)
+    check_against_oracle(q, descs, points, 5, 1)
+
+
+def test_config_c2_shape_k2():
+    """BASELINE configs[1]: 10-object DB (50k descriptors), 1k query keypoints, k=2."""
+    descs, points = synth.make_db(10, 5000, seed=synth.BASE_SEED + 1)
+    q, _, _ = synth.make_queries(descs, 1000, seed=synth.BASE_SEED + 101)
+    check_against_oracle(q, descs, points, 2, 0)
+
+
+def test_radius_cut_like_detection_ork():
+    descs, points = synth.make_db(10, 5000, seed=31)
+    q, src_obj, src_row = synth.make_queries(descs, 1000, seed=32)
+    out = check_against_oracle(q, descs, points, 5, 35)
+    true = src_obj >= 0
+    assert (out["counts"][true] >= 1).mean() > 0.99      # 4% flips ~ 10 bits < radius 35
+    assert (out["counts"][~true] == 0).all()             # random clutter never gets within 35 bits
+    hit = out["matches"][true][:, 0]
+    assert (hit["imgIdx"] == src_obj[true]).mean() > 0.99
+
+
+def test_config_c3_full_size_2k_by_1m():
+    """north_star size: 2k keypoints x 1M descriptors (100 objects x 10k), k=2 — bit-exact against the C oracle on a
+    query subset, plus size-independent properties on all queries."""
+    descs, points = synth.make_db(100, 10000, seed=synth.BASE_SEED + 2)
+    q, src_obj, src_row = synth.make_queries(descs, 2000, seed=synth.BASE_SEED + 102)
+    out = run_matcher(q, descs, points, 2, 0)
+    m, c = out["matches"], out["counts"]
+    assert (c == 2).all()
+    assert (m["distance"][:, 0] <= m["distance"][:, 1]).all()            # sortedness
+    true = src_obj >= 0                                                  # planted rows are found as the best match
+    assert (m["imgIdx"][true, 0] == src_obj[true]).mean() > 0.999
+    assert (m["trainIdx"][true, 0] == src_row[true]).mean() > 0.999
+    sub = np.arange(0, 2000, 8)
+    em, ec = hk.knn_c(q[sub], descs, 2, 0)
+    for f in ("trainIdx", "imgIdx", "distance"):
+        assert (m[f][sub] == em[f]).all()
+    # idempotence: distances recomputed from the returned indices
+    db, off = hk.concat_objects(descs)
+    g = off[m["imgIdx"]] + m["trainIdx"]
+    d = np.bitwise_count(q.view(np.uint64)[:, None, :] ^ db.view(np.uint64)[g]).sum(axis=2)
+    assert (d == m["distance"]).all()
+
+
+def test_empty_and_error_paths():
+    from tod_b200 import capi
+    m = DescriptorMatcher(k=5)
+    with pytest.raises(capi.TodError) as e:
+        m.process(np.zeros((4, 32), np.uint8))
+    assert e.value.code == capi.TOD_ERR_STATE                            # knn before train
+    m.train()                                                            # empty DB
+    out = m.process(np.zeros((4, 32), np.uint8))
+    assert (out["counts"] == 0).all()
+    descs, points = synth.make_db(1, 3, seed=1)                          # DB smaller than k
+    m.add_object("tiny", descs[0], points[0])
+    m.train()
+    out = m.process(np.zeros((2, 32), np.uint8))
+    assert (out["counts"] == 3).all()
+    out = m.process(np.zeros((0, 32), np.uint8))                         # no queries
+    assert out["matches"].shape == (0, 5)
+    with pytest.raises(capi.TodError):
+        DescriptorMatcher(k=9)
+    m.close()

@@ -1,0 +1,8 @@
+"""tod_b200 — B200-native (sm_100a) implementation of TOD's detection hot path: ORB descriptor k-NN Hamming matching
+against the trained object DB + geometric guess generation, behind the reference's DescriptorMatcher /
+GuessGenerator cell surface.  All compute lives in libtod_b200.so (hand-written CUDA, C-ABI in include/tod_b200.h);
+this package is the Python binding.  There is no CPU fallback."""
+from . import capi  # noqa: F401
+from .cells import DescriptorMatcher, GuessGenerator, fill_adjacency, score_hypotheses  # noqa: F401
+
+__all__ = ["capi", "DescriptorMatcher", "GuessGenerator", "fill_adjacency", "score_hypotheses"]

@@ -1,0 +1,234 @@
+"""Python view of the two cells of the hot path, named and parameterised like the reference's ecto cells
+(src/detection/DescriptorMatcher.cpp:131-152, src/detection/GuessGenerator.cpp:71-99).  Pure plumbing over the C-ABI
+(tod_b200/capi.py): numpy arrays in, numpy arrays out, all compute inside libtod_b200.so on the GPU."""
+import ctypes
+import json
+
+import numpy as np
+
+from . import capi
+
+
+class DescriptorMatcher:
+    """Mirror of tod::DescriptorMatcher.
+
+    params: search_json_params (str, like conf/detection.ork's `search:` subtree serialised to JSON), or explicit
+            k / radius.  inputs: descriptors (nq x 32 u8).  outputs: matches, matches_3d, object_ids, spans.
+    """
+
+    def __init__(self, search_json_params=None, k=None, radius=None, device=0, shard_rank=0, shard_count=1,
+                 kernel=capi.TOD_KERNEL_AUTO):
+        lib = capi.load()
+        p = capi.MatcherParams()
+        lib.tod_matcher_default_params(ctypes.byref(p))
+        if search_json_params is not None:
+            if not isinstance(search_json_params, str):
+                search_json_params = json.dumps(search_json_params)
+            capi.check(lib.tod_matcher_params_from_json(search_json_params.encode(), ctypes.byref(p)))
+        if k is not None:
+            p.k = int(k)
+        if radius is not None:
+            p.radius = int(radius)
+        p.device, p.shard_rank, p.shard_count, p.kernel = int(device), int(shard_rank), int(shard_count), int(kernel)
+        self.params = p
+        self._h = ctypes.c_void_p()
+        capi.check(lib.tod_matcher_create(ctypes.byref(p), ctypes.byref(self._h)))
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tod_matcher_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def k(self):
+        return int(self.params.k)
+
+    # -- parameter_callback -------------------------------------------------------------------------------------
+    def add_object(self, object_id, descriptors, points):
+        d = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        if d.shape[0] != p.shape[0]:
+            raise ValueError("descriptors and points disagree: %d vs %d" % (d.shape[0], p.shape[0]))
+        capi.check(self._lib.tod_matcher_add_object(self._h, str(object_id).encode(), capi._ptr(d), capi._ptr(p),
+                                                    d.shape[0]))
+
+    def clear(self):
+        capi.check(self._lib.tod_matcher_clear(self._h))
+
+    def train(self):
+        capi.check(self._lib.tod_matcher_train(self._h))
+
+    @property
+    def object_ids(self):
+        return [self._lib.tod_matcher_object_id(self._h, i).decode()
+                for i in range(self._lib.tod_matcher_num_objects(self._h))]
+
+    @property
+    def spans(self):
+        """map object_id -> span, like outputs["spans"]."""
+        return {oid: float(self._lib.tod_matcher_span(self._h, i)) for i, oid in enumerate(self.object_ids)}
+
+    @property
+    def spans_by_index(self):
+        return np.array([self._lib.tod_matcher_span(self._h, i)
+                         for i in range(self._lib.tod_matcher_num_objects(self._h))], np.float32)
+
+    @property
+    def num_descriptors(self):
+        return int(self._lib.tod_matcher_num_descriptors(self._h))
+
+    @property
+    def shard_rows(self):
+        return int(self._lib.tod_matcher_shard_rows(self._h))
+
+    # -- process ------------------------------------------------------------------------------------------------
+    def process(self, descriptors, out=None):
+        """Host-buffer call.  Returns dict(matches[nq,k] MATCH_DTYPE, counts[nq], matches_3d[nq,k,3], object_ids,
+        spans).  `out` may hold preallocated (pinned) arrays under the same keys."""
+        q = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        nq, k = q.shape[0], self.k
+        if out is None:
+            out = {}
+        m = out.get("matches")
+        if m is None:
+            m = np.empty((nq, k), capi.MATCH_DTYPE)
+        c = out.get("counts")
+        if c is None:
+            c = np.empty(nq, np.int32)
+        p3 = out.get("matches_3d")
+        if p3 is None:
+            p3 = np.empty((nq, k, 3), np.float32)
+        capi.check(self._lib.tod_matcher_knn(self._h, capi._ptr(q), nq, capi._ptr(m), capi._ptr(c), capi._ptr(p3)))
+        return {"matches": m, "counts": c, "matches_3d": p3, "object_ids": self.object_ids, "spans": self.spans}
+
+    def knn_keys_device(self, d_query_ptr, nq, d_keys_ptr, stream=None):
+        capi.check(self._lib.tod_matcher_knn_keys_device(self._h, ctypes.c_void_p(d_query_ptr), int(nq),
+                                                         ctypes.c_void_p(d_keys_ptr),
+                                                         ctypes.c_void_p(stream) if stream else None))
+
+    def merge_device(self, d_keys_all_ptr, n_src, nq, d_matches_ptr, d_counts_ptr, d_points3d_ptr, stream=None):
+        capi.check(self._lib.tod_matcher_merge_device(self._h, ctypes.c_void_p(d_keys_all_ptr), int(n_src), int(nq),
+                                                      ctypes.c_void_p(d_matches_ptr), ctypes.c_void_p(d_counts_ptr),
+                                                      ctypes.c_void_p(d_points3d_ptr) if d_points3d_ptr else None,
+                                                      ctypes.c_void_p(stream) if stream else None))
+
+    @property
+    def last_k1_ms(self):
+        return float(self._lib.tod_matcher_last_k1_ms(self._h))
+
+    @property
+    def last_kernel(self):
+        return self._lib.tod_matcher_last_kernel(self._h).decode()
+
+
+def fill_adjacency(offsets, query_pts, train_pts, pixels, spans, sensor_error, device=0):
+    """K2 for a batch of clusters (AdjacencyRansac::FillAdjacency, adjacency_ransac.cpp:127-172).
+    Returns (physical, sample, matrix_offsets): flat u32 arrays holding one n_c x row_words(n_c) bit-matrix per cluster."""
+    lib = capi.load()
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    nc = offsets.shape[0] - 1
+    q = np.ascontiguousarray(query_pts, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(train_pts, np.float32).reshape(-1, 3)
+    px = np.ascontiguousarray(pixels, np.float32).reshape(-1, 2)
+    sp = np.ascontiguousarray(spans, np.float32).reshape(-1)
+    sizes = np.diff(offsets).astype(np.int64)
+    words = np.array([capi.adjacency_row_words(int(n)) for n in sizes], np.int64)
+    total = int((sizes * words).sum())
+    physical = np.zeros(max(total, 1), np.uint32)
+    sample = np.zeros(max(total, 1), np.uint32)
+    mo = np.zeros(nc + 1, np.int64)
+    capi.check(lib.tod_fill_adjacency(int(device), nc, capi._ptr(offsets), capi._ptr(q), capi._ptr(t), capi._ptr(px),
+                                      capi._ptr(sp), ctypes.c_float(sensor_error), capi._ptr(physical),
+                                      capi._ptr(sample), capi._ptr(mo)))
+    return physical[:total], sample[:total], mo
+
+
+def score_hypotheses(query_pts, train_pts, physical, valid, triples, threshold=float("inf"), device=0,
+                     want_pose=True):
+    """K3 for one cluster.  Returns (counts[H], R[H,9] or None, T[H,3] or None)."""
+    lib = capi.load()
+    q = np.ascontiguousarray(query_pts, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(train_pts, np.float32).reshape(-1, 3)
+    n = q.shape[0]
+    P = np.ascontiguousarray(physical, np.uint32)
+    V = np.ascontiguousarray(valid, np.uint32)
+    tr = np.ascontiguousarray(triples, np.uint32).reshape(-1, 3)
+    H = tr.shape[0]
+    counts = np.zeros(H, np.int32)
+    R = np.zeros((H, 9), np.float32) if want_pose else None
+    T = np.zeros((H, 3), np.float32) if want_pose else None
+    capi.check(lib.tod_score_hypotheses(int(device), n, capi._ptr(q), capi._ptr(t), capi._ptr(P), capi._ptr(V), H,
+                                        capi._ptr(tr), ctypes.c_double(threshold), capi._ptr(counts), capi._ptr(R),
+                                        capi._ptr(T)))
+    return counts, R, T
+
+
+class GuessGenerator:
+    """Mirror of tod::GuessGenerator: params min_inliers, n_ransac_iterations, sensor_error (GuessGenerator.cpp:74-80);
+    inputs points3d, keypoints, matches, matches_3d, spans, object_ids; outputs pose_results, Rs, Ts."""
+
+    def __init__(self, min_inliers=15, n_ransac_iterations=1000, sensor_error=0.01, ransac_threshold=float("inf"),
+                 seed=0, device=0):
+        lib = capi.load()
+        p = capi.GuessParams()
+        lib.tod_guess_default_params(ctypes.byref(p))
+        p.min_inliers, p.n_ransac_iterations = int(min_inliers), int(n_ransac_iterations)
+        p.sensor_error, p.ransac_threshold = float(sensor_error), float(ransac_threshold)
+        p.seed, p.device = int(seed), int(device)
+        self.params = p
+        self._h = ctypes.c_void_p()
+        capi.check(lib.tod_guess_create(ctypes.byref(p), ctypes.byref(self._h)))
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tod_guess_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def process(self, keypoints, points3d, matches, counts, matches_3d, spans_by_index, max_poses=256):
+        """keypoints: KEYPOINT_DTYPE[n] or (n,2) float pixel coords; points3d: H x W x 3 f32 cloud.
+        Returns dict(pose_results POSE_DTYPE[n_poses], Rs, Ts, inliers list of arrays)."""
+        if keypoints.dtype != capi.KEYPOINT_DTYPE:
+            xy = np.asarray(keypoints, np.float32).reshape(-1, 2)
+            kp = np.zeros(xy.shape[0], capi.KEYPOINT_DTYPE)
+            kp["x"], kp["y"] = xy[:, 0], xy[:, 1]
+        else:
+            kp = np.ascontiguousarray(keypoints)
+        cloud = np.ascontiguousarray(points3d, np.float32)
+        H, W = cloud.shape[0], cloud.shape[1]
+        m = np.ascontiguousarray(matches)
+        assert m.dtype == capi.MATCH_DTYPE
+        k = m.shape[1]
+        c = np.ascontiguousarray(counts, np.int32)
+        p3 = np.ascontiguousarray(matches_3d, np.float32)
+        sp = np.ascontiguousarray(spans_by_index, np.float32)
+        poses = np.zeros(max_poses, capi.POSE_DTYPE)
+        n_poses = ctypes.c_int32(0)
+        cap = max(1, kp.shape[0] * 2)
+        inl = np.zeros(cap, np.int32)
+        capi.check(self._lib.tod_guess_process(self._h, capi._ptr(kp), kp.shape[0], capi._ptr(cloud), H, W,
+                                               capi._ptr(m), capi._ptr(c), k, capi._ptr(p3), capi._ptr(sp),
+                                               sp.shape[0], capi._ptr(poses), max_poses, ctypes.byref(n_poses),
+                                               capi._ptr(inl), cap))
+        poses = poses[:n_poses.value]
+        inliers, o = [], 0
+        for p in poses:
+            inliers.append(inl[o:o + int(p["n_inliers"])].copy())
+            o += int(p["n_inliers"])
+        return {"pose_results": poses, "Rs": poses["R"].reshape(-1, 3, 3).copy(), "Ts": poses["T"].copy(),
+                "inliers": inliers}
+
+    def last_stats(self):
+        k2, k3 = ctypes.c_float(), ctypes.c_float()
+        nh, nr = ctypes.c_int64(), ctypes.c_int32()
+        self._lib.tod_guess_last_stats(self._h, ctypes.byref(k2), ctypes.byref(k3), ctypes.byref(nh), ctypes.byref(nr))
+        return {"k2_ms": k2.value, "k3_ms": k3.value, "n_hypotheses": nh.value, "n_rounds": nr.value}

@@ -1,0 +1,149 @@
+// Stage-level C-ABI entry points of the geometry half (include/tod_b200.h: tod_fill_adjacency,
+// tod_score_hypotheses): host buffers in, host buffers out, compute in K2 / K3 on the GPU.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "tod_internal.h"
+
+using tod::DeviceBuffer;
+using tod::fail;
+
+namespace {
+
+struct Scratch {  // freed on scope exit
+  std::vector<DeviceBuffer *> bufs;
+  ~Scratch() {
+    for (DeviceBuffer *b : bufs) b->release();
+  }
+  void own(DeviceBuffer &b) { bufs.push_back(&b); }
+};
+
+int check_device(int device) {
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return fail(TOD_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  TOD_REQUIRE(device >= 0 && device < n_dev, "device %d out of range (%d devices)", device, n_dev);
+  TOD_CUDA(cudaSetDevice(device));
+  return TOD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t tod_adjacency_row_words(int32_t n) { return n <= 0 ? 0 : tod::adjacency_row_words(n); }
+
+int tod_fill_adjacency(int32_t device, int32_t n_clusters, const int32_t *offsets, const float *query_pts,
+                       const float *train_pts, const float *pixels, const float *spans, float sensor_error,
+                       uint32_t *physical, uint32_t *sample, int64_t *matrix_offsets) {
+  TOD_REQUIRE(n_clusters >= 0 && offsets && spans, "bad cluster table");
+  if (n_clusters == 0) return TOD_OK;
+  const int64_t N = offsets[n_clusters];
+  TOD_REQUIRE(offsets[0] == 0 && N >= 0, "offsets must start at 0 and be non-decreasing");
+  TOD_REQUIRE(N == 0 || (query_pts && train_pts && pixels && physical && sample), "null point/matrix buffer");
+  std::vector<int64_t> mo(size_t(n_clusters) + 1, 0);
+  int max_cluster = 0;
+  for (int c = 0; c < n_clusters; ++c) {
+    const int n = offsets[c + 1] - offsets[c];
+    TOD_REQUIRE(n >= 0, "offsets must be non-decreasing");
+    max_cluster = std::max(max_cluster, n);
+    mo[size_t(c) + 1] = mo[size_t(c)] + int64_t(n) * tod_adjacency_row_words(n);
+  }
+  if (matrix_offsets) std::memcpy(matrix_offsets, mo.data(), mo.size() * sizeof(int64_t));
+  if (N == 0 || mo.back() == 0) return TOD_OK;
+  if (int rc = check_device(device)) return rc;
+
+  DeviceBuffer d_off, d_mo, d_q, d_t, d_px, d_sp, d_P, d_S;
+  Scratch scratch;
+  for (DeviceBuffer *b : {&d_off, &d_mo, &d_q, &d_t, &d_px, &d_sp, &d_P, &d_S}) scratch.own(*b);
+  const size_t mat_bytes = size_t(mo.back()) * sizeof(uint32_t);
+  TOD_CUDA(d_off.reserve((size_t(n_clusters) + 1) * sizeof(int32_t)));
+  TOD_CUDA(d_mo.reserve(mo.size() * sizeof(int64_t)));
+  TOD_CUDA(d_q.reserve(size_t(N) * 12));
+  TOD_CUDA(d_t.reserve(size_t(N) * 12));
+  TOD_CUDA(d_px.reserve(size_t(N) * 8));
+  TOD_CUDA(d_sp.reserve(size_t(n_clusters) * 4));
+  TOD_CUDA(d_P.reserve(mat_bytes));
+  TOD_CUDA(d_S.reserve(mat_bytes));
+  cudaStream_t st = nullptr;
+  TOD_CUDA(cudaMemcpyAsync(d_off.ptr, offsets, (size_t(n_clusters) + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_mo.ptr, mo.data(), mo.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_q.ptr, query_pts, size_t(N) * 12, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_t.ptr, train_pts, size_t(N) * 12, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_px.ptr, pixels, size_t(N) * 8, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_sp.ptr, spans, size_t(n_clusters) * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(tod::launch_fill_adjacency(n_clusters, d_off.as<int32_t>(), d_mo.as<int64_t>(), d_q.as<float>(),
+                                      d_t.as<float>(), d_px.as<float>(), d_sp.as<float>(), sensor_error,
+                                      d_P.as<uint32_t>(), d_S.as<uint32_t>(), max_cluster, st));
+  TOD_CUDA(cudaMemcpyAsync(physical, d_P.ptr, mat_bytes, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaMemcpyAsync(sample, d_S.ptr, mat_bytes, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  return TOD_OK;
+}
+
+int tod_score_hypotheses(int32_t device, int32_t n, const float *query_pts, const float *train_pts,
+                         const uint32_t *physical, const uint32_t *valid, int32_t n_hyp, const uint32_t *triples,
+                         double threshold, int32_t *counts, float *R, float *T) {
+  TOD_REQUIRE(n >= 0 && n_hyp >= 0, "negative size");
+  if (n_hyp == 0) return TOD_OK;
+  TOD_REQUIRE(n >= 3 && query_pts && train_pts && physical && valid && triples && counts, "null/too-small input");
+  for (int64_t i = 0; i < int64_t(n_hyp) * 3; ++i)
+    TOD_REQUIRE(triples[i] < uint32_t(n), "sample index %u out of range (n=%d)", triples[i], n);
+  if (int rc = check_device(device)) return rc;
+  const int W = tod::adjacency_row_words(n);
+
+  // finite mask (see k3_score.cu): correspondence i can only pass `distSq < inf` if all its coordinates are finite
+  std::vector<uint32_t> finite(size_t(W), 0u);
+  for (int i = 0; i < n; ++i) {
+    bool ok = true;
+    for (int d = 0; d < 3; ++d) ok = ok && std::isfinite(query_pts[size_t(i) * 3 + d]) && std::isfinite(train_pts[size_t(i) * 3 + d]);
+    if (ok) finite[size_t(i) >> 5] |= 1u << (i & 31);
+  }
+  std::vector<uint32_t> hyps(size_t(n_hyp) * 4);
+  for (int h = 0; h < n_hyp; ++h) {
+    hyps[size_t(h) * 4 + 0] = triples[size_t(h) * 3 + 0];
+    hyps[size_t(h) * 4 + 1] = triples[size_t(h) * 3 + 1];
+    hyps[size_t(h) * 4 + 2] = triples[size_t(h) * 3 + 2];
+    hyps[size_t(h) * 4 + 3] = 0;
+  }
+  std::vector<unsigned char> desc(tod::k3_cluster_desc_size());
+  tod::k3_fill_cluster_desc(desc.data(), n, W, 0, 0, 0);
+
+  DeviceBuffer d_desc, d_q, d_t, d_P, d_V, d_F, d_h, d_c, d_R, d_T;
+  Scratch scratch;
+  for (DeviceBuffer *b : {&d_desc, &d_q, &d_t, &d_P, &d_V, &d_F, &d_h, &d_c, &d_R, &d_T}) scratch.own(*b);
+  const size_t mat_bytes = size_t(n) * W * sizeof(uint32_t);
+  TOD_CUDA(d_desc.reserve(desc.size()));
+  TOD_CUDA(d_q.reserve(size_t(n) * 12));
+  TOD_CUDA(d_t.reserve(size_t(n) * 12));
+  TOD_CUDA(d_P.reserve(mat_bytes));
+  TOD_CUDA(d_V.reserve(size_t(W) * 4));
+  TOD_CUDA(d_F.reserve(size_t(W) * 4));
+  TOD_CUDA(d_h.reserve(hyps.size() * 4));
+  TOD_CUDA(d_c.reserve(size_t(n_hyp) * 4));
+  if (R) TOD_CUDA(d_R.reserve(size_t(n_hyp) * 36));
+  if (T) TOD_CUDA(d_T.reserve(size_t(n_hyp) * 12));
+  cudaStream_t st = nullptr;
+  TOD_CUDA(cudaMemcpyAsync(d_desc.ptr, desc.data(), desc.size(), cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_q.ptr, query_pts, size_t(n) * 12, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_t.ptr, train_pts, size_t(n) * 12, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_P.ptr, physical, mat_bytes, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_V.ptr, valid, size_t(W) * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_F.ptr, finite.data(), size_t(W) * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(d_h.ptr, hyps.data(), hyps.size() * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(tod::launch_score_hypotheses_batched(d_desc.ptr, d_q.as<float>(), d_t.as<float>(), d_P.as<uint32_t>(),
+                                                d_V.as<uint32_t>(), d_F.as<uint32_t>(), n_hyp, d_h.as<uint32_t>(),
+                                                threshold, d_c.as<int32_t>(), R ? d_R.as<float>() : nullptr,
+                                                T ? d_T.as<float>() : nullptr, st));
+  TOD_CUDA(cudaMemcpyAsync(counts, d_c.ptr, size_t(n_hyp) * 4, cudaMemcpyDeviceToHost, st));
+  if (R) TOD_CUDA(cudaMemcpyAsync(R, d_R.ptr, size_t(n_hyp) * 36, cudaMemcpyDeviceToHost, st));
+  if (T) TOD_CUDA(cudaMemcpyAsync(T, d_T.ptr, size_t(n_hyp) * 12, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  return TOD_OK;
+}
+
+}  // extern "C"

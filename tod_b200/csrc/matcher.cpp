@@ -1,0 +1,276 @@
+// C-ABI of the DescriptorMatcher half of the hot path (include/tod_b200.h: tod_matcher_*).
+// Host logic mirrors src/detection/DescriptorMatcher.cpp of the reference: parameter_callback (:60-129) ->
+// add_object/train, configure (:154-188) -> params_from_json, process (:195-252) -> knn.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "json_min.h"
+#include "tod_internal.h"
+
+using tod::DeviceBuffer;
+using tod::fail;
+
+struct tod_matcher {
+  tod_matcher_params p{};
+  // host copy of the DB (concatenated in imgIdx order)
+  std::vector<std::string> ids;
+  std::vector<float> spans;
+  std::vector<uint32_t> offsets{0};  // n_objects + 1 global row offsets
+  std::vector<uint8_t> h_desc;
+  std::vector<float> h_pts;
+  bool trained = false;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int64_t shard_begin = 0, shard_rows = 0;
+  DeviceBuffer d_db, d_pts, d_offsets, d_query, d_partial, d_matches, d_counts, d_pts3d;
+  const char *last_kernel = "none";
+};
+
+namespace {
+
+int use_device(const tod_matcher *m) {
+  TOD_CUDA(cudaSetDevice(m->p.device));
+  return TOD_OK;
+}
+
+int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1Plan *plan_out) {
+  if (m->p.kernel == TOD_KERNEL_MMA) return fail(TOD_ERR_INVALID, "K1 tcgen05 formulation is not built in this version");
+  tod::K1Plan plan = tod::k1_popc_plan(nq, m->shard_rows, m->sm_count);
+  TOD_CUDA(m->d_partial.reserve(size_t(plan.n_chunks) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
+  TOD_CUDA(cudaEventRecord(m->ev0, st));
+  TOD_CUDA(tod::launch_k1_popc(plan, d_query, nq, m->d_db.ptr, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
+                               m->p.radius, m->d_partial.as<uint32_t>(), st));
+  TOD_CUDA(cudaEventRecord(m->ev1, st));
+  m->ev_valid = true;
+  m->last_kernel = "popc";
+  *plan_out = plan;
+  return TOD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void tod_matcher_default_params(tod_matcher_params *p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->k = 5;
+  p->radius = 0;
+  p->search_type = TOD_SEARCH_EXACT;
+  p->device = 0;
+  p->shard_rank = 0;
+  p->shard_count = 1;
+  p->kernel = TOD_KERNEL_AUTO;
+}
+
+int tod_matcher_params_from_json(const char *search_json_params, tod_matcher_params *p) {
+  TOD_REQUIRE(search_json_params && p, "null argument");
+  tod::json::Value v;
+  if (!tod::json::parse(search_json_params, v) || v.type != tod::json::Value::Object)
+    return fail(TOD_ERR_PARSE, "search_json_params is not a JSON object");
+  // radius_ and ratio_ are `unsigned int` members assigned from get_real() (DescriptorMatcher.cpp:170-171,257-259):
+  // the value is truncated toward zero; ratio 0.8 becomes 0 and the ratio block is empty anyway (:223-227).
+  if (v.has("radius")) {
+    const double r = v.at("radius").num;
+    TOD_REQUIRE(v.at("radius").type == tod::json::Value::Number && r >= 0 && r < 4294967296.0, "bad radius");
+    p->radius = static_cast<uint32_t>(r);
+  }
+  const tod::json::Value &type = v.at("type");
+  TOD_REQUIRE(type.type == tod::json::Value::String, "search type missing");
+  if (type.str == "LSH") {
+    p->search_type = TOD_SEARCH_LSH;  // n_tables / key_size / multi_probe_level are accepted and ignored: exact search
+  } else if (type.str == "BruteForce" || type.str == "exact" || type.str == "BruteForce-Hamming") {
+    p->search_type = TOD_SEARCH_EXACT;
+  } else {
+    return fail(TOD_ERR_INVALID, "Search not implemented for that type: %s", type.str.c_str());
+  }
+  return TOD_OK;
+}
+
+int tod_matcher_create(const tod_matcher_params *p, tod_matcher **out) {
+  TOD_REQUIRE(p && out, "null argument");
+  TOD_REQUIRE(p->k >= 1 && p->k <= TOD_MAX_K, "k must be in 1..%d (got %d)", TOD_MAX_K, p->k);
+  TOD_REQUIRE(p->shard_count >= 1 && p->shard_rank >= 0 && p->shard_rank < p->shard_count, "bad shard %d/%d",
+              p->shard_rank, p->shard_count);
+  TOD_REQUIRE(p->search_type == TOD_SEARCH_EXACT || p->search_type == TOD_SEARCH_LSH, "bad search_type");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return fail(TOD_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  TOD_REQUIRE(p->device >= 0 && p->device < n_dev, "device %d out of range (%d devices)", p->device, n_dev);
+  TOD_CUDA(cudaSetDevice(p->device));
+  int major = 0;
+  TOD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, p->device));
+  if (major != 10) return fail(TOD_ERR_CUDA, "device %d is sm_%dx; this library is built for sm_100a only", p->device, major);
+  tod_matcher *m = new tod_matcher();
+  m->p = *p;
+  TOD_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+  TOD_CUDA(cudaStreamCreate(&m->stream));
+  TOD_CUDA(cudaEventCreate(&m->ev0));
+  TOD_CUDA(cudaEventCreate(&m->ev1));
+  *out = m;
+  return TOD_OK;
+}
+
+void tod_matcher_destroy(tod_matcher *m) {
+  if (!m) return;
+  cudaSetDevice(m->p.device);
+  for (DeviceBuffer *b : {&m->d_db, &m->d_pts, &m->d_offsets, &m->d_query, &m->d_partial, &m->d_matches,
+                          &m->d_counts, &m->d_pts3d})
+    b->release();
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int tod_matcher_add_object(tod_matcher *m, const char *object_id, const uint8_t *descriptors, const float *points,
+                           int32_t n) {
+  TOD_REQUIRE(m && object_id, "null argument");
+  TOD_REQUIRE(n >= 0 && (n == 0 || (descriptors && points)), "bad descriptor/point buffers");
+  const int64_t total = int64_t(m->offsets.back()) + n;
+  if (total > tod::kMaxGlobalRows)
+    return fail(TOD_ERR_LIMIT, "DB would hold %lld descriptors; packed u32 keys address at most %lld rows",
+                (long long)total, (long long)tod::kMaxGlobalRows);
+  m->ids.emplace_back(object_id);
+  m->h_desc.insert(m->h_desc.end(), descriptors, descriptors + size_t(n) * 32);
+  m->h_pts.insert(m->h_pts.end(), points, points + size_t(n) * 3);
+  m->offsets.push_back(uint32_t(total));
+  // span of the object: DescriptorMatcher.cpp:106-121 (bounding-box diagonal, float arithmetic)
+  float min_x = std::numeric_limits<float>::max(), max_x = -std::numeric_limits<float>::max(), min_y = min_x,
+        max_y = max_x, min_z = min_x, max_z = max_x;
+  for (int32_t i = 0; i < n; ++i) {
+    const float *v = points + size_t(i) * 3;
+    min_x = std::min(min_x, v[0]); max_x = std::max(max_x, v[0]);
+    min_y = std::min(min_y, v[1]); max_y = std::max(max_y, v[1]);
+    min_z = std::min(min_z, v[2]); max_z = std::max(max_z, v[2]);
+  }
+  const float max_span_sq =
+      (max_x - min_x) * (max_x - min_x) + (max_y - min_y) * (max_y - min_y) + (max_z - min_z) * (max_z - min_z);
+  m->spans.push_back(std::sqrt(max_span_sq));
+  m->trained = false;
+  return TOD_OK;
+}
+
+int tod_matcher_clear(tod_matcher *m) {
+  TOD_REQUIRE(m, "null argument");
+  m->ids.clear();
+  m->spans.clear();
+  m->offsets.assign(1, 0u);
+  m->h_desc.clear();
+  m->h_pts.clear();
+  m->trained = false;
+  m->shard_begin = m->shard_rows = 0;
+  return TOD_OK;
+}
+
+int tod_matcher_train(tod_matcher *m) {
+  TOD_REQUIRE(m, "null argument");
+  if (int rc = use_device(m)) return rc;
+  const int64_t total = m->offsets.back();
+  const int64_t per = (total + m->p.shard_count - 1) / m->p.shard_count;
+  m->shard_begin = std::min<int64_t>(total, per * m->p.shard_rank);
+  m->shard_rows = std::min<int64_t>(total, m->shard_begin + per) - m->shard_begin;
+  TOD_CUDA(m->d_db.reserve(std::max<size_t>(size_t(m->shard_rows) * 32, 256)));
+  TOD_CUDA(m->d_pts.reserve(std::max<size_t>(size_t(total) * 3 * sizeof(float), 256)));
+  TOD_CUDA(m->d_offsets.reserve(m->offsets.size() * sizeof(uint32_t)));
+  if (m->shard_rows)
+    TOD_CUDA(cudaMemcpyAsync(m->d_db.ptr, m->h_desc.data() + size_t(m->shard_begin) * 32, size_t(m->shard_rows) * 32,
+                             cudaMemcpyHostToDevice, m->stream));
+  if (total)
+    TOD_CUDA(cudaMemcpyAsync(m->d_pts.ptr, m->h_pts.data(), size_t(total) * 3 * sizeof(float),
+                             cudaMemcpyHostToDevice, m->stream));
+  TOD_CUDA(cudaMemcpyAsync(m->d_offsets.ptr, m->offsets.data(), m->offsets.size() * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice, m->stream));
+  TOD_CUDA(cudaStreamSynchronize(m->stream));
+  m->trained = true;
+  return TOD_OK;
+}
+
+int32_t tod_matcher_num_objects(const tod_matcher *m) { return m ? int32_t(m->ids.size()) : 0; }
+int64_t tod_matcher_num_descriptors(const tod_matcher *m) { return m ? int64_t(m->offsets.back()) : 0; }
+int64_t tod_matcher_shard_rows(const tod_matcher *m) { return m ? m->shard_rows : 0; }
+const char *tod_matcher_object_id(const tod_matcher *m, int32_t i) {
+  return (m && i >= 0 && size_t(i) < m->ids.size()) ? m->ids[size_t(i)].c_str() : "";
+}
+float tod_matcher_span(const tod_matcher *m, int32_t i) {
+  return (m && i >= 0 && size_t(i) < m->spans.size()) ? m->spans[size_t(i)] : 0.f;
+}
+int32_t tod_matcher_k(const tod_matcher *m) { return m ? m->p.k : 0; }
+
+int tod_matcher_knn(tod_matcher *m, const uint8_t *descriptors, int32_t nq, tod_match *matches, int32_t *counts,
+                    float *points3d) {
+  TOD_REQUIRE(m && matches && counts, "null argument");
+  TOD_REQUIRE(nq >= 0 && (nq == 0 || descriptors), "bad query buffer");
+  if (!m->trained) return fail(TOD_ERR_STATE, "tod_matcher_knn called before tod_matcher_train");
+  if (m->p.shard_count != 1)
+    return fail(TOD_ERR_STATE, "tod_matcher_knn needs the whole DB on one GPU; use the *_device stages when sharded");
+  if (nq == 0) return TOD_OK;
+  if (int rc = use_device(m)) return rc;
+  const int k = m->p.k;
+  const size_t nk = size_t(nq) * k;
+  TOD_CUDA(m->d_query.reserve(size_t(nq) * 32));
+  TOD_CUDA(m->d_matches.reserve(nk * sizeof(tod_match)));
+  TOD_CUDA(m->d_counts.reserve(size_t(nq) * sizeof(int32_t)));
+  TOD_CUDA(m->d_pts3d.reserve(nk * 3 * sizeof(float)));
+  TOD_CUDA(cudaMemcpyAsync(m->d_query.ptr, descriptors, size_t(nq) * 32, cudaMemcpyHostToDevice, m->stream));
+  tod::K1Plan plan;
+  if (int rc = run_k1(m, m->d_query.ptr, nq, m->stream, &plan)) return rc;
+  TOD_CUDA(tod::launch_finalize_matches(m->d_partial.as<uint32_t>(), plan.n_chunks, nq, k, m->p.radius,
+                                        m->d_offsets.as<uint32_t>(), int(m->ids.size()), m->d_pts.as<float>(),
+                                        m->d_matches.as<tod_match>(), m->d_counts.as<int32_t>(),
+                                        points3d ? m->d_pts3d.as<float>() : nullptr, m->stream));
+  TOD_CUDA(cudaMemcpyAsync(matches, m->d_matches.ptr, nk * sizeof(tod_match), cudaMemcpyDeviceToHost, m->stream));
+  TOD_CUDA(cudaMemcpyAsync(counts, m->d_counts.ptr, size_t(nq) * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+  if (points3d)
+    TOD_CUDA(cudaMemcpyAsync(points3d, m->d_pts3d.ptr, nk * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  TOD_CUDA(cudaStreamSynchronize(m->stream));
+  return TOD_OK;
+}
+
+int tod_matcher_knn_keys_device(tod_matcher *m, const void *d_descriptors, int32_t nq, uint32_t *d_keys,
+                                void *stream) {
+  TOD_REQUIRE(m && d_keys, "null argument");
+  TOD_REQUIRE(nq >= 0 && (nq == 0 || d_descriptors), "bad query buffer");
+  if (!m->trained) return fail(TOD_ERR_STATE, "tod_matcher_knn_keys_device called before tod_matcher_train");
+  if (nq == 0) return TOD_OK;
+  if (int rc = use_device(m)) return rc;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : m->stream;
+  tod::K1Plan plan;
+  if (int rc = run_k1(m, d_descriptors, nq, st, &plan)) return rc;
+  TOD_CUDA(tod::launch_reduce_keys(m->d_partial.as<uint32_t>(), plan.n_chunks, nq, m->p.k, d_keys, st));
+  return TOD_OK;
+}
+
+int tod_matcher_merge_device(tod_matcher *m, const uint32_t *d_keys_all, int32_t n_src, int32_t nq,
+                             tod_match *d_matches, int32_t *d_counts, float *d_points3d, void *stream) {
+  TOD_REQUIRE(m && d_keys_all && d_matches && d_counts, "null argument");
+  TOD_REQUIRE(n_src >= 1 && nq >= 0, "bad sizes");
+  if (!m->trained) return fail(TOD_ERR_STATE, "tod_matcher_merge_device called before tod_matcher_train");
+  if (nq == 0) return TOD_OK;
+  if (int rc = use_device(m)) return rc;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : m->stream;
+  TOD_CUDA(tod::launch_finalize_matches(d_keys_all, n_src, nq, m->p.k, m->p.radius, m->d_offsets.as<uint32_t>(),
+                                        int(m->ids.size()), m->d_pts.as<float>(), d_matches, d_counts, d_points3d,
+                                        st));
+  return TOD_OK;
+}
+
+float tod_matcher_last_k1_ms(const tod_matcher *m) {
+  if (!m || !m->ev_valid) return -1.f;
+  if (cudaEventSynchronize(m->ev1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+const char *tod_matcher_last_kernel(const tod_matcher *m) { return m ? m->last_kernel : "none"; }
+
+}  // extern "C"

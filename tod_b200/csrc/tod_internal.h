@@ -1,0 +1,112 @@
+// Internal helpers shared by the C-ABI translation units of libtod_b200.so (not installed).
+#ifndef TOD_INTERNAL_H_
+#define TOD_INTERNAL_H_
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "tod_b200.h"
+
+namespace tod {
+
+// thread-local error message behind tod_last_error()
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define TOD_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return ::tod::fail(TOD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                                      \
+  } while (0)
+
+#define TOD_REQUIRE(cond, ...)                                  \
+  do {                                                          \
+    if (!(cond)) return ::tod::fail(TOD_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// Growable device buffer (cudaMalloc'd, never shrinks).
+struct DeviceBuffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    size_t want = n + n / 4;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T *as() const { return static_cast<T *>(ptr); }
+};
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------------------------------------------
+
+// Packed key of one candidate: distance (9 bits) << 23 | global DB row (23 bits).  min() over keys is exactly the
+// (distance, imgIdx, trainIdx) order of cv::BFMatcher because objects are concatenated in imgIdx order.
+constexpr int kKeyRowBits = 23;
+constexpr uint32_t kKeyRowMask = (1u << kKeyRowBits) - 1;
+constexpr uint32_t kKeyEmpty = 0xFFFFFFFFu;
+constexpr int64_t kMaxGlobalRows = int64_t(1) << kKeyRowBits;
+
+struct K1Plan {
+  int q_per_thread;    // 1, 2 or 4
+  int q_tile;          // queries per CTA = 256 * q_per_thread
+  int n_qtiles;
+  int rows_per_chunk;  // multiple of the smem tile
+  int n_chunks;
+};
+K1Plan k1_popc_plan(int nq, int64_t shard_rows, int sm_count);
+
+// K1 (SIMT popc formulation).  partial: n_chunks x nq x k keys.
+cudaError_t launch_k1_popc(const K1Plan &plan, const void *d_query, int nq, const void *d_db, int64_t shard_rows,
+                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial,
+                           cudaStream_t stream);
+
+// Reduce n_src x nq x k key lists to nq x k keys (ascending).
+cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t *d_out,
+                               cudaStream_t stream);
+// Reduce + radius cut + decode (imgIdx, trainIdx) + matches_3d gather.
+cudaError_t launch_finalize_matches(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t radius,
+                                    const uint32_t *d_obj_offsets, int n_objects, const float *d_points,
+                                    tod_match *d_matches, int32_t *d_counts, float *d_points3d,
+                                    cudaStream_t stream);
+
+// K2: one launch over all clusters. Device pointers.
+cudaError_t launch_fill_adjacency(int n_clusters, const int32_t *d_offsets, const int64_t *d_matrix_offsets,
+                                  const float *d_query, const float *d_train, const float *d_pixels,
+                                  const float *d_spans, float sensor_error, uint32_t *d_physical,
+                                  uint32_t *d_sample, int max_cluster, cudaStream_t stream);
+
+// K3: hypotheses (s0, s1, s2, cluster) of a batch of clusters described by K3Cluster records (k3_score.cu).
+// d_finite may be null (all points finite).
+cudaError_t launch_score_hypotheses_batched(const void *d_clusters, const float *d_query, const float *d_train,
+                                            const uint32_t *d_physical, const uint32_t *d_valid,
+                                            const uint32_t *d_finite, int n_hyp, const uint32_t *d_hyps,
+                                            double threshold, int32_t *d_counts, float *d_R, float *d_T,
+                                            cudaStream_t stream);
+size_t k3_cluster_desc_size();
+void k3_fill_cluster_desc(void *dst, int32_t n, int32_t W, int64_t point_offset, int64_t matrix_offset,
+                          int64_t valid_offset);
+
+inline int adjacency_row_words(int n) { return ((n + 31) / 32 + 3) & ~3; }
+
+}  // namespace tod
+#endif
