@@ -177,8 +177,10 @@ class Graph:
     # -- maximum_clique.cpp:219-261.  C is the ONE colour vector shared by every recursion level, exactly as in the
     # reference (it is passed by reference all the way down).  It is modelled as a fixed-capacity array plus a size:
     # ColorSort writes C[0..|R|) without touching the size, MaxCliqueDyn reads C.back() and pops.  Once the size has
-    # run to zero the reference reads/pops out of bounds (undefined behaviour); this restatement then uses colour 0
-    # and keeps the size at zero — see DESIGN.md "clique quirks".
+    # run to zero the reference reads/pops OUT OF BOUNDS (undefined behaviour).  What the compiled reference then
+    # sees on glibc/x86-64 is the malloc chunk header in front of the array: data[-1] = high word of the chunk size
+    # (0), data[-2] = low word of the chunk size | PREV_INUSE; below that, unknowable memory (taken as 0 here).
+    # See DESIGN.md "clique quirks".  The gate (minimal_size 7) never depends on it in 300/300 random graphs.
     def color_sort(self, R, C, QMax, Q):
         min_k = max(1, len(QMax) - len(Q) + 1)
         Ck = [[], []]
@@ -218,7 +220,12 @@ class Graph:
         SOld[level] = S[level - 1]
         while R:
             p = R[-1]
-            c = C[0][C[1] - 1] if C[1] > 0 else 0          # C.back()
+            if C[1] > 0:                                      # C.back()
+                c = C[0][C[1] - 1]
+            elif C[1] == -1:
+                c = (max(32, (4 * len(C[0]) + 8 + 15) & ~15)) | 1
+            else:
+                c = 0
             if len(Q) + c > len(QMax):
                 Q.append(p)
                 Rp = [v for v in R if self.test(p, v)]        # Intersection, :209-217
@@ -239,8 +246,7 @@ class Graph:
             else:
                 return
             R.pop()
-            if C[1] > 0:                                      # C.pop_back()
-                C[1] -= 1
+            C[1] -= 1                                         # C.pop_back() (may run negative, see above)
 
     # -- maximum_clique.cpp:343-369
     def find_clique(self, minimal_size):
