@@ -1,0 +1,174 @@
+// Host-side clique gate: bounded Konc–Janezic MaxCliqueDyn search with the reference's exact stopping rules.
+//
+// Stays on the host by design (north_star: "only the branchy clique search and the final refinement left on the host").
+// Behavioural contract = tod::maximum_clique::Graph::FindClique (src/common/maximum_clique.cpp:343-369 of the
+// reference) with its helpers DegreeSort (:263-284), ColorSort (:219-261), Intersection (:209-217) and MaxCliqueDyn
+// (:286-336): early exit as soon as a clique of `minimal_size` exists (:290, :325), step budget of 100000 (:318),
+// re-sort by degree while the per-level step ratio is under 0.025 (:313).  Data structure is a dense bit-matrix
+// instead of sorted neighbour lists.
+//
+// One reference quirk is reproduced on purpose: the colour vector is shared by all recursion levels (it is passed by
+// reference and popped by every level).  When it runs empty the reference reads past the front of the array; this
+// implementation returns the values a glibc heap yields there (0, then the chunk size word) — see DESIGN.md.
+#ifndef TOD_CLIQUE_H_
+#define TOD_CLIQUE_H_
+
+#include <algorithm>
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+namespace tod {
+
+class CliqueFinder {
+ public:
+  explicit CliqueFinder(int n_vertices)
+      : n_(n_vertices), words_((n_vertices + 31) / 32), bits_(size_t(n_vertices) * size_t((n_vertices + 31) / 32), 0u),
+        degree_(size_t(n_vertices), 0u) {}
+
+  void add_edge(int a, int b) {
+    if (a == b || connected(a, b)) return;
+    bits_[size_t(a) * words_ + (b >> 5)] |= 1u << (b & 31);
+    bits_[size_t(b) * words_ + (a >> 5)] |= 1u << (a & 31);
+    ++degree_[size_t(a)];
+    ++degree_[size_t(b)];
+  }
+
+  bool connected(int a, int b) const { return (bits_[size_t(a) * words_ + (b >> 5)] >> (b & 31)) & 1u; }
+
+  // Returns the clique found: the first one reaching `minimal_size`, else the largest seen within the step budget.
+  std::vector<int> find(unsigned minimal_size) {
+    best_.clear();
+    if (n_ == 0) return best_;
+    minimal_ = minimal_size;
+    steps_ = 1;
+    ratio_limit_ = 0.025;
+    std::vector<int> order(static_cast<size_t>(n_));
+    for (int i = 0; i < n_; ++i) order[size_t(i)] = i;
+    sort_by_degree(order);
+    const unsigned top = degree_[size_t(order[0])];
+    colour_.assign(size_t(n_), 0u);
+    for (unsigned i = 0; i < top && i < unsigned(n_); ++i) colour_[i] = i + 1;
+    for (unsigned i = top; i < unsigned(n_); ++i) colour_[i] = top + 1;
+    colour_size_ = n_;
+    level_steps_.assign(size_t(n_) + 1, 0u);
+    level_steps_old_.assign(size_t(n_) + 1, 0u);
+    current_.clear();
+    expand(order, 1);
+    return best_;
+  }
+
+ private:
+  // descending by (degree inside `r`, vertex id): std::sort of (degree, vertex) pairs read backwards
+  void sort_by_degree(std::vector<int> &r) const {
+    const size_t m = r.size();
+    std::vector<std::pair<unsigned, int> > d(m);
+    for (size_t i = 0; i < m; ++i) {
+      d[i] = std::make_pair(0u, r[i]);
+      for (size_t j = 0; j < i; ++j)
+        if (connected(r[i], r[j])) {
+          ++d[i].first;
+          ++d[j].first;
+        }
+    }
+    std::sort(d.begin(), d.end());
+    for (size_t i = 0; i < m; ++i) r[i] = d[m - 1 - i].second;
+  }
+
+  // greedy sequential colouring; vertices whose colour cannot extend the incumbent go first with colour 0
+  void colour_sort(std::vector<int> &r) {
+    const int gap = int(best_.size()) - int(current_.size()) + 1;
+    const unsigned min_k = unsigned(std::max(1, gap));
+    std::vector<std::vector<int> > classes(2);
+    size_t keep = 0;
+    size_t n_classes = 2;
+    const std::vector<int> snapshot(r);
+    for (int p : snapshot) {
+      size_t k = 1;
+      while (touches(p, classes[k])) {
+        ++k;
+        if (k >= n_classes) {
+          ++n_classes;
+          classes.resize(n_classes);
+          break;
+        }
+      }
+      if (k < min_k) r[keep++] = p;
+      else classes[k].push_back(p);
+    }
+    if (keep > 0) colour_[keep - 1] = 0;
+    size_t pos = keep;
+    for (size_t k = min_k; k < n_classes; ++k)
+      for (int v : classes[k]) {
+        r[pos] = v;
+        colour_[pos] = unsigned(k);
+        ++pos;
+      }
+  }
+
+  bool touches(int p, const std::vector<int> &cls) const {
+    for (int v : cls)
+      if (connected(p, v)) return true;
+    return false;
+  }
+
+  unsigned colour_back() const {
+    if (colour_size_ > 0) return colour_[size_t(colour_size_ - 1)];
+    if (colour_size_ == -1) {  // word in front of the array on a glibc heap: chunk size | PREV_INUSE
+      const unsigned long chunk = std::max(32ul, (4ul * unsigned(n_) + 8ul + 15ul) & ~15ul);
+      return unsigned(chunk | 1ul);
+    }
+    return 0u;
+  }
+
+  void expand(std::vector<int> &r, size_t level) {
+    if (best_.size() >= minimal_) return;
+    if (level >= level_steps_.size()) {
+      level_steps_.push_back(0u);
+      level_steps_old_.push_back(0u);
+    }
+    level_steps_[level] = level_steps_[level] + level_steps_[level - 1] - level_steps_old_[level];
+    level_steps_old_[level] = level_steps_[level - 1];
+    while (!r.empty()) {
+      const int p = r.back();
+      const unsigned c = colour_back();
+      if (current_.size() + c > best_.size()) {
+        current_.push_back(p);
+        std::vector<int> next;
+        for (int v : r)
+          if (connected(p, v)) next.push_back(v);
+        if (!next.empty()) {
+          if (double(level_steps_[level]) / steps_ < ratio_limit_) sort_by_degree(next);
+          colour_sort(next);
+          ++level_steps_[level];
+          ++steps_;
+          if (steps_ > 100000) return;
+          expand(next, level + 1);
+        } else if (current_.size() > best_.size()) {
+          best_ = current_;
+          if (best_.size() >= minimal_) return;
+        }
+        current_.pop_back();
+      } else {
+        return;
+      }
+      r.pop_back();
+      --colour_size_;
+    }
+  }
+
+  int n_;
+  int words_;
+  std::vector<uint32_t> bits_;
+  std::vector<unsigned> degree_;
+  std::vector<unsigned> colour_;
+  long colour_size_ = 0;
+  std::vector<unsigned> level_steps_, level_steps_old_;
+  std::vector<int> current_, best_;
+  unsigned minimal_ = 0;
+  int steps_ = 1;
+  double ratio_limit_ = 0.025;
+};
+
+}  // namespace tod
+#endif

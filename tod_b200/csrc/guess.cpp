@@ -1,13 +1,208 @@
-// C-ABI of the GuessGenerator half (include/tod_b200.h: tod_guess_*).  PLACEHOLDER — replaced by the full host
-// driver (cluster -> K2 -> sampler -> K3 -> replay/gate/refine) in the next commit.
+// C-ABI of the GuessGenerator half of the hot path (include/tod_b200.h: tod_guess_*).
+//
+// Host driver mirroring tod::GuessGenerator::process (src/detection/GuessGenerator.cpp:127-250 of the reference) and
+// tod::AdjacencyRansac (src/common/adjacency_ransac.cpp), restructured around two GPU kernels:
+//
+//   ClusterPerObject (adjacency_ransac.cpp:176-205)            host, one pass over the matches
+//   FillAdjacency    (:127-172)                                K2, one launch for all (object) clusters of the frame
+//   per RANSAC round, for all still-active objects together:
+//     sampler        (sac_model_registration_graph.h:102-168)  host, on bit-rows, seeded stream (replaces libc rand())
+//     model + inlier count (:171-200, :271-347)                K3, one launch for every hypothesis of every object
+//     best / adaptive-k scan (ransac.h:95-135)                 host replay over the K3 counts, in hypothesis order
+//     clique gate    (:203-268)                                host, only for hypotheses that beat the current best
+//     refinement + pose inversion (adjacency_ransac.cpp:255-308)   host
+//     InvalidateQueryIndices (:93-123) + cascade (:63-89)      host, as a valid-bit mask ANDed in at use
+//
+// Equivalences used: sorted neighbour lists <-> bit-rows; InvalidateCluster <-> AND with the valid
+// mask; the gate can only keep or zero a count, so it is evaluated lazily; the early stop of computeModel is a prefix
+// of the hypothesis list, so hypotheses are generated and scored in growing batches.
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <vector>
 
+#include "clique.h"
+#include "host_geometry.h"
 #include "tod_internal.h"
+
+using tod::DeviceBuffer;
+using tod::fail;
+
+namespace {
+
+inline int popc32(uint32_t x) { return __builtin_popcount(x); }
+
+struct Cluster {
+  int object = 0;
+  int n = 0, W = 0;
+  std::vector<float> q, t, px;     // n x 3, n x 3, n x 2
+  std::vector<uint32_t> qidx;      // query_indices_ (non-decreasing)
+  std::vector<uint32_t> valid;     // W words: valid_indices_ as a mask
+  std::vector<uint32_t> finite;    // W words: all six coordinates finite
+  int n_valid = 0;
+  int64_t point_offset = 0, matrix_offset = 0, valid_offset = 0;
+  const uint32_t *P = nullptr, *S = nullptr;  // host copies of the bit-matrices (n x W)
+  bool active = true;
+  unsigned round = 0;
+
+  // --- per-round RANSAC replay state (pcl::RandomSampleConsensus::computeModel) ---
+  uint64_t rng = 0;
+  int iterations = 0;
+  int n_best = -INT_MAX;
+  double k = 1.0;
+  bool stopped = false;
+  std::vector<uint32_t> best_inliers;
+  float best_R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, best_T[3] = {0, 0, 0};  // R_, T_ of the best hypothesis (finite mode)
+  std::vector<uint32_t> hyps;  // triples of the current batch
+  int batch_begin = 0;         // offset of this cluster's hypotheses in the frame-wide batch
+};
+
+// index of the r-th set bit (ascending) of a W-word mask
+inline uint32_t select_bit(const uint32_t *m, int W, uint32_t r) {
+  for (int w = 0; w < W; ++w) {
+    const uint32_t c = uint32_t(popc32(m[w]));
+    if (r < c) {
+      uint32_t x = m[w];
+      for (uint32_t i = 0; i < r; ++i) x &= x - 1;
+      return uint32_t(w) * 32u + uint32_t(__builtin_ctz(x));
+    }
+    r -= c;
+  }
+  return 0xFFFFFFFFu;
+}
+
+inline int mask_count(const uint32_t *m, int W) {
+  int c = 0;
+  for (int w = 0; w < W; ++w) c += popc32(m[w]);
+  return c;
+}
+
+// drawIndexSampleHelper (sac_model_registration_graph.h:102-132) on bit masks.  `cur` is consumed.
+bool draw_samples(const Cluster &c, std::vector<uint32_t> &cur, int count, int n_samples, uint64_t &rng,
+                  std::vector<uint32_t> &out) {
+  if (n_samples == 0) return true;
+  if (count == 0) return false;
+  const int W = c.W;
+  std::vector<uint32_t> next(static_cast<size_t>(W));
+  while (true) {
+    const uint32_t r = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count));
+    const uint32_t s = select_bit(cur.data(), W, r);
+    const uint32_t *row = c.S + size_t(s) * W;
+    int nc = 0;
+    for (int w = 0; w < W; ++w) {
+      next[size_t(w)] = cur[size_t(w)] & row[w];
+      nc += popc32(next[size_t(w)]);
+    }
+    if (draw_samples(c, next, nc, n_samples - 1, rng, out)) {
+      out.push_back(s);
+      return true;
+    }
+    cur[s >> 5] &= ~(1u << (s & 31));
+    if (--count == 0) return false;
+  }
+}
+
+// getSamples (:141-168).  Returns false when the valid set holds no triangle of the sample graph (every one of the
+// reference's 1000 retries would then fail identically, so one exhaustive attempt decides).
+bool get_samples(const Cluster &c, uint64_t &rng, uint32_t triple[3]) {
+  if (c.n_valid < 3) return false;
+  std::vector<uint32_t> cur(c.valid);
+  std::vector<uint32_t> out;
+  if (!draw_samples(c, cur, c.n_valid, 3, rng, out)) return false;
+  triple[0] = out[0];
+  triple[1] = out[1];
+  triple[2] = out[2];
+  return true;
+}
+
+struct GateScratch {
+  std::vector<uint32_t> inliers, filtered, mask;
+};
+
+// Inlier list of one hypothesis exactly as selectWithinDistance builds it before the gate (:178-200): common valid
+// physical neighbours in ascending order, then the samples; each kept if it passes the distance test.
+void hypothesis_inliers(const Cluster &c, const uint32_t s[3], bool inf_threshold, double thr2, const float *R,
+                        const float *T, std::vector<uint32_t> &out) {
+  out.clear();
+  const int W = c.W;
+  if (inf_threshold) {
+    // a sample with a non-finite coordinate makes (R, T) NaN and every `distSq < inf` test false (K3 returns 0 too)
+    for (int k = 0; k < 3; ++k)
+      if (!((c.finite[s[k] >> 5] >> (s[k] & 31)) & 1u)) return;
+  }
+  const uint32_t *r0 = c.P + size_t(s[0]) * W, *r1 = c.P + size_t(s[1]) * W, *r2 = c.P + size_t(s[2]) * W;
+  auto passes = [&](uint32_t i) -> bool {
+    if (inf_threshold) return (c.finite[i >> 5] >> (i & 31)) & 1u;
+    float p[3];
+    tod::transform_point(R, T, c.q.data() + size_t(i) * 3, p);
+    const float *t = c.t.data() + size_t(i) * 3;
+    const float dx = p[0] - t[0], dy = p[1] - t[1], dz = p[2] - t[2];
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    return double(d2) < thr2;
+  };
+  for (int w = 0; w < W; ++w) {
+    uint32_t m = r0[w] & r1[w] & r2[w] & c.valid[size_t(w)];
+    while (m) {
+      const uint32_t i = uint32_t(w) * 32u + uint32_t(__builtin_ctz(m));
+      m &= m - 1;
+      if (passes(i)) out.push_back(i);
+    }
+  }
+  for (int k = 0; k < 3; ++k)
+    if (passes(s[k])) out.push_back(s[k]);
+}
+
+// The clique gate of selectWithinDistance (:203-268) on an inlier list of size > 7.  Returns true if the list stands.
+bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScratch &g) {
+  const size_t minimal = 7;  // std::min(best_inlier_number_, 7) with best_inlier_number_ >= 8 always (:85, :203)
+  const int W = c.W;
+  g.filtered.clear();
+  for (uint32_t v : inliers) {  // :209-213 — sample-degree inside the current valid set
+    const uint32_t *row = c.S + size_t(v) * W;
+    int deg = 0;
+    for (int w = 0; w < W; ++w) deg += popc32(row[w] & c.valid[size_t(w)]);
+    if (size_t(deg) >= minimal) g.filtered.push_back(v);
+  }
+  if (g.filtered.size() <= minimal) return false;
+  std::sort(g.filtered.begin(), g.filtered.end());
+  g.mask.assign(size_t(W), 0u);
+  for (uint32_t v : g.filtered) g.mask[v >> 5] |= 1u << (v & 31);
+  size_t reach = 0;  // :222-238
+  for (uint32_t v : g.filtered) {
+    const uint32_t *row = c.S + size_t(v) * W;
+    int m = 0;
+    for (int w = 0; w < W; ++w) m += popc32(row[w] & g.mask[size_t(w)]);
+    reach = size_t(m);
+    if (reach > minimal) break;
+  }
+  if (reach <= minimal) return false;
+  // induced sample sub-graph on `filtered` (:241-255), then the bounded clique search (:258-265)
+  const int nv = int(g.filtered.size());
+  tod::CliqueFinder finder(nv);
+  for (int a = 0; a < nv - 1; ++a) {
+    const uint32_t *row = c.S + size_t(g.filtered[size_t(a)]) * W;
+    for (int b = a + 1; b < nv; ++b) {
+      const uint32_t v = g.filtered[size_t(b)];
+      if ((row[v >> 5] >> (v & 31)) & 1u) finder.add_edge(a, b);
+    }
+  }
+  return finder.find(unsigned(minimal)).size() > minimal;
+}
+
+}  // namespace
 
 struct tod_guess {
   tod_guess_params p{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DeviceBuffer d_off, d_mo, d_q, d_t, d_px, d_sp, d_P, d_S, d_desc, d_valid, d_finite, d_hyps, d_counts, d_R, d_T;
+  std::vector<uint32_t> h_P, h_S;
+  float k2_ms = 0, k3_ms = 0;
+  int64_t n_hyp_total = 0;
+  int32_t n_rounds = 0;
 };
 
 extern "C" {
@@ -25,25 +220,435 @@ void tod_guess_default_params(tod_guess_params *p) {
 
 int tod_guess_create(const tod_guess_params *p, tod_guess **out) {
   TOD_REQUIRE(p && out, "null argument");
+  TOD_REQUIRE(p->sensor_error >= 0.f, "negative sensor_error");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return fail(TOD_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  TOD_REQUIRE(p->device >= 0 && p->device < n_dev, "device %d out of range (%d devices)", p->device, n_dev);
+  TOD_CUDA(cudaSetDevice(p->device));
   tod_guess *g = new tod_guess();
   g->p = *p;
+  TOD_CUDA(cudaStreamCreate(&g->stream));
+  TOD_CUDA(cudaEventCreate(&g->ev0));
+  TOD_CUDA(cudaEventCreate(&g->ev1));
   *out = g;
   return TOD_OK;
 }
 
-void tod_guess_destroy(tod_guess *g) { delete g; }
-
-int tod_guess_process(tod_guess *, const tod_keypoint *, int32_t, const float *, int32_t, int32_t, const tod_match *,
-                      const int32_t *, int32_t, const float *, const float *, int32_t, tod_pose *, int32_t, int32_t *,
-                      int32_t *, int32_t) {
-  return tod::fail(TOD_ERR_STATE, "tod_guess_process: not built yet");
+void tod_guess_destroy(tod_guess *g) {
+  if (!g) return;
+  cudaSetDevice(g->p.device);
+  for (DeviceBuffer *b : {&g->d_off, &g->d_mo, &g->d_q, &g->d_t, &g->d_px, &g->d_sp, &g->d_P, &g->d_S, &g->d_desc,
+                          &g->d_valid, &g->d_finite, &g->d_hyps, &g->d_counts, &g->d_R, &g->d_T})
+    b->release();
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
 }
 
-void tod_guess_last_stats(const tod_guess *, float *k2_ms, float *k3_ms, int64_t *n_hyp, int32_t *n_rounds) {
-  if (k2_ms) *k2_ms = 0;
-  if (k3_ms) *k3_ms = 0;
-  if (n_hyp) *n_hyp = 0;
-  if (n_rounds) *n_rounds = 0;
+void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_t *n_hyp, int32_t *n_rounds) {
+  if (k2_ms) *k2_ms = g ? g->k2_ms : 0.f;
+  if (k3_ms) *k3_ms = g ? g->k3_ms : 0.f;
+  if (n_hyp) *n_hyp = g ? g->n_hyp_total : 0;
+  if (n_rounds) *n_rounds = g ? g->n_rounds : 0;
+}
+
+int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp, const float *cloud, int32_t height,
+                      int32_t width, const tod_match *matches, const int32_t *counts, int32_t k,
+                      const float *points3d, const float *spans, int32_t n_objects, tod_pose *poses,
+                      int32_t max_poses, int32_t *n_poses, int32_t *inlier_keypoints, int32_t max_inlier_total) {
+  TOD_REQUIRE(g && n_poses, "null argument");
+  *n_poses = 0;
+  g->k2_ms = g->k3_ms = 0.f;
+  g->n_hyp_total = 0;
+  g->n_rounds = 0;
+  TOD_REQUIRE(n_kp >= 0 && k >= 1 && n_objects >= 0 && max_poses >= 0, "bad sizes");
+  if (n_kp == 0) return TOD_OK;
+  TOD_REQUIRE(keypoints && matches && counts && points3d && spans && (poses || max_poses == 0), "null input buffer");
+  // "if (point_cloud.empty()) { TODO 2d-3d }" — no cloud, no poses (GuessGenerator.cpp:147-152)
+  if (!cloud || height <= 0 || width <= 0) return TOD_OK;
+  TOD_CUDA(cudaSetDevice(g->p.device));
+  cudaStream_t st = g->stream;
+  const float err = g->p.sensor_error;
+  const bool inf_thr = !(g->p.ransac_threshold < 1e150);
+  const double thr2 = inf_thr ? std::numeric_limits<double>::infinity() : g->p.ransac_threshold * g->p.ransac_threshold;
+
+  // ---- ClusterPerObject (adjacency_ransac.cpp:176-205) -------------------------------------------------------------
+  std::map<int, Cluster> by_object;
+  for (int32_t qi = 0; qi < n_kp; ++qi) {
+    const int cnt = counts[qi];
+    TOD_REQUIRE(cnt >= 0 && cnt <= k, "counts[%d] = %d outside [0, k=%d]", qi, cnt, k);
+    // point_cloud.at<Vec3f>(pt.y, pt.x): float -> int conversion truncates (quirk Q9)
+    const int y = int(keypoints[qi].y), x = int(keypoints[qi].x);
+    TOD_REQUIRE(y >= 0 && y < height && x >= 0 && x < width, "keypoint %d at (%g, %g) outside the %dx%d cloud", qi,
+                keypoints[qi].x, keypoints[qi].y, width, height);
+    const float *qp = cloud + (size_t(y) * width + x) * 3;
+    if (std::isnan(qp[0])) continue;  // x only, like cvIsNaN(query_point[0]) (:189)
+    for (int j = 0; j < cnt; ++j) {
+      const tod_match &m = matches[size_t(qi) * k + j];
+      TOD_REQUIRE(m.imgIdx >= 0 && m.imgIdx < n_objects, "match imgIdx %d outside [0, %d)", m.imgIdx, n_objects);
+      Cluster &c = by_object[m.imgIdx];
+      const float *tp = points3d + (size_t(qi) * k + j) * 3;
+      c.t.insert(c.t.end(), tp, tp + 3);
+      c.q.insert(c.q.end(), qp, qp + 3);
+      c.px.push_back(keypoints[qi].x);
+      c.px.push_back(keypoints[qi].y);
+      c.qidx.push_back(uint32_t(qi));
+    }
+  }
+  if (by_object.empty()) return TOD_OK;
+
+  std::vector<Cluster *> clusters;
+  std::vector<int32_t> offsets(1, 0);
+  std::vector<int64_t> mo(1, 0);
+  std::vector<float> spans_c;
+  int64_t vo = 0;
+  int max_n = 0;
+  for (auto &kv : by_object) {
+    Cluster &c = kv.second;
+    c.object = kv.first;
+    c.n = int(c.qidx.size());
+    c.W = tod::adjacency_row_words(c.n);
+    c.point_offset = offsets.back();
+    c.matrix_offset = mo.back();
+    c.valid_offset = vo;
+    c.valid.assign(size_t(c.W), 0u);
+    c.finite.assign(size_t(c.W), 0u);
+    for (int i = 0; i < c.n; ++i) {
+      c.valid[size_t(i) >> 5] |= 1u << (i & 31);
+      bool fin = true;
+      for (int d = 0; d < 3; ++d) fin = fin && std::isfinite(c.q[size_t(i) * 3 + d]) && std::isfinite(c.t[size_t(i) * 3 + d]);
+      if (fin) c.finite[size_t(i) >> 5] |= 1u << (i & 31);
+    }
+    c.n_valid = c.n;
+    offsets.push_back(offsets.back() + c.n);
+    mo.push_back(mo.back() + int64_t(c.n) * c.W);
+    vo += c.W;
+    spans_c.push_back(spans[c.object]);
+    max_n = std::max(max_n, c.n);
+    clusters.push_back(&c);
+  }
+  const int nc = int(clusters.size());
+  const int64_t N = offsets.back();
+  const size_t mat_words = size_t(mo.back());
+
+  // ---- FillAdjacency for every cluster: K2 --------------------------------------------------------------------------
+  std::vector<float> all_q(size_t(N) * 3), all_t(size_t(N) * 3), all_px(size_t(N) * 2);
+  std::vector<uint32_t> all_valid(static_cast<size_t>(vo)), all_finite(static_cast<size_t>(vo));
+  std::vector<unsigned char> desc(size_t(nc) * tod::k3_cluster_desc_size());
+  for (int ci = 0; ci < nc; ++ci) {
+    Cluster &c = *clusters[size_t(ci)];
+    std::copy(c.q.begin(), c.q.end(), all_q.begin() + c.point_offset * 3);
+    std::copy(c.t.begin(), c.t.end(), all_t.begin() + c.point_offset * 3);
+    std::copy(c.px.begin(), c.px.end(), all_px.begin() + c.point_offset * 2);
+    std::copy(c.finite.begin(), c.finite.end(), all_finite.begin() + c.valid_offset);
+    tod::k3_fill_cluster_desc(desc.data() + size_t(ci) * tod::k3_cluster_desc_size(), c.n, c.W, c.point_offset,
+                              c.matrix_offset, c.valid_offset);
+  }
+  TOD_CUDA(g->d_off.reserve(offsets.size() * 4));
+  TOD_CUDA(g->d_mo.reserve(mo.size() * 8));
+  TOD_CUDA(g->d_q.reserve(all_q.size() * 4));
+  TOD_CUDA(g->d_t.reserve(all_t.size() * 4));
+  TOD_CUDA(g->d_px.reserve(all_px.size() * 4));
+  TOD_CUDA(g->d_sp.reserve(spans_c.size() * 4));
+  TOD_CUDA(g->d_P.reserve(mat_words * 4));
+  TOD_CUDA(g->d_S.reserve(mat_words * 4));
+  TOD_CUDA(g->d_desc.reserve(desc.size()));
+  TOD_CUDA(g->d_valid.reserve(all_valid.size() * 4));
+  TOD_CUDA(g->d_finite.reserve(all_finite.size() * 4));
+  TOD_CUDA(cudaMemcpyAsync(g->d_off.ptr, offsets.data(), offsets.size() * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_mo.ptr, mo.data(), mo.size() * 8, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_q.ptr, all_q.data(), all_q.size() * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_t.ptr, all_t.data(), all_t.size() * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_px.ptr, all_px.data(), all_px.size() * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_sp.ptr, spans_c.data(), spans_c.size() * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_desc.ptr, desc.data(), desc.size(), cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_finite.ptr, all_finite.data(), all_finite.size() * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaEventRecord(g->ev0, st));
+  TOD_CUDA(tod::launch_fill_adjacency(nc, g->d_off.as<int32_t>(), g->d_mo.as<int64_t>(), g->d_q.as<float>(),
+                                      g->d_t.as<float>(), g->d_px.as<float>(), g->d_sp.as<float>(), err,
+                                      g->d_P.as<uint32_t>(), g->d_S.as<uint32_t>(), max_n, st));
+  TOD_CUDA(cudaEventRecord(g->ev1, st));
+  g->h_P.resize(mat_words);
+  g->h_S.resize(mat_words);
+  TOD_CUDA(cudaMemcpyAsync(g->h_P.data(), g->d_P.ptr, mat_words * 4, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaMemcpyAsync(g->h_S.data(), g->d_S.ptr, mat_words * 4, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  TOD_CUDA(cudaEventElapsedTime(&g->k2_ms, g->ev0, g->ev1));
+  for (Cluster *c : clusters) {
+    c->P = g->h_P.data() + c->matrix_offset;
+    c->S = g->h_S.data() + c->matrix_offset;
+  }
+  // "InvalidateIndices({})" at the end of FillAdjacency is a no-op (quirk Q4): no pruning before the first round.
+
+  // ---- RANSAC rounds, all active objects in lock-step ------------------------------------------------------------------
+  struct Found {
+    int object;
+    unsigned round;
+    tod_pose pose;
+    std::vector<uint32_t> kp;
+  };
+  std::vector<Found> found;
+  const int max_iter = int(g->p.n_ransac_iterations);
+  GateScratch scratch;
+  std::vector<uint32_t> tmp_inliers;
+  std::vector<uint32_t> batch_hyps;
+  std::vector<int32_t> batch_counts;
+  std::vector<float> batch_R, batch_T;
+
+  while (true) {
+    // start a round on every active cluster (AdjacencyRansac::Ransac, adjacency_ransac.cpp:234-253)
+    bool any = false;
+    for (Cluster *c : clusters) {
+      if (!c->active) continue;
+      if (c->n_valid < 3) {  // :238-241 -> no inliers -> below min_inliers -> object finished
+        c->active = false;
+        continue;
+      }
+      c->rng = tod_rng_seed(g->p.seed, uint32_t(c->object), c->round);
+      c->iterations = 0;
+      c->n_best = -INT_MAX;
+      c->k = 1.0;
+      c->stopped = false;
+      c->best_inliers.clear();
+      std::copy(c->valid.begin(), c->valid.end(), all_valid.begin() + c->valid_offset);
+      any = true;
+    }
+    if (!any) break;
+    ++g->n_rounds;
+    TOD_CUDA(cudaMemcpyAsync(g->d_valid.ptr, all_valid.data(), all_valid.size() * 4, cudaMemcpyHostToDevice, st));
+
+    // computeModel (ransac.h:80-143): hypotheses are drawn and scored in growing batches; the replay below consumes
+    // them in order and stops exactly where the reference's loop would.
+    int batch_size = 64;
+    while (true) {
+      batch_hyps.clear();
+      for (size_t ci = 0; ci < clusters.size(); ++ci) {
+        Cluster *c = clusters[ci];
+        c->hyps.clear();
+        if (!c->active || c->stopped) continue;
+        // the loop can run at most until iterations_ exceeds max_iterations_ (ransac.h:132-134)
+        const int room = std::min(batch_size, max_iter + 1 - c->iterations);
+        c->batch_begin = int(batch_hyps.size() / 4);
+        for (int h = 0; h < room; ++h) {
+          uint32_t tr[3];
+          if (!get_samples(*c, c->rng, tr)) break;  // empty selection -> loop breaks (ransac.h:100-101)
+          c->hyps.insert(c->hyps.end(), tr, tr + 3);
+          batch_hyps.insert(batch_hyps.end(), tr, tr + 3);
+          batch_hyps.push_back(uint32_t(ci));
+        }
+      }
+      const int H = int(batch_hyps.size() / 4);
+      if (H > 0) {
+        batch_counts.resize(size_t(H));
+        TOD_CUDA(g->d_hyps.reserve(batch_hyps.size() * 4));
+        TOD_CUDA(g->d_counts.reserve(size_t(H) * 4));
+        if (!inf_thr) {
+          TOD_CUDA(g->d_R.reserve(size_t(H) * 36));
+          TOD_CUDA(g->d_T.reserve(size_t(H) * 12));
+          batch_R.resize(size_t(H) * 9);
+          batch_T.resize(size_t(H) * 3);
+        }
+        TOD_CUDA(cudaMemcpyAsync(g->d_hyps.ptr, batch_hyps.data(), batch_hyps.size() * 4, cudaMemcpyHostToDevice, st));
+        TOD_CUDA(cudaEventRecord(g->ev0, st));
+        TOD_CUDA(tod::launch_score_hypotheses_batched(
+            g->d_desc.ptr, g->d_q.as<float>(), g->d_t.as<float>(), g->d_P.as<uint32_t>(), g->d_valid.as<uint32_t>(),
+            g->d_finite.as<uint32_t>(), H, g->d_hyps.as<uint32_t>(), g->p.ransac_threshold, g->d_counts.as<int32_t>(),
+            inf_thr ? nullptr : g->d_R.as<float>(), inf_thr ? nullptr : g->d_T.as<float>(), st));
+        TOD_CUDA(cudaEventRecord(g->ev1, st));
+        TOD_CUDA(cudaMemcpyAsync(batch_counts.data(), g->d_counts.ptr, size_t(H) * 4, cudaMemcpyDeviceToHost, st));
+        if (!inf_thr) {
+          TOD_CUDA(cudaMemcpyAsync(batch_R.data(), g->d_R.ptr, size_t(H) * 36, cudaMemcpyDeviceToHost, st));
+          TOD_CUDA(cudaMemcpyAsync(batch_T.data(), g->d_T.ptr, size_t(H) * 12, cudaMemcpyDeviceToHost, st));
+        }
+        TOD_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        TOD_CUDA(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+        g->k3_ms += ms;
+        g->n_hyp_total += H;
+      }
+
+      bool more = false;
+      for (Cluster *c : clusters) {
+        if (!c->active || c->stopped) continue;
+        const int nh = int(c->hyps.size() / 3);
+        const int room = std::min(batch_size, max_iter + 1 - c->iterations);
+        int h = 0;
+        for (; h < nh; ++h) {
+          if (!(double(c->iterations) < c->k)) {  // while (iterations_ < k)
+            c->stopped = true;
+            break;
+          }
+          const int pre = batch_counts[size_t(c->batch_begin + h)];
+          if (pre > c->n_best) {
+            // only now does the exact post-gate count matter (the gate keeps or zeroes the pre-gate count)
+            const uint32_t *s = c->hyps.data() + size_t(h) * 3;
+            const float *R = inf_thr ? nullptr : batch_R.data() + size_t(c->batch_begin + h) * 9;
+            const float *T = inf_thr ? nullptr : batch_T.data() + size_t(c->batch_begin + h) * 3;
+            hypothesis_inliers(*c, s, inf_thr, thr2, R, T, tmp_inliers);
+            if (int(tmp_inliers.size()) != pre)
+              return fail(TOD_ERR_STATE, "K3 count %d disagrees with the host candidate list %zu (object %d)", pre,
+                          tmp_inliers.size(), c->object);
+            int final_count = pre;
+            if (tmp_inliers.size() > 7 && !clique_gate(*c, tmp_inliers, scratch)) {
+              tmp_inliers.clear();
+              final_count = 0;
+            }
+            if (final_count > c->n_best) {  // ransac.h:115-130
+              c->n_best = final_count;
+              c->best_inliers = tmp_inliers;
+              if (R) std::memcpy(c->best_R, R, sizeof(c->best_R));
+              if (T) std::memcpy(c->best_T, T, sizeof(c->best_T));
+              const double w = double(c->n_best) / double(c->n_valid);
+              double p_no = 1.0 - std::pow(w, 3.0);
+              p_no = std::max(std::numeric_limits<double>::epsilon(), p_no);
+              p_no = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no);
+              c->k = std::log(1.0 - 0.99) / std::log(p_no);
+            }
+          }
+          ++c->iterations;
+          if (c->iterations > max_iter) {
+            c->stopped = true;
+            ++h;
+            break;
+          }
+        }
+        if (!c->stopped) {
+          if (nh < room) c->stopped = true;                        // sampler ran dry: selection.empty() -> break
+          else if (!(double(c->iterations) < c->k)) c->stopped = true;
+          else more = true;
+        }
+      }
+      if (!more) break;
+      batch_size = std::min(batch_size * 4, 4096);
+    }
+
+    // finish the round per cluster: refinement, pose, invalidation (adjacency_ransac.cpp:255-308, GuessGenerator.cpp:205-230)
+    for (Cluster *c : clusters) {
+      if (!c->active) continue;
+      if (c->best_inliers.empty()) {  // computeModel() returned false -> inliers_in stays empty -> below min_inliers
+        c->active = false;
+        continue;
+      }
+      std::vector<uint32_t> inliers(c->best_inliers);
+      std::sort(inliers.begin(), inliers.end());
+      std::vector<uint32_t> in_mask(size_t(c->W), 0u);
+      for (uint32_t i : inliers) in_mask[i >> 5] |= 1u << (i & 31);
+      std::vector<uint32_t> rest;  // valid_indices_ \ inliers, ascending
+      for (int w = 0; w < c->W; ++w) {
+        uint32_t m = c->valid[size_t(w)] & ~in_mask[size_t(w)];
+        while (m) {
+          rest.push_back(uint32_t(w) * 32u + uint32_t(__builtin_ctz(m)));
+          m &= m - 1;
+        }
+      }
+      bool do_final = false;
+      double thresh = double(err * err);  // :267 (float product widened)
+      float R[9], T[3];
+      std::memcpy(R, c->best_R, sizeof(R));
+      std::memcpy(T, c->best_T, sizeof(T));
+      while (true) {
+        // optimizeModelCoefficients leaves (R, T) untouched with fewer than 3 inliers (sac_model...h:307-308)
+        if (inliers.size() >= 3)
+          tod::rigid_fit(c->q.data(), c->t.data(), inliers.data(), int(inliers.size()), R, T);  // :272
+        std::vector<uint32_t> extra, keep;
+        for (uint32_t i : rest) {  // :276-283
+          float p[3];
+          tod::transform_point(R, T, c->q.data() + size_t(i) * 3, p);
+          const float *t = c->t.data() + size_t(i) * 3;
+          const double dx = double(p[0] - t[0]), dy = double(p[1] - t[1]), dz = double(p[2] - t[2]);
+          const double nrm = std::sqrt(dx * dx + dy * dy + dz * dz);  // cv::norm(Vec3f): double accumulation
+          if (nrm * nrm < thresh) extra.push_back(i);
+          else keep.push_back(i);
+        }
+        if (!extra.empty()) {
+          std::vector<uint32_t> merged(inliers.size() + extra.size());
+          std::merge(inliers.begin(), inliers.end(), extra.begin(), extra.end(), merged.begin());
+          inliers.swap(merged);
+          rest.swap(keep);
+        }
+        if (do_final) break;
+        if (extra.empty()) {
+          do_final = true;
+          thresh *= 4;
+        }
+      }
+      // R = R^T ; T = -R * T   (object -> camera, :304-305)
+      float Rt[9];
+      for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 3; ++cc) Rt[r * 3 + cc] = R[cc * 3 + r];
+      float nR[9], Tn[3];
+      for (int i = 0; i < 9; ++i) nR[i] = Rt[i] * -1.f;
+      const float zero[3] = {0.f, 0.f, 0.f};
+      tod::transform_point(nR, zero, T, Tn);
+      std::vector<uint32_t> kp;
+      kp.reserve(inliers.size());
+      for (uint32_t i : inliers) kp.push_back(c->qidx[i]);
+      std::sort(kp.begin(), kp.end());
+      kp.erase(std::unique(kp.begin(), kp.end()), kp.end());
+      if (kp.size() < g->p.min_inliers) {  // GuessGenerator.cpp:205-206
+        c->active = false;
+        continue;
+      }
+      // InvalidateQueryIndices (:93-123): drop every still-valid match whose keypoint is an inlier, then cascade
+      std::vector<uint32_t> todo;
+      for (int w = 0; w < c->W; ++w) {
+        uint32_t m = c->valid[size_t(w)];
+        while (m) {
+          const uint32_t i = uint32_t(w) * 32u + uint32_t(__builtin_ctz(m));
+          m &= m - 1;
+          if (std::binary_search(kp.begin(), kp.end(), c->qidx[i])) todo.push_back(i);
+        }
+      }
+      while (!todo.empty()) {  // InvalidateIndices (:63-89)
+        for (uint32_t i : todo) c->valid[i >> 5] &= ~(1u << (i & 31));
+        c->n_valid -= int(todo.size());
+        todo.clear();
+        for (int w = 0; w < c->W; ++w) {
+          uint32_t m = c->valid[size_t(w)];
+          while (m) {
+            const uint32_t i = uint32_t(w) * 32u + uint32_t(__builtin_ctz(m));
+            m &= m - 1;
+            const uint32_t *row = c->S + size_t(i) * c->W;
+            int deg = 0;
+            for (int ww = 0; ww < c->W; ++ww) deg += popc32(row[ww] & c->valid[size_t(ww)]);
+            if (deg < 3) todo.push_back(i);  // min_sample_size_ (adjacency_ransac.h:58)
+          }
+        }
+      }
+      Found f;
+      f.object = c->object;
+      f.round = c->round;
+      std::memcpy(f.pose.R, Rt, sizeof(Rt));
+      std::memcpy(f.pose.T, Tn, sizeof(Tn));
+      f.pose.object_index = c->object;
+      f.pose.n_inliers = int32_t(kp.size());
+      f.kp.swap(kp);
+      found.push_back(std::move(f));
+      ++c->round;
+    }
+  }
+
+  // emission order of the reference: objects ascending (std::map), rounds in order (GuessGenerator.cpp:170-235)
+  std::stable_sort(found.begin(), found.end(), [](const Found &a, const Found &b) {
+    return a.object != b.object ? a.object < b.object : a.round < b.round;
+  });
+  if (int64_t(found.size()) > max_poses)
+    return fail(TOD_ERR_LIMIT, "%zu poses found but max_poses = %d", found.size(), max_poses);
+  int64_t n_inl = 0;
+  for (size_t i = 0; i < found.size(); ++i) {
+    poses[i] = found[i].pose;
+    if (inlier_keypoints) {
+      if (n_inl + int64_t(found[i].kp.size()) > max_inlier_total)
+        return fail(TOD_ERR_LIMIT, "inlier_keypoints capacity %d too small", max_inlier_total);
+      for (uint32_t v : found[i].kp) inlier_keypoints[n_inl++] = int32_t(v);
+    }
+  }
+  *n_poses = int32_t(found.size());
+  return TOD_OK;
 }
 
 }  // extern "C"

@@ -149,7 +149,9 @@ K1Plan k1_popc_plan(int nq, int64_t shard_rows, int sm_count) {
   p.n_qtiles = (nq + p.q_tile - 1) / p.q_tile;
   if (p.n_qtiles < 1) p.n_qtiles = 1;
   const int64_t max_chunks = (shard_rows + kTileRows - 1) / kTileRows;
-  int64_t target = (2LL * sm_count + p.n_qtiles - 1) / p.n_qtiles;  // 2 resident CTAs per SM
+  // 2 CTAs are resident per SM: size the grid to at most ONE full wave (floor), so that no tail wave runs at low
+  // occupancy; with more query tiles than CTA slots the DB is not split at all
+  int64_t target = (2LL * sm_count) / p.n_qtiles;
   if (target > max_chunks) target = max_chunks;
   if (target < 1) target = 1;
   int64_t rpc = (shard_rows + target - 1) / target;

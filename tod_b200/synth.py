@@ -122,3 +122,56 @@ def make_cluster(n, inlier_fraction=0.5, seed=BASE_SEED + 3, span=0.25, noise_si
     px = np.stack([f * query[:, 0] / query[:, 2] + (width - 1) / 2.0,
                    f * query[:, 1] / query[:, 2] + (height - 1) / 2.0], axis=1).astype(np.float32)
     return query, train, px, (R.astype(np.float32), T.astype(np.float32)), ~out
+
+
+def make_guess_inputs(n_objects, n_per_object, inlier_fraction, seed=BASE_SEED + 4, span=0.25, noise_sigma=0.002,
+                      height=480, width=640, k=2):
+    """Inputs injected directly at the GuessGenerator boundary (BASELINE config C5: outlier-heavy matches): every
+    keypoint carries one match to one object; a fraction of each object's correspondences follow the object's planted
+    rigid pose, the rest are geometrically inconsistent.  Returns dict(keypoints_xy, cloud, matches (MATCH dtype
+    [n_kp,k]), counts, points3d [n_kp,k,3], spans [n_objects], poses {obj: (R, T)} object->camera)."""
+    rng = np.random.default_rng(seed)
+    f = 525.0 * width / 640.0
+    cx, cy = (width - 1) / 2.0, (height - 1) / 2.0
+    side = span / np.sqrt(3.0)
+    n_kp = n_objects * n_per_object
+    cloud = np.full((height, width, 3), np.nan, np.float32)
+    mdt = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+    matches = np.zeros((n_kp, k), mdt)
+    matches["queryIdx"] = -1
+    matches["trainIdx"] = -1
+    matches["imgIdx"] = -1
+    counts = np.zeros(n_kp, np.int32)
+    p3 = np.zeros((n_kp, k, 3), np.float32)
+    kps = np.zeros((n_kp, 2), np.float32)
+    poses = {}
+    taken = set()
+    order = rng.permutation(n_kp)
+    qi = 0
+    for o in range(n_objects):
+        R = random_rotation(rng)
+        T = np.array([rng.uniform(-0.2, 0.2), rng.uniform(-0.15, 0.15), rng.uniform(0.7, 1.1)])
+        poses[o] = (R.astype(np.float32), T.astype(np.float32))
+        for i in range(n_per_object):
+            tp = (rng.random(3) - 0.5) * side
+            if rng.random() < inlier_fraction:
+                qp = R @ tp + T + rng.normal(0, noise_sigma, 3)
+            else:
+                qp = (rng.random(3) - 0.5) * side * 1.6 + T
+            while True:
+                u, v = f * qp[0] / qp[2] + cx, f * qp[1] / qp[2] + cy
+                xi, yi = int(u), int(v)
+                if 0 <= xi < width and 0 <= yi < height and (yi, xi) not in taken:
+                    break
+                qp = qp + rng.normal(0, 0.01, 3)   # nudge until it lands on a free pixel
+            taken.add((yi, xi))
+            q = int(order[qi])
+            qi += 1
+            cloud[yi, xi] = qp.astype(np.float32)
+            kps[q] = (xi + rng.random() * 0.99, yi + rng.random() * 0.99)
+            matches[q, 0] = (q, i, o, float(rng.integers(0, 30)))
+            counts[q] = 1
+            p3[q, 0] = tp.astype(np.float32)
+    spans = np.full(n_objects, np.float32(span), np.float32)
+    return {"keypoints_xy": kps, "cloud": cloud, "matches": matches, "counts": counts, "points3d": p3,
+            "spans": spans, "poses": poses}
