@@ -4,25 +4,29 @@ import pytest
 
 from conftest import assert_matches_equal, golden_names, load_golden
 from oracle import hamming_knn as hk
-from tod_b200 import DescriptorMatcher, synth
+from tod_b200 import DescriptorMatcher, capi, synth
 
 pytestmark = pytest.mark.gpu
 
+KERNELS = {"popc": capi.TOD_KERNEL_POPC, "mma": capi.TOD_KERNEL_MMA}
+both_kernels = pytest.mark.parametrize("kernel", ["popc", "mma"])
 
-def run_matcher(query, descs, points, k, radius, **kw):
-    m = DescriptorMatcher(k=k, radius=radius, **kw)
+
+def run_matcher(query, descs, points, k, radius, kernel="popc", **kw):
+    m = DescriptorMatcher(k=k, radius=radius, kernel=KERNELS[kernel], **kw)
     for i, (d, p) in enumerate(zip(descs, points)):
         m.add_object("obj%d" % i, d, p)
     m.train()
     out = m.process(query)
     out["kernel"] = m.last_kernel
+    assert query.shape[0] == 0 or m.num_descriptors == 0 or out["kernel"] == kernel
     out["span_idx"] = m.spans_by_index
     m.close()
     return out
 
 
-def check_against_oracle(query, descs, points, k, radius):
-    out = run_matcher(query, descs, points, k, radius)
+def check_against_oracle(query, descs, points, k, radius, kernel="popc"):
+    out = run_matcher(query, descs, points, k, radius, kernel)
     em, ec = hk.knn_c(query, descs, k, radius)
     assert_matches_equal(out["matches"], out["counts"], em["trainIdx"], em["imgIdx"], em["distance"], ec)
     e3 = hk.gather_points3d(em, ec, points)
@@ -33,30 +37,34 @@ def check_against_oracle(query, descs, points, k, radius):
     return out
 
 
+@both_kernels
 @pytest.mark.parametrize("name", golden_names())
-def test_cv2_golden_vectors(name):
+def test_cv2_golden_vectors(name, kernel):
     g, objs = load_golden(name)
     pts = [np.zeros((o.shape[0], 3), np.float32) for o in objs]
-    out = run_matcher(g["query"], objs, pts, int(g["k"]), int(g["radius"]))
+    out = run_matcher(g["query"], objs, pts, int(g["k"]), int(g["radius"]), kernel)
     assert_matches_equal(out["matches"], out["counts"], g["trainIdx"], g["imgIdx"], g["distance"], g["counts"])
     assert out["kernel"] in ("popc", "mma")
 
 
+@both_kernels
 @pytest.mark.parametrize("nq", [1, 31, 255, 256, 257, 513, 1025, 2000])
-def test_ragged_query_counts(nq):
+def test_ragged_query_counts(nq, kernel):
     descs, points = synth.make_db(3, [700, 1300, 555], seed=11)
     q, _, _ = synth.make_queries(descs, nq, seed=nq)
-    check_against_oracle(q, descs, points, 5, 0)
+    check_against_oracle(q, descs, points, 5, 0, kernel)
 
 
+@both_kernels
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
-def test_every_k(k):
+def test_every_k(k, kernel):
     descs, points = synth.make_db(4, 2500, seed=21)
     q, _, _ = synth.make_queries(descs, 300, seed=22)
-    check_against_oracle(q, descs, points, k, 0)
+    check_against_oracle(q, descs, points, k, 0, kernel)
 
 
-def test_tie_heavy_descriptors():
+@both_kernels
+def test_tie_heavy_descriptors(kernel):
     rng = np.random.default_rng(3)
     descs = [np.zeros((n, 32), np.uint8) for n in (3000, 2000, 4100)]
     for d in descs:
@@ -64,21 +72,23 @@ def test_tie_heavy_descriptors():
     points = [rng.random((d.shape[0], 3)).astype(np.float32) for d in descs]
     q = np.zeros((200, 32), np.uint8)
     q[:, 5] = rng.integers(0, 8, 200)
-    check_against_oracle(q, descs, points, 5, 0)
-    check_against_oracle(q, descs, points, 5, 1)
+    check_against_oracle(q, descs, points, 5, 0, kernel)
+    check_against_oracle(q, descs, points, 5, 1, kernel)
 
 
-def test_config_c2_shape_k2():
+@both_kernels
+def test_config_c2_shape_k2(kernel):
     """BASELINE configs[1]: 10-object DB (50k descriptors), 1k query keypoints, k=2."""
     descs, points = synth.make_db(10, 5000, seed=synth.BASE_SEED + 1)
     q, _, _ = synth.make_queries(descs, 1000, seed=synth.BASE_SEED + 101)
-    check_against_oracle(q, descs, points, 2, 0)
+    check_against_oracle(q, descs, points, 2, 0, kernel)
 
 
-def test_radius_cut_like_detection_ork():
+@both_kernels
+def test_radius_cut_like_detection_ork(kernel):
     descs, points = synth.make_db(10, 5000, seed=31)
     q, src_obj, src_row = synth.make_queries(descs, 1000, seed=32)
-    out = check_against_oracle(q, descs, points, 5, 35)
+    out = check_against_oracle(q, descs, points, 5, 35, kernel)
     true = src_obj >= 0
     assert (out["counts"][true] >= 1).mean() > 0.99      # 4% flips ~ 10 bits < radius 35
     assert (out["counts"][~true] == 0).all()             # random clutter never gets within 35 bits
@@ -86,12 +96,13 @@ def test_radius_cut_like_detection_ork():
     assert (hit["imgIdx"] == src_obj[true]).mean() > 0.99
 
 
-def test_config_c3_full_size_2k_by_1m():
+@both_kernels
+def test_config_c3_full_size_2k_by_1m(kernel):
     """north_star size: 2k keypoints x 1M descriptors (100 objects x 10k), k=2 — bit-exact against the C oracle on a
     query subset, plus size-independent properties on all queries."""
     descs, points = synth.make_db(100, 10000, seed=synth.BASE_SEED + 2)
     q, src_obj, src_row = synth.make_queries(descs, 2000, seed=synth.BASE_SEED + 102)
-    out = run_matcher(q, descs, points, 2, 0)
+    out = run_matcher(q, descs, points, 2, 0, kernel)
     m, c = out["matches"], out["counts"]
     assert (c == 2).all()
     assert (m["distance"][:, 0] <= m["distance"][:, 1]).all()            # sortedness

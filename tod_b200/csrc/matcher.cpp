@@ -29,6 +29,13 @@ struct tod_matcher {
   bool ev_valid = false;
   int64_t shard_begin = 0, shard_rows = 0;
   DeviceBuffer d_db, d_pts, d_offsets, d_query, d_partial, d_matches, d_counts, d_pts3d;
+  // tensor-core formulation: +-1 int8 copies (256 B / descriptor) and their TMA tensor maps
+  DeviceBuffer d_db8, d_q8;
+  alignas(64) unsigned char map_db[128];
+  alignas(64) unsigned char map_q[128];
+  bool have_db8 = false;
+  const void *map_q_ptr = nullptr;
+  int64_t map_q_rows = -1;
   const char *last_kernel = "none";
 };
 
@@ -39,8 +46,31 @@ int use_device(const tod_matcher *m) {
   return TOD_OK;
 }
 
+bool use_mma(const tod_matcher *m) { return m->p.kernel == TOD_KERNEL_MMA; }
+
 int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1Plan *plan_out) {
-  if (m->p.kernel == TOD_KERNEL_MMA) return fail(TOD_ERR_INVALID, "K1 tcgen05 formulation is not built in this version");
+  if (use_mma(m)) {
+    if (!m->have_db8) return fail(TOD_ERR_STATE, "tensor-core K1 requested but the int8 database was not built");
+    tod::K1Plan plan = tod::k1_mma_plan(nq, m->shard_rows, m->sm_count);
+    TOD_CUDA(m->d_partial.reserve(size_t(plan.n_chunks) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
+    const bool realloc = size_t(nq) * 256 > m->d_q8.bytes;
+    TOD_CUDA(m->d_q8.reserve(size_t(nq) * 256));
+    if (realloc || m->map_q_ptr != m->d_q8.ptr || m->map_q_rows != nq) {
+      if (!tod::make_desc_tensor_map(m->map_q, m->d_q8.ptr, nq, tod::k1_mma_query_box_rows()))
+        return fail(TOD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the query matrix");
+      m->map_q_ptr = m->d_q8.ptr;
+      m->map_q_rows = nq;
+    }
+    TOD_CUDA(tod::launch_expand_pm1(d_query, m->d_q8.ptr, nq, st));
+    TOD_CUDA(cudaEventRecord(m->ev0, st));
+    TOD_CUDA(tod::launch_k1_mma(plan, m->map_q, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
+                                m->p.radius, m->d_partial.as<uint32_t>(), st));
+    TOD_CUDA(cudaEventRecord(m->ev1, st));
+    m->ev_valid = true;
+    m->last_kernel = "mma";
+    *plan_out = plan;
+    return TOD_OK;
+  }
   tod::K1Plan plan = tod::k1_popc_plan(nq, m->shard_rows, m->sm_count);
   TOD_CUDA(m->d_partial.reserve(size_t(plan.n_chunks) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
   TOD_CUDA(cudaEventRecord(m->ev0, st));
@@ -123,7 +153,7 @@ void tod_matcher_destroy(tod_matcher *m) {
   if (!m) return;
   cudaSetDevice(m->p.device);
   for (DeviceBuffer *b : {&m->d_db, &m->d_pts, &m->d_offsets, &m->d_query, &m->d_partial, &m->d_matches,
-                          &m->d_counts, &m->d_pts3d})
+                          &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8})
     b->release();
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -189,6 +219,16 @@ int tod_matcher_train(tod_matcher *m) {
                              cudaMemcpyHostToDevice, m->stream));
   TOD_CUDA(cudaMemcpyAsync(m->d_offsets.ptr, m->offsets.data(), m->offsets.size() * sizeof(uint32_t),
                            cudaMemcpyHostToDevice, m->stream));
+  m->have_db8 = false;
+  if (use_mma(m)) {
+    static_assert(sizeof(m->map_db) >= 128, "CUtensorMap is 128 bytes");
+    if (tod::tensor_map_bytes() > sizeof(m->map_db)) return fail(TOD_ERR_CUDA, "unexpected CUtensorMap size");
+    TOD_CUDA(m->d_db8.reserve(std::max<size_t>(size_t(m->shard_rows) * 256, 1024)));
+    TOD_CUDA(tod::launch_expand_pm1(m->d_db.ptr, m->d_db8.ptr, m->shard_rows, m->stream));
+    if (!tod::make_desc_tensor_map(m->map_db, m->d_db8.ptr, m->shard_rows, tod::k1_mma_db_box_rows()))
+      return fail(TOD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the database");
+    m->have_db8 = true;
+  }
   TOD_CUDA(cudaStreamSynchronize(m->stream));
   m->trained = true;
   return TOD_OK;

@@ -80,6 +80,17 @@ cudaError_t launch_k1_popc(const K1Plan &plan, const void *d_query, int nq, cons
                            uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial,
                            cudaStream_t stream);
 
+// K1 (tcgen05 int8 formulation, k1_mma.cu).  The database / queries are expanded to +-1 int8 (256 B per descriptor)
+// and described by TMA tensor maps (opaque CUtensorMap blobs of tensor_map_bytes() bytes, host memory).
+K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count);
+cudaError_t launch_expand_pm1(const void *d_bits, void *d_int8, int64_t rows, cudaStream_t stream);
+bool make_desc_tensor_map(void *map_out, const void *d_int8, int64_t rows, int box_rows);
+int k1_mma_query_box_rows();
+int k1_mma_db_box_rows();
+size_t tensor_map_bytes();
+cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
+                          uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, cudaStream_t stream);
+
 // Reduce n_src x nq x k key lists to nq x k keys (ascending).
 cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t *d_out,
                                cudaStream_t stream);
