@@ -14,15 +14,24 @@
 //   warp 1 / lane 0 : MMA issuer.  Per (db tile, query tile): 8 x tcgen05.mma.kind::i8 (M128 N256 K32) from shared-
 //                     memory descriptors into one of two 256-column TMEM accumulator stages, then tcgen05.commit to
 //                     the epilogue's mbarrier; a second commit frees the db ring slot.  Warp 1 also owns TMEM alloc.
-//   warps 2-5       : epilogue.  Thread = one query row (TMEM lane).  tcgen05.ld 32 columns at a time, a max-reduce
-//                     per group against the query's current threshold (fast path), and a rare divergent slow path
-//                     that inserts candidates into a register top-k of packed keys (distance << 23 | global_row).
-//                     Rows ascend within a thread, so ties never displace earlier rows (same argument as k1_popc.cu).
+//   warps 2-9       : epilogue, two warps per TMEM lane quarter (each takes 128 of the 256 accumulator columns).
+//                     Thread = one query row.  Fast path (a few dozen instructions, instruction-cache resident):
+//                     tcgen05.ld 32 columns at a time, software-pipelined over two register buffers, a VIMNMX3 tree
+//                     per group and ONE compare against the query's threshold.  Slow path (rare, warp-uniform call of
+//                     one out-of-line function): re-reads the 32 columns from TMEM and inserts candidates into the
+//                     thread's top-k list of packed keys (distance << 23 | global_row) kept in shared memory.  Rows
+//                     ascend within a thread, so ties never displace earlier rows (same argument as k1_popc.cu).
+//                     The two column halves are separate merge sources.
+//   Thresholds      : every list prunes with min(own k-th distance [strict], best k-th distance published by ANY
+//                     list of the same query [non-strict]) — the latter through one u32 per query in global memory
+//                     (atomicMin on publish, one relaxed load per tile).  Exact: a candidate farther than some list's
+//                     k-th best can never be in the global top-k; equal distances are kept for the tie-break.
 // Grid = (query groups, db chunks): CTAs that share a db chunk are adjacent in launch order, so the int8-expanded
 // database (256 B / descriptor) is read from HBM about once per frame batch and served from L2 to the other groups.
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "ptx.cuh"
 #include "tod_internal.h"
@@ -31,16 +40,31 @@ namespace tod {
 namespace {
 
 constexpr int kBlockM = 128;          // queries per tile (TMEM lanes)
-constexpr int kBlockN = 256;          // db rows per tile (TMEM columns of one accumulator stage)
-constexpr int kQT = 2;                // resident query tiles per CTA
-constexpr int kBStages = 2;           // db ring depth
-constexpr int kAccStages = 2;         // TMEM accumulator stages (2 x 256 = all 512 columns)
-constexpr int kThreadsMma = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+#ifndef TOD_MMA_BLOCK_N
+#define TOD_MMA_BLOCK_N 128
+#endif
+#ifndef TOD_MMA_BSTAGES
+#define TOD_MMA_BSTAGES 5
+#endif
+constexpr int kBlockN = TOD_MMA_BLOCK_N;  // db rows per tile (TMEM columns of one accumulator stage)
+#ifndef TOD_MMA_QT
+#define TOD_MMA_QT 4
+#endif
+constexpr int kQT = TOD_MMA_QT;       // resident query tiles per CTA (in TMEM)
+constexpr int kBStages = TOD_MMA_BSTAGES;  // db ring depth
+constexpr int kAColsPerTile = 64;      // a 128 x 256-byte query tile in TMEM: 128 lanes x 64 32-bit columns
+constexpr int kACols = kQT * kAColsPerTile;               // TMEM columns [0, kACols) hold the resident queries
+constexpr int kAccStages = (512 - kACols) / kBlockN;      // accumulator stages in the remaining columns
+static_assert(kBlockN % 64 == 0 && kBlockN <= 256 && kAccStages >= 2, "unsupported tile width");
+constexpr int kEpiWarps = 8;
+constexpr int kThreadsMma = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiCols = kBlockN / (kEpiWarps / 4);  // accumulator columns per epilogue warp (128)
 constexpr int kKBytes = 256;          // int8 elements (= bytes) per descriptor
 constexpr int kSwizzleBytes = 128;    // inner TMA box / swizzle span
 constexpr int kATileBytes = kBlockM * kKBytes;   // 32 KB
 constexpr int kBTileBytes = kBlockN * kKBytes;   // 64 KB
-constexpr int kSmemMma = kQT * kATileBytes + kBStages * kBTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kListWords = kQT * 2 * TOD_MAX_K * kBlockM;  // top-k lists: [j][half][slot][row]
+constexpr int kSmemMma = kBStages * kBTileBytes + 1024 /*align*/ + 256 /*barriers*/ + kListWords * 4;
 constexpr uint32_t kSpinLimit = 1u << 26;  // bounded waits: a protocol bug traps instead of hanging the GPU
 
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
@@ -82,6 +106,29 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t a_desc, uint64
       : "memory");
 }
 
+// A operand from TMEM (TS form): smem bandwidth is then spent on the streamed db tile only.
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(kInstrDesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ptx::smem_u32(bar))
                : "memory");
@@ -104,15 +151,51 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-template <int K>
+// Slow path of the epilogue, one copy, out of line (keeps the hot loop small enough for the instruction cache).
+// Called warp-uniformly: re-reads 32 accumulator columns (tcgen05.ld is .sync.aligned) and inserts every candidate
+// of this thread's query into its sorted top-k list in shared memory.  Returns the new dot-product threshold.
+//   list[i * kBlockM] (i < k) : ascending packed keys;   n_valid : columns of this group that are real db rows
+__device__ __noinline__ int k1_mma_slow_scan(uint32_t taddr, uint32_t *list, int k, uint32_t thr_init, uint32_t grow,
+                                             int n_valid, int thr_dot, uint32_t *gthr) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+  tmem_wait_ld();
+  bool inserted = false;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int dot = int(v[i]);
+    if (i < n_valid && dot > thr_dot) {
+      const uint32_t dist = uint32_t(256 - dot) >> 1;
+      uint32_t key = (dist << kKeyRowBits) | (grow + uint32_t(i));
+      // sorted insert: the new key displaces the worst entry and sinks to its place
+      int pos = k - 1;
+      while (pos > 0 && list[(pos - 1) * kBlockM] > key) {
+        list[pos * kBlockM] = list[(pos - 1) * kBlockM];
+        --pos;
+      }
+      list[pos * kBlockM] = key;
+      const uint32_t kth = min(thr_init, list[(k - 1) * kBlockM] >> kKeyRowBits);  // strict bound of this list
+      thr_dot = max(thr_dot, 256 - 2 * int(kth));
+      inserted = true;
+    }
+  }
+  if (inserted && gthr) {
+    const uint32_t kth = list[(k - 1) * kBlockM] >> kKeyRowBits;   // 511 while the list is not full
+    if (kth < 511u) {
+      const uint32_t old = atomicMin(gthr, kth);                   // publish; non-strict bound for everyone else
+      thr_dot = max(thr_dot, 255 - 2 * int(min(old, kth)));
+    }
+  }
+  return thr_dot;
+}
+
 __global__ void __launch_bounds__(kThreadsMma, 1)
-k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, int nq,
-              int shard_rows, uint32_t global_row_base, int rows_per_chunk, uint32_t thr_init,
-              uint32_t *__restrict__ partial) {
+k1_mma_kernel(const uint4 *__restrict__ q8, const __grid_constant__ CUtensorMap map_db, int nq,
+              int shard_rows, uint32_t global_row_base, int rows_per_chunk, uint32_t thr_init, int K,
+              uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, int debug_mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *a_smem = smem;                                   // [kQT][2 k-halves][128 rows][128 B]
-  uint8_t *b_smem = smem + kQT * kATileBytes;               // [kBStages][2 k-halves][256 rows][128 B]
+  uint8_t *b_smem = smem;                                   // [kBStages][2 k-halves][kBlockN rows][128 B]
   uint64_t *bars = reinterpret_cast<uint64_t *>(b_smem + kBStages * kBTileBytes);
   uint64_t *a_full = bars;                                  // 1
   uint64_t *b_full = bars + 1;                              // kBStages
@@ -120,6 +203,7 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   uint64_t *acc_full = b_empty + kBStages;                  // kAccStages
   uint64_t *acc_empty = acc_full + kAccStages;              // kAccStages
   uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(acc_empty + kAccStages);
+  uint32_t *lists = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bars) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,14 +215,14 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const int n_tiles = (row1 - row0 + kBlockN - 1) / kBlockN;
 
   if (threadIdx.x == 0) {
-    ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_full, 4);  // the four warps that write the query tiles into TMEM
     for (int s = 0; s < kBStages; ++s) {
       ptx::mbar_init(&b_full[s], 1);
       ptx::mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
-      ptx::mbar_init(&acc_empty[s], 4);  // one arrival per epilogue warp
+      ptx::mbar_init(&acc_empty[s], kEpiWarps);  // one arrival per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -156,12 +240,8 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(a_full, kQT * kATileBytes);
-      for (int j = 0; j < kQT; ++j)
-        for (int kh = 0; kh < 2; ++kh)
-          tma_load_2d(a_smem + j * kATileBytes + kh * (kBlockM * kSwizzleBytes), &map_q, kh * kSwizzleBytes,
-                      q_row0 + j * kBlockM, a_full);
       for (int t = 0; t < n_tiles; ++t) {
+        if ((debug_mode & 2) && t >= kBStages) break;  // profiling only: no db streaming (results are garbage)
         const int s = t % kBStages;
         mbar_wait_bounded(&b_empty[s], ((t / kBStages) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&b_full[s], kBTileBytes);
@@ -178,22 +258,21 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       uint32_t acc_iter = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t % kBStages;
-        mbar_wait_bounded(&b_full[s], (t / kBStages) & 1);
+        if (!((debug_mode & 2) && t >= kBStages)) mbar_wait_bounded(&b_full[s], (t / kBStages) & 1);
         tc_fence_after();
         for (int j = 0; j < kQT; ++j, ++acc_iter) {
           const uint32_t as = acc_iter % kAccStages;
           mbar_wait_bounded(&acc_empty[as], ((acc_iter / kAccStages) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * kBlockN;
+          const uint32_t d_tmem = tmem_base + kACols + as * kBlockN;
+          const uint32_t a_tmem = tmem_base + j * kAColsPerTile;  // lane 0, 8 columns (32 bytes of K) per step
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh) {
-            const uint64_t a_desc =
-                make_kmajor_sw128_desc(ptx::smem_u32(a_smem + j * kATileBytes + kh * (kBlockM * kSwizzleBytes)));
             const uint64_t b_desc =
                 make_kmajor_sw128_desc(ptx::smem_u32(b_smem + s * kBTileBytes + kh * (kBlockN * kSwizzleBytes)));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)  // 32-byte K steps inside the 128-byte swizzle span: +2 in 16-byte units
-              umma_i8(d_tmem, a_desc + uint64_t(ks * 2), b_desc + uint64_t(ks * 2), (kh | ks) ? 1u : 0u);
+              umma_i8_ts(d_tmem, a_tmem + uint32_t((kh * 4 + ks) * 8), b_desc + uint64_t(ks * 2), (kh | ks) ? 1u : 0u);
           }
           umma_commit(&acc_full[as]);  // accumulator ready for the epilogue (implies fence::before_thread_sync)
         }
@@ -201,17 +280,60 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       }
     }
   } else {
-    // ===================================== epilogue: warps 2..5 =====================================
+    // ===================================== epilogue: warps 2..9 =====================================
     const int quarter = warp & 3;                         // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int half = (warp - 2) >> 2;                     // which 128-column half of the accumulator
     const int row_in_tile = quarter * 32 + lane;
-    uint32_t best[kQT][K];
+    const int col0 = half * kEpiCols;
     int thr_dot[kQT];
+    uint32_t g_next[kQT];                                 // shared bound, loaded one tile ahead of its use
+    uint32_t *my_list[kQT];
+    uint32_t *my_gthr[kQT];
 #pragma unroll
     for (int j = 0; j < kQT; ++j) {
-#pragma unroll
-      for (int i = 0; i < K; ++i) best[j][i] = kKeyEmpty;
+      my_list[j] = lists + size_t((j * 2 + half) * TOD_MAX_K) * kBlockM + row_in_tile;
+      for (int i = 0; i < K; ++i) my_list[j][i * kBlockM] = kKeyEmpty;
       thr_dot[j] = 256 - 2 * int(thr_init);               // distance < thr  <=>  dot > 256 - 2 thr
+      const int qi = q_row0 + j * kBlockM + row_in_tile;
+      my_gthr[j] = (qi < nq && !(debug_mode & 16)) ? gthr + qi : nullptr;
+      g_next[j] = 511u;
     }
+
+    if (half == 0) {
+      // Resident query tiles -> TMEM (the A operand of the TS-form MMA): lane = query row, column c = bytes
+      // [4c, 4c+4) of the row's 256 +-1 values.  Rows past nq are zero (their results are never written).
+#pragma unroll
+      for (int j = 0; j < kQT; ++j) {
+        const int qi = q_row0 + j * kBlockM + row_in_tile;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t w[32];
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (qi < nq) u = __ldg(q8 + size_t(qi) * 16 + h * 8 + x);
+            w[4 * x] = u.x; w[4 * x + 1] = u.y; w[4 * x + 2] = u.z; w[4 * x + 3] = u.w;
+          }
+          tmem_st32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(j * kAColsPerTile + h * 32), w);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_full);
+    }
+
+    // max over 32 accumulator columns (VIMNMX3 tree, depth 4)
+    auto max32 = [](const uint32_t (&v)[32]) -> int {
+      int r[11];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) r[i] = __vimax3_s32(int(v[3 * i]), int(v[3 * i + 1]), int(v[3 * i + 2]));
+      r[10] = max(int(v[30]), int(v[31]));
+      const int a = __vimax3_s32(r[0], r[1], r[2]), b = __vimax3_s32(r[3], r[4], r[5]),
+                c = __vimax3_s32(r[6], r[7], r[8]), d = max(r[9], r[10]);
+      return max(__vimax3_s32(a, b, c), d);
+    };
+
     uint32_t acc_iter = 0;
     for (int t = 0; t < n_tiles; ++t) {
       const int cols_valid = min(kBlockN, (row1 - row0) - t * kBlockN);
@@ -221,40 +343,25 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const uint32_t as = acc_iter % kAccStages;
         mbar_wait_bounded(&acc_full[as], (acc_iter / kAccStages) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * kBlockN;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN; c += 32) {
-          if (c >= cols_valid) break;
-          uint32_t v[32];
-          tmem_ld32(taddr + uint32_t(c), v);
+        // shared bound of this query: use the value loaded during the previous tile, start the next load now
+        thr_dot[j] = max(thr_dot[j], 255 - 2 * int(g_next[j]));
+        if (my_gthr[j]) g_next[j] = *reinterpret_cast<volatile uint32_t *>(my_gthr[j]);
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kACols + as * kBlockN + uint32_t(col0);
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+#pragma unroll
+        for (int cc = 0; cc < kEpiCols / 32; ++cc) {  // software pipeline: next load in flight while scanning
+          uint32_t (&cur)[32] = (cc & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
           tmem_wait_ld();
-          if (c + 32 > cols_valid) {  // ragged end of the shard: TMA zero-filled rows must never match
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c + i >= cols_valid) v[i] = 0x80000000u;
-          }
-          int m = int(v[0]);
-#pragma unroll
-          for (int i = 1; i < 32; ++i) m = max(m, int(v[i]));
-          if (m > thr_dot[j]) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int dot = int(v[i]);
-              if (dot > thr_dot[j]) {
-                const uint32_t dist = uint32_t(256 - dot) >> 1;
-                best[j][K - 1] = (dist << kKeyRowBits) | (grow0 + uint32_t(c + i));
-#pragma unroll
-                for (int x = K - 1; x > 0; --x) {
-                  const uint32_t lo = min(best[j][x - 1], best[j][x]);
-                  const uint32_t hi = max(best[j][x - 1], best[j][x]);
-                  best[j][x - 1] = lo;
-                  best[j][x] = hi;
-                }
-                thr_dot[j] = 256 - 2 * int(min(thr_init, best[j][K - 1] >> kKeyRowBits));
-              }
-            }
-          }
+          if (cc + 1 < kEpiCols / 32) tmem_ld32(taddr + uint32_t(32 * (cc + 1)), nxt);
+          const int col = col0 + 32 * cc;
+          const bool hit = !(debug_mode & 4) && col < cols_valid && max32(cur) > thr_dot[j];
+          if (__any_sync(0xffffffffu, hit) && !(debug_mode & 8))
+            thr_dot[j] = k1_mma_slow_scan(taddr + uint32_t(32 * cc), my_list[j], K, thr_init, grow0 + uint32_t(col),
+                                          min(32, cols_valid - col), thr_dot[j], my_gthr[j]);
         }
+        if (debug_mode & 4) thr_dot[j] = max(thr_dot[j], int(va[0] ^ vb[7]) == 0x7fffffff ? 1 : 0);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
@@ -264,9 +371,9 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     for (int j = 0; j < kQT; ++j) {
       const int qi = q_row0 + j * kBlockM + row_in_tile;
       if (qi < nq) {
-        uint32_t *o = partial + (size_t(chunk) * nq + qi) * K;
-#pragma unroll
-        for (int i = 0; i < K; ++i) o[i] = best[j][i];
+        // the two column halves are independent candidate lists: sources 2*chunk and 2*chunk + 1 of the merge
+        uint32_t *o = partial + (size_t(chunk * 2 + half) * nq + qi) * K;
+        for (int i = 0; i < K; ++i) o[i] = my_list[j][i * kBlockM];
       }
     }
   }
@@ -306,20 +413,30 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-template <int K>
-cudaError_t launch_mma_k(const K1Plan &plan, const CUtensorMap &map_q, const CUtensorMap &map_db, int nq, int64_t rows,
-                         uint32_t base, uint32_t thr_init, uint32_t *partial, cudaStream_t stream) {
+cudaError_t launch_mma_k(const K1Plan &plan, const void *d_q8, const CUtensorMap &map_db, int nq, int64_t rows,
+                         uint32_t base, uint32_t thr_init, int k, uint32_t *partial, uint32_t *gthr,
+                         cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k1_mma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMma);
+    cudaError_t e = cudaFuncSetAttribute(k1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMma);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  static const int debug_mode = [] {  // TOD_K1_DEBUG_MODE: profiling knob, never set in production
+    const char *e = getenv("TOD_K1_DEBUG_MODE");
+    return e ? atoi(e) : 0;
+  }();
   dim3 grid(plan.n_qtiles, plan.n_chunks);
-  k1_mma_kernel<K><<<grid, kThreadsMma, kSmemMma, stream>>>(map_q, map_db, nq, int(rows), base, plan.rows_per_chunk,
-                                                            thr_init, partial);
+  k1_mma_kernel<<<grid, kThreadsMma, kSmemMma, stream>>>(static_cast<const uint4 *>(d_q8), map_db, nq, int(rows), base, plan.rows_per_chunk,
+                                                         thr_init, k, partial, gthr, debug_mode);
   count_launch();
   return cudaGetLastError();
+}
+
+// bits -> +-1 int8 (see expand_pm1_kernel) fused with the reset of the per-query shared thresholds
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *__restrict__ p, uint32_t v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 }  // namespace
@@ -330,12 +447,25 @@ K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count) {
   p.q_tile = kQT * kBlockM;
   p.n_qtiles = std::max(1, (nq + p.q_tile - 1) / p.q_tile);
   const int64_t max_chunks = std::max<int64_t>(1, (shard_rows + kBlockN - 1) / kBlockN);
-  int64_t target = std::max<int64_t>(1, sm_count / p.n_qtiles);  // one CTA per SM, at most one wave
-  target = std::min(target, max_chunks);
-  int64_t rpc = (shard_rows + target - 1) / target;
+  // One CTA per SM.  Pick the number of db chunks that fills whole waves of sm_count CTAs best (>= 97% counts as
+  // full; fewer chunks preferred: each chunk restarts the top-k thresholds and adds merge sources).
+  int64_t best_c = 1;
+  double best_eff = 0.0;
+  const int64_t c_hi = std::min<int64_t>(max_chunks, std::max<int64_t>(16, (4LL * sm_count) / p.n_qtiles));
+  for (int64_t c = 1; c <= std::max<int64_t>(1, c_hi); ++c) {
+    const int64_t ctas = c * p.n_qtiles;
+    const int64_t waves = (ctas + sm_count - 1) / sm_count;
+    const double eff = double(ctas) / double(waves * sm_count);
+    if (eff > best_eff + 1e-9 && best_eff < 0.97) {
+      best_eff = eff;
+      best_c = c;
+    }
+  }
+  int64_t rpc = (shard_rows + best_c - 1) / best_c;
   rpc = std::max<int64_t>(kBlockN, (rpc + kBlockN - 1) / kBlockN * kBlockN);
   p.rows_per_chunk = int(rpc);
   p.n_chunks = int(std::max<int64_t>(1, (shard_rows + rpc - 1) / rpc));
+  p.n_sources = p.n_chunks * (kEpiWarps / 4);
   return p;
 }
 
@@ -366,22 +496,20 @@ int k1_mma_query_box_rows() { return kBlockM; }
 int k1_mma_db_box_rows() { return kBlockN; }
 size_t tensor_map_bytes() { return sizeof(CUtensorMap); }
 
-cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
-                          uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, cudaStream_t stream) {
+cudaError_t launch_fill_u32(uint32_t *d_p, uint32_t v, int n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  fill_u32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_p, v, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k1_mma(const K1Plan &plan, const void *d_q8, const void *map_db, int nq, int64_t shard_rows,
+                          uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
+                          cudaStream_t stream) {
+  if (k < 1 || k > TOD_MAX_K) return cudaErrorInvalidValue;
   const uint32_t thr_init = radius ? min(radius + 1u, 511u) : 511u;
-  const CUtensorMap &mq = *static_cast<const CUtensorMap *>(map_q);
   const CUtensorMap &md = *static_cast<const CUtensorMap *>(map_db);
-  switch (k) {
-    case 1: return launch_mma_k<1>(plan, mq, md, nq, shard_rows, global_row_base, thr_init, d_partial, stream);
-    case 2: return launch_mma_k<2>(plan, mq, md, nq, shard_rows, global_row_base, thr_init, d_partial, stream);
-    case 3: return launch_mma_k<3>(plan, mq, md, nq, shard_rows, global_row_base, thr_init, d_partial, stream);
-    case 4: return launch_mma_k<4>(plan, mq, md, nq, shard_rows, global_row_base, thr_init, d_partial, stream);
-    case 5: return launch_mma_k<5>(plan, mq, md, nq, shard_rows, global_row_base, thr_init, d_partial, stream);
-    case 6: return launch_mma_k<6>(plan, mq, md, nq, shard_rows, global_row_base, thr_init, d_partial, stream);
-    case 7: return launch_mma_k<7>(plan, mq, md, nq, shard_rows, global_row_base, thr_init, d_partial, stream);
-    case 8: return launch_mma_k<8>(plan, mq, md, nq, shard_rows, global_row_base, thr_init, d_partial, stream);
-    default: return cudaErrorInvalidValue;
-  }
+  return launch_mma_k(plan, d_q8, md, nq, shard_rows, global_row_base, thr_init, k, d_partial, d_gthr, stream);
 }
 
 }  // namespace tod

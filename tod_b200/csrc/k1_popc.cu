@@ -160,6 +160,7 @@ K1Plan k1_popc_plan(int nq, int64_t shard_rows, int sm_count) {
   p.rows_per_chunk = int(rpc);
   p.n_chunks = int((shard_rows + rpc - 1) / rpc);
   if (p.n_chunks < 1) p.n_chunks = 1;
+  p.n_sources = p.n_chunks;
   return p;
 }
 

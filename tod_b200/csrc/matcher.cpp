@@ -30,12 +30,9 @@ struct tod_matcher {
   int64_t shard_begin = 0, shard_rows = 0;
   DeviceBuffer d_db, d_pts, d_offsets, d_query, d_partial, d_matches, d_counts, d_pts3d;
   // tensor-core formulation: +-1 int8 copies (256 B / descriptor) and their TMA tensor maps
-  DeviceBuffer d_db8, d_q8;
+  DeviceBuffer d_db8, d_q8, d_gthr;
   alignas(64) unsigned char map_db[128];
-  alignas(64) unsigned char map_q[128];
   bool have_db8 = false;
-  const void *map_q_ptr = nullptr;
-  int64_t map_q_rows = -1;
   const char *last_kernel = "none";
 };
 
@@ -52,19 +49,14 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
   if (use_mma(m)) {
     if (!m->have_db8) return fail(TOD_ERR_STATE, "tensor-core K1 requested but the int8 database was not built");
     tod::K1Plan plan = tod::k1_mma_plan(nq, m->shard_rows, m->sm_count);
-    TOD_CUDA(m->d_partial.reserve(size_t(plan.n_chunks) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
-    const bool realloc = size_t(nq) * 256 > m->d_q8.bytes;
+    TOD_CUDA(m->d_partial.reserve(size_t(plan.n_sources) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
     TOD_CUDA(m->d_q8.reserve(size_t(nq) * 256));
-    if (realloc || m->map_q_ptr != m->d_q8.ptr || m->map_q_rows != nq) {
-      if (!tod::make_desc_tensor_map(m->map_q, m->d_q8.ptr, nq, tod::k1_mma_query_box_rows()))
-        return fail(TOD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the query matrix");
-      m->map_q_ptr = m->d_q8.ptr;
-      m->map_q_rows = nq;
-    }
+    TOD_CUDA(m->d_gthr.reserve(size_t(nq) * sizeof(uint32_t)));
     TOD_CUDA(tod::launch_expand_pm1(d_query, m->d_q8.ptr, nq, st));
+    TOD_CUDA(tod::launch_fill_u32(m->d_gthr.as<uint32_t>(), 511u, nq, st));
     TOD_CUDA(cudaEventRecord(m->ev0, st));
-    TOD_CUDA(tod::launch_k1_mma(plan, m->map_q, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
-                                m->p.radius, m->d_partial.as<uint32_t>(), st));
+    TOD_CUDA(tod::launch_k1_mma(plan, m->d_q8.ptr, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
+                                m->p.radius, m->d_partial.as<uint32_t>(), m->d_gthr.as<uint32_t>(), st));
     TOD_CUDA(cudaEventRecord(m->ev1, st));
     m->ev_valid = true;
     m->last_kernel = "mma";
@@ -72,7 +64,7 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
     return TOD_OK;
   }
   tod::K1Plan plan = tod::k1_popc_plan(nq, m->shard_rows, m->sm_count);
-  TOD_CUDA(m->d_partial.reserve(size_t(plan.n_chunks) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
+  TOD_CUDA(m->d_partial.reserve(size_t(plan.n_sources) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
   TOD_CUDA(cudaEventRecord(m->ev0, st));
   TOD_CUDA(tod::launch_k1_popc(plan, d_query, nq, m->d_db.ptr, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
                                m->p.radius, m->d_partial.as<uint32_t>(), st));
@@ -153,7 +145,7 @@ void tod_matcher_destroy(tod_matcher *m) {
   if (!m) return;
   cudaSetDevice(m->p.device);
   for (DeviceBuffer *b : {&m->d_db, &m->d_pts, &m->d_offsets, &m->d_query, &m->d_partial, &m->d_matches,
-                          &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8})
+                          &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8, &m->d_gthr})
     b->release();
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -263,7 +255,7 @@ int tod_matcher_knn(tod_matcher *m, const uint8_t *descriptors, int32_t nq, tod_
   TOD_CUDA(cudaMemcpyAsync(m->d_query.ptr, descriptors, size_t(nq) * 32, cudaMemcpyHostToDevice, m->stream));
   tod::K1Plan plan;
   if (int rc = run_k1(m, m->d_query.ptr, nq, m->stream, &plan)) return rc;
-  TOD_CUDA(tod::launch_finalize_matches(m->d_partial.as<uint32_t>(), plan.n_chunks, nq, k, m->p.radius,
+  TOD_CUDA(tod::launch_finalize_matches(m->d_partial.as<uint32_t>(), plan.n_sources, nq, k, m->p.radius,
                                         m->d_offsets.as<uint32_t>(), int(m->ids.size()), m->d_pts.as<float>(),
                                         m->d_matches.as<tod_match>(), m->d_counts.as<int32_t>(),
                                         points3d ? m->d_pts3d.as<float>() : nullptr, m->stream));
@@ -285,7 +277,7 @@ int tod_matcher_knn_keys_device(tod_matcher *m, const void *d_descriptors, int32
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : m->stream;
   tod::K1Plan plan;
   if (int rc = run_k1(m, d_descriptors, nq, st, &plan)) return rc;
-  TOD_CUDA(tod::launch_reduce_keys(m->d_partial.as<uint32_t>(), plan.n_chunks, nq, m->p.k, d_keys, st));
+  TOD_CUDA(tod::launch_reduce_keys(m->d_partial.as<uint32_t>(), plan.n_sources, nq, m->p.k, d_keys, st));
   return TOD_OK;
 }
 

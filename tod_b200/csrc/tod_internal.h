@@ -72,6 +72,7 @@ struct K1Plan {
   int n_qtiles;
   int rows_per_chunk;  // multiple of the smem tile
   int n_chunks;
+  int n_sources;       // candidate lists per query written to `partial` (merge fan-in)
 };
 K1Plan k1_popc_plan(int nq, int64_t shard_rows, int sm_count);
 
@@ -88,8 +89,11 @@ bool make_desc_tensor_map(void *map_out, const void *d_int8, int64_t rows, int b
 int k1_mma_query_box_rows();
 int k1_mma_db_box_rows();
 size_t tensor_map_bytes();
-cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
-                          uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, cudaStream_t stream);
+// d_gthr: nq u32 shared per-query bounds, must hold 511 (no bound) before the launch (launch_fill_u32).
+cudaError_t launch_k1_mma(const K1Plan &plan, const void *d_q8, const void *map_db, int nq, int64_t shard_rows,
+                          uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
+                          cudaStream_t stream);
+cudaError_t launch_fill_u32(uint32_t *d_p, uint32_t v, int n, cudaStream_t stream);
 
 // Reduce n_src x nq x k key lists to nq x k keys (ascending).
 cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t *d_out,

@@ -27,6 +27,9 @@ __global__ void __launch_bounds__(1024) rate_kernel(uint32_t *out, uint32_t seed
       if (OP == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));  // LOP3
       if (OP == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b)); // IADD
       if (OP == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));      // IMAD
+      if (OP == 4) a[i] = __vimax3_s32(int(a[i]), int(b + it), int(c - i));                      // VIMNMX3
+      if (OP == 5) a[i] = max(int(a[i]), int(b + it));                                           // VIMNMX
+      if (OP == 6) a[i] = __vimax3_s16x2(a[i], b + it, c - i);                                   // VIMNMX3.S16x2
     }
   }
   uint32_t s = 0;
@@ -68,8 +71,8 @@ int main() {
   const int sms = prop.multiProcessorCount;
   const int blocks = sms * 2, threads = 1024;
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_max_mhz\": %.0f", prop.name, sms, clock_khz / 1000.0);
-  const char *names[4] = {"popc", "lop3", "iadd", "imad"};
-  for (int op = 0; op < 4; ++op) {
+  const char *names[7] = {"popc", "lop3", "iadd", "imad", "vimnmx3", "vimnmx", "vimnmx3_s16x2"};
+  for (int op = 0; op < 7; ++op) {
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
       CK(cudaEventRecord(e0));
@@ -77,6 +80,9 @@ int main() {
       if (op == 1) rate_kernel<1><<<blocks, threads>>>(d_out, 12345u + rep);
       if (op == 2) rate_kernel<2><<<blocks, threads>>>(d_out, 12345u + rep);
       if (op == 3) rate_kernel<3><<<blocks, threads>>>(d_out, 12345u + rep);
+      if (op == 4) rate_kernel<4><<<blocks, threads>>>(d_out, 12345u + rep);
+      if (op == 5) rate_kernel<5><<<blocks, threads>>>(d_out, 12345u + rep);
+      if (op == 6) rate_kernel<6><<<blocks, threads>>>(d_out, 12345u + rep);
       CK(cudaEventRecord(e1));
       CK(cudaEventSynchronize(e1));
       float ms;
