@@ -1,4 +1,4 @@
-// K1, tensor-core formulation: exact Hamming k-NN as a dense int8 contraction on tcgen05 (sm_100a).
+// K1, tensor-core formulation: exact Hamming k-NN as a dense int8 contraction on tcgen05 (sm_100a), CTA pairs.
 //
 // Replaces `matcher_->knnMatch(descriptors, matches, 5)` at src/detection/DescriptorMatcher.cpp:211 of the reference
 // (cv::BFMatcher(NORM_HAMMING) semantics, see oracle/hamming_knn.py) — same contract and same packed-key output as
@@ -7,14 +7,17 @@
 // Identity: with every descriptor bit b mapped to the int8 value (1 - 2b), a . b = 256 - 2 * Hamming(a, b); the int32
 // accumulation is exact, so distances are bit-identical to XOR+POPC.
 //
-// Structure (one CTA per SM, 192 threads, warp-specialised):
-//   warp 0 / lane 0 : TMA producer.  Loads the CTA's QT resident query tiles (128 x 256 B each, once) and streams
-//                     database tiles (256 rows x 256 B) through a 2-stage shared-memory ring, SWIZZLE_128B boxes of
-//                     128 B x rows, completion on mbarriers (cp.async.bulk.tensor -> UTMALDG).
-//   warp 1 / lane 0 : MMA issuer.  Per (db tile, query tile): 8 x tcgen05.mma.kind::i8 (M128 N256 K32) from shared-
-//                     memory descriptors into one of two 256-column TMEM accumulator stages, then tcgen05.commit to
-//                     the epilogue's mbarrier; a second commit frees the db ring slot.  Warp 1 also owns TMEM alloc.
-//   warps 2-9       : epilogue, two warps per TMEM lane quarter (each takes 128 of the 256 accumulator columns).
+// Structure — a cluster of 2 CTAs (one per SM of a TPC) runs tcgen05.mma.cta_group::2 tiles of M = 256 queries
+// (128 per CTA) x N = 256 database rows (128 per CTA) x K = 256:
+//   warp 0 / lane 0 : TMA producer (both CTAs).  Loads the CTA's own QT resident query tiles once and streams ITS
+//                     128-row half of every database tile through a 4-stage shared-memory ring (SWIZZLE_128B boxes of
+//                     128 B x 128 rows, cp.async.bulk.tensor.cta_group::2 -> UTMALDG, completion on the LEADER's
+//                     mbarrier).  A fetched database row is thus shared by 512 queries: 0.5 byte of L2 traffic per
+//                     comparison, which is what lets the tensor pipe run near its peak (DESIGN.md, K1 roofline).
+//   warp 1 / lane 0 : MMA issuer (leader CTA only).  Per (db tile, query tile): 8 x tcgen05.mma.cta_group::2.kind::i8
+//                     (M256 N256 K32) into one of two 256-column TMEM accumulator stages; tcgen05.commit multicast to
+//                     both CTAs' mbarriers (accumulator ready / ring slot free).  Warp 1 of each CTA owns TMEM alloc.
+//   warps 2-9       : epilogue (both CTAs), two warps per TMEM lane quarter (each takes 128 of the 256 columns).
 //                     Thread = one query row.  Fast path (a few dozen instructions, instruction-cache resident):
 //                     tcgen05.ld 32 columns at a time, software-pipelined over two register buffers, a VIMNMX3 tree
 //                     per group and ONE compare against the query's threshold.  Slow path (rare, warp-uniform call of
@@ -26,8 +29,7 @@
 //                     list of the same query [non-strict]) — the latter through one u32 per query in global memory
 //                     (atomicMin on publish, one relaxed load per tile).  Exact: a candidate farther than some list's
 //                     k-th best can never be in the global top-k; equal distances are kept for the tie-break.
-// Grid = (query groups, db chunks): CTAs that share a db chunk are adjacent in launch order, so the int8-expanded
-// database (256 B / descriptor) is read from HBM about once per frame batch and served from L2 to the other groups.
+// Grid = (2 x query-group pairs, db chunks), cluster (2,1,1).
 #include <cuda.h>
 
 #include <algorithm>
@@ -39,32 +41,25 @@
 namespace tod {
 namespace {
 
-constexpr int kBlockM = 128;          // queries per tile (TMEM lanes)
-#ifndef TOD_MMA_BLOCK_N
-#define TOD_MMA_BLOCK_N 128
+#ifndef TOD_MMA_PAIR
+#define TOD_MMA_PAIR 0                // 1: CTA pairs (tcgen05 cta_group::2), 0: one CTA per tile (cta_group::1)
 #endif
-#ifndef TOD_MMA_BSTAGES
-#define TOD_MMA_BSTAGES 5
-#endif
-constexpr int kBlockN = TOD_MMA_BLOCK_N;  // db rows per tile (TMEM columns of one accumulator stage)
-#ifndef TOD_MMA_QT
-#define TOD_MMA_QT 4
-#endif
-constexpr int kQT = TOD_MMA_QT;       // resident query tiles per CTA (in TMEM)
-constexpr int kBStages = TOD_MMA_BSTAGES;  // db ring depth
-constexpr int kAColsPerTile = 64;      // a 128 x 256-byte query tile in TMEM: 128 lanes x 64 32-bit columns
-constexpr int kACols = kQT * kAColsPerTile;               // TMEM columns [0, kACols) hold the resident queries
-constexpr int kAccStages = (512 - kACols) / kBlockN;      // accumulator stages in the remaining columns
-static_assert(kBlockN % 64 == 0 && kBlockN <= 256 && kAccStages >= 2, "unsupported tile width");
+constexpr int kCtas = TOD_MMA_PAIR ? 2 : 1;   // CTAs cooperating on one MMA tile
+constexpr int kBlockM = 128;          // queries per tile and CTA (TMEM lanes)
+constexpr int kBlockN = 256;          // db rows per MMA tile (TMEM columns of one accumulator stage)
+constexpr int kHalfN = kBlockN / kCtas;  // db rows each CTA stages per tile
+constexpr int kQT = 2;                // resident query tiles per CTA
+constexpr int kBStages = TOD_MMA_PAIR ? 4 : 2;  // db ring depth per CTA (4 x 32 KB or 2 x 64 KB)
+constexpr int kAccStages = 2;         // TMEM accumulator stages (2 x 256 = all 512 columns)
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsMma = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpiCols = kBlockN / (kEpiWarps / 4);  // accumulator columns per epilogue warp (128)
 constexpr int kKBytes = 256;          // int8 elements (= bytes) per descriptor
 constexpr int kSwizzleBytes = 128;    // inner TMA box / swizzle span
 constexpr int kATileBytes = kBlockM * kKBytes;   // 32 KB
-constexpr int kBTileBytes = kBlockN * kKBytes;   // 64 KB
+constexpr int kBHalfBytes = kHalfN * kKBytes;    // 32 KB
 constexpr int kListWords = kQT * 2 * TOD_MAX_K * kBlockM;  // top-k lists: [j][half][slot][row]
-constexpr int kSmemMma = kBStages * kBTileBytes + 1024 /*align*/ + 256 /*barriers*/ + kListWords * 4;
+constexpr int kSmemMma = kQT * kATileBytes + kBStages * kBHalfBytes + 1024 /*align*/ + 256 /*barriers*/ + kListWords * 4;
 constexpr uint32_t kSpinLimit = 1u << 26;  // bounded waits: a protocol bug traps instead of hanging the GPU
 
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
@@ -74,12 +69,69 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
   }
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+#if TOD_MMA_PAIR
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+#else
+  return 0u;
+#endif
+}
+
+// all threads of the CTA (single mode) or of both CTAs of the pair
+__device__ __forceinline__ void cluster_sync_all() {
+#if TOD_MMA_PAIR
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
+  __syncthreads();
+#endif
+}
+
+// shared::cluster address of `local` (a shared::cta address of this CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+#if TOD_MMA_PAIR
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+#else
+  return local;  // a shared::cta address is a valid shared::cluster address of the executing CTA
+#endif
+}
+
+// Arrive on a barrier given by its shared::cluster address (own CTA or the pair's leader).  Default semantics
+// (.release.cta) on purpose: a cluster-scope release costs hundreds of cycles on the accumulator hand-off, and no
+// generic-proxy data is published through these barriers (TMEM reads are ordered by tcgen05.fence).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// plain TMA load (own smem, own mbarrier)
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
           ptx::smem_u32(smem_dst)),
       "l"(map), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// pair TMA load: data lands in THIS CTA's smem, the transaction bytes complete on `bar_cluster_addr` (leader's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, int c0, int c1,
+                                                 uint32_t bar_cluster_addr) {
+#if TOD_MMA_PAIR
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+#else
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          ptx::smem_u32(smem_dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+#endif
 }
 
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, rows packed at 128 B, 8-row groups 1024 B apart.
@@ -93,45 +145,40 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor: kind::i8, A/B signed 8-bit K-major, D = S32, dense, M = 128, N = 256.
-constexpr uint32_t kInstrDesc = (2u << 4) /*c S32*/ | (1u << 7) /*a S8*/ | (1u << 10) /*b S8*/ | (0u << 15) | (0u << 16) |
-                                (uint32_t(kBlockN >> 3) << 17) | (uint32_t(kBlockM >> 4) << 24);
+// Instruction descriptor: kind::i8, A/B signed 8-bit K-major, D = S32, dense, M = 256 (pair), N = 256.
+constexpr uint32_t kInstrDesc = (2u << 4) /*c S32*/ | (1u << 7) /*a S8*/ | (1u << 10) /*b S8*/ |
+                                (uint32_t(kBlockN >> 3) << 17) | (uint32_t((kCtas * kBlockM) >> 4) << 24);
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+#if TOD_MMA_PAIR
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(kInstrDesc), "r"(accumulate)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(kInstrDesc), "r"(accumulate)
       : "memory");
+#endif
 }
 
-// A operand from TMEM (TS form): smem bandwidth is then spent on the streamed db tile only.
-__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t accumulate) {
+// commit all prior MMAs of the pair to the mbarrier at this smem offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+#if TOD_MMA_PAIR
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(kInstrDesc), "r"(accumulate)
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(uint16_t(3))
       : "memory");
-}
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
-        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
-        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+#else
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ptx::smem_u32(bar))
                : "memory");
+#endif
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -181,33 +228,39 @@ __device__ __noinline__ int k1_mma_slow_scan(uint32_t taddr, uint32_t *list, int
   }
   if (inserted && gthr) {
     const uint32_t kth = list[(k - 1) * kBlockM] >> kKeyRowBits;   // 511 while the list is not full
-    if (kth < 511u) {
-      const uint32_t old = atomicMin(gthr, kth);                   // publish; non-strict bound for everyone else
-      thr_dot = max(thr_dot, 255 - 2 * int(min(old, kth)));
-    }
+    // publish as a fire-and-forget reduction (RED.MIN): a returning atomic would stall the warp for a full L2
+    // round trip on every insert.  Everyone, this list included, picks the bound up at its next per-tile refresh.
+    if (kth < 511u) atomicMin(gthr, kth);
   }
   return thr_dot;
 }
 
+#if TOD_MMA_PAIR
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsMma, 1)
+#else
 __global__ void __launch_bounds__(kThreadsMma, 1)
-k1_mma_kernel(const uint4 *__restrict__ q8, const __grid_constant__ CUtensorMap map_db, int nq,
+#endif
+k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, int nq,
               int shard_rows, uint32_t global_row_base, int rows_per_chunk, uint32_t thr_init, int K,
               uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, int debug_mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *b_smem = smem;                                   // [kBStages][2 k-halves][kBlockN rows][128 B]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(b_smem + kBStages * kBTileBytes);
-  uint64_t *a_full = bars;                                  // 1
-  uint64_t *b_full = bars + 1;                              // kBStages
-  uint64_t *b_empty = b_full + kBStages;                    // kBStages
-  uint64_t *acc_full = b_empty + kBStages;                  // kAccStages
-  uint64_t *acc_empty = acc_full + kAccStages;              // kAccStages
+  uint8_t *a_smem = smem;                                   // [kQT][2 k-halves][128 rows][128 B]   (own queries)
+  uint8_t *b_smem = smem + kQT * kATileBytes;               // [kBStages][2 k-halves][128 rows][128 B] (own db half)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(b_smem + kBStages * kBHalfBytes);
+  uint64_t *a_full = bars;                                  // local : own query tiles landed
+  uint64_t *a_ready = bars + 1;                             // leader: both CTAs' query tiles landed (count 2)
+  uint64_t *b_full = bars + 2;                              // leader: both halves of a db tile landed   [kBStages]
+  uint64_t *b_empty = b_full + kBStages;                    // local : ring slot free (multicast commit) [kBStages]
+  uint64_t *acc_full = b_empty + kBStages;                  // local : accumulator ready (multicast commit) [2]
+  uint64_t *acc_empty = acc_full + kAccStages;              // leader: both CTAs' epilogues drained it (count 16) [2]
   uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(acc_empty + kAccStages);
   uint32_t *lists = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bars) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_group = blockIdx.x;
+  const uint32_t rank = cluster_ctarank();                  // 0 = leader
+  const int q_group = blockIdx.x;                           // the pair handles query groups 2p and 2p + 1
   const int chunk = blockIdx.y;
   const int q_row0 = q_group * (kQT * kBlockM);
   const int row0 = chunk * rows_per_chunk;
@@ -215,45 +268,61 @@ k1_mma_kernel(const uint4 *__restrict__ q8, const __grid_constant__ CUtensorMap 
   const int n_tiles = (row1 - row0 + kBlockN - 1) / kBlockN;
 
   if (threadIdx.x == 0) {
-    ptx::mbar_init(a_full, 4);  // the four warps that write the query tiles into TMEM
+    ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_ready, kCtas);
     for (int s = 0; s < kBStages; ++s) {
       ptx::mbar_init(&b_full[s], 1);
       ptx::mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
-      ptx::mbar_init(&acc_empty[s], kEpiWarps);  // one arrival per epilogue warp
+      ptx::mbar_init(&acc_empty[s], kCtas * kEpiWarps);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
+  if (warp == 1) {  // TMEM: all 512 columns of both SMs, same warp id in both CTAs
+#if TOD_MMA_PAIR
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(tmem_base_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+#else
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(tmem_base_slot)),
                  "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+#endif
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
+    // ===================================== TMA producer (both CTAs) =====================================
     if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(a_full, kQT * kATileBytes);
+      for (int j = 0; j < kQT; ++j)
+        for (int kh = 0; kh < 2; ++kh)
+          tma_load_2d(a_smem + j * kATileBytes + kh * (kBlockM * kSwizzleBytes), &map_q, kh * kSwizzleBytes,
+                      q_row0 + j * kBlockM, a_full);
+      mbar_wait_bounded(a_full, 0);
+      mbar_arrive_cluster(mapa_u32(ptx::smem_u32(a_ready), 0));
       for (int t = 0; t < n_tiles; ++t) {
         if ((debug_mode & 2) && t >= kBStages) break;  // profiling only: no db streaming (results are garbage)
         const int s = t % kBStages;
         mbar_wait_bounded(&b_empty[s], ((t / kBStages) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&b_full[s], kBTileBytes);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&b_full[s], kCtas * kBHalfBytes);
+        const uint32_t full_addr = mapa_u32(ptx::smem_u32(&b_full[s]), 0);
         for (int kh = 0; kh < 2; ++kh)
-          tma_load_2d(b_smem + s * kBTileBytes + kh * (kBlockN * kSwizzleBytes), &map_db, kh * kSwizzleBytes,
-                      row0 + t * kBlockN, &b_full[s]);
+          tma_load_2d_pair(b_smem + s * kBHalfBytes + kh * (kHalfN * kSwizzleBytes), &map_db, kh * kSwizzleBytes,
+                           row0 + t * kBlockN + int(rank) * kHalfN, full_addr);
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      mbar_wait_bounded(a_full, 0);
+    // ===================================== MMA issuer (leader CTA only) =====================================
+    if (lane == 0 && rank == 0) {
+      mbar_wait_bounded(a_ready, 0);
       tc_fence_after();
       uint32_t acc_iter = 0;
       for (int t = 0; t < n_tiles; ++t) {
@@ -264,23 +333,24 @@ k1_mma_kernel(const uint4 *__restrict__ q8, const __grid_constant__ CUtensorMap 
           const uint32_t as = acc_iter % kAccStages;
           mbar_wait_bounded(&acc_empty[as], ((acc_iter / kAccStages) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + kACols + as * kBlockN;
-          const uint32_t a_tmem = tmem_base + j * kAColsPerTile;  // lane 0, 8 columns (32 bytes of K) per step
+          const uint32_t d_tmem = tmem_base + as * kBlockN;
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh) {
+            const uint64_t a_desc =
+                make_kmajor_sw128_desc(ptx::smem_u32(a_smem + j * kATileBytes + kh * (kBlockM * kSwizzleBytes)));
             const uint64_t b_desc =
-                make_kmajor_sw128_desc(ptx::smem_u32(b_smem + s * kBTileBytes + kh * (kBlockN * kSwizzleBytes)));
+                make_kmajor_sw128_desc(ptx::smem_u32(b_smem + s * kBHalfBytes + kh * (kHalfN * kSwizzleBytes)));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)  // 32-byte K steps inside the 128-byte swizzle span: +2 in 16-byte units
-              umma_i8_ts(d_tmem, a_tmem + uint32_t((kh * 4 + ks) * 8), b_desc + uint64_t(ks * 2), (kh | ks) ? 1u : 0u);
+              umma_i8_pair(d_tmem, a_desc + uint64_t(ks * 2), b_desc + uint64_t(ks * 2), (kh | ks) ? 1u : 0u);
           }
-          umma_commit(&acc_full[as]);  // accumulator ready for the epilogue (implies fence::before_thread_sync)
+          umma_commit_pair(&acc_full[as]);  // accumulator ready in both CTAs
         }
-        umma_commit(&b_empty[s]);      // db ring slot may be refilled once these MMAs have read it
+        umma_commit_pair(&b_empty[s]);      // ring slot of both CTAs may be refilled once these MMAs have read it
       }
     }
   } else {
-    // ===================================== epilogue: warps 2..9 =====================================
+    // ===================================== epilogue: warps 2..9 (both CTAs) =====================================
     const int quarter = warp & 3;                         // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
     const int half = (warp - 2) >> 2;                     // which 128-column half of the accumulator
     const int row_in_tile = quarter * 32 + lane;
@@ -298,30 +368,8 @@ k1_mma_kernel(const uint4 *__restrict__ q8, const __grid_constant__ CUtensorMap 
       my_gthr[j] = (qi < nq && !(debug_mode & 16)) ? gthr + qi : nullptr;
       g_next[j] = 511u;
     }
-
-    if (half == 0) {
-      // Resident query tiles -> TMEM (the A operand of the TS-form MMA): lane = query row, column c = bytes
-      // [4c, 4c+4) of the row's 256 +-1 values.  Rows past nq are zero (their results are never written).
-#pragma unroll
-      for (int j = 0; j < kQT; ++j) {
-        const int qi = q_row0 + j * kBlockM + row_in_tile;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t w[32];
-#pragma unroll
-          for (int x = 0; x < 8; ++x) {
-            uint4 u = make_uint4(0, 0, 0, 0);
-            if (qi < nq) u = __ldg(q8 + size_t(qi) * 16 + h * 8 + x);
-            w[4 * x] = u.x; w[4 * x + 1] = u.y; w[4 * x + 2] = u.z; w[4 * x + 3] = u.w;
-          }
-          tmem_st32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(j * kAColsPerTile + h * 32), w);
-        }
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(a_full);
-    }
+    const uint32_t acc_empty_leader[kAccStages] = {mapa_u32(ptx::smem_u32(&acc_empty[0]), 0),
+                                                   mapa_u32(ptx::smem_u32(&acc_empty[1]), 0)};
 
     // max over 32 accumulator columns (VIMNMX3 tree, depth 4)
     auto max32 = [](const uint32_t (&v)[32]) -> int {
@@ -346,7 +394,7 @@ k1_mma_kernel(const uint4 *__restrict__ q8, const __grid_constant__ CUtensorMap 
         // shared bound of this query: use the value loaded during the previous tile, start the next load now
         thr_dot[j] = max(thr_dot[j], 255 - 2 * int(g_next[j]));
         if (my_gthr[j]) g_next[j] = *reinterpret_cast<volatile uint32_t *>(my_gthr[j]);
-        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kACols + as * kBlockN + uint32_t(col0);
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * kBlockN + uint32_t(col0);
         uint32_t va[32], vb[32];
         tmem_ld32(taddr, va);
 #pragma unroll
@@ -364,7 +412,7 @@ k1_mma_kernel(const uint4 *__restrict__ q8, const __grid_constant__ CUtensorMap 
         if (debug_mode & 4) thr_dot[j] = max(thr_dot[j], int(va[0] ^ vb[7]) == 0x7fffffff ? 1 : 0);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
       }
     }
 #pragma unroll
@@ -379,10 +427,14 @@ k1_mma_kernel(const uint4 *__restrict__ q8, const __grid_constant__ CUtensorMap 
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal it or read its accumulators
   if (warp == 1) {
     tc_fence_after();
+#if TOD_MMA_PAIR
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+#else
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+#endif
   }
 }
 
@@ -395,6 +447,11 @@ __global__ void __launch_bounds__(256) expand_pm1_kernel(const uint8_t *__restri
   const uint32_t lo = ((x & 0xFu) * 0x00204081u) & 0x01010101u;
   const uint32_t hi = ((x >> 4) * 0x00204081u) & 0x01010101u;
   out[i] = make_uint2(lo * 0xFEu + 0x01010101u, hi * 0xFEu + 0x01010101u);
+}
+
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *__restrict__ p, uint32_t v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -413,32 +470,6 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-cudaError_t launch_mma_k(const K1Plan &plan, const void *d_q8, const CUtensorMap &map_db, int nq, int64_t rows,
-                         uint32_t base, uint32_t thr_init, int k, uint32_t *partial, uint32_t *gthr,
-                         cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMma);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  static const int debug_mode = [] {  // TOD_K1_DEBUG_MODE: profiling knob, never set in production
-    const char *e = getenv("TOD_K1_DEBUG_MODE");
-    return e ? atoi(e) : 0;
-  }();
-  dim3 grid(plan.n_qtiles, plan.n_chunks);
-  k1_mma_kernel<<<grid, kThreadsMma, kSmemMma, stream>>>(static_cast<const uint4 *>(d_q8), map_db, nq, int(rows), base, plan.rows_per_chunk,
-                                                         thr_init, k, partial, gthr, debug_mode);
-  count_launch();
-  return cudaGetLastError();
-}
-
-// bits -> +-1 int8 (see expand_pm1_kernel) fused with the reset of the per-query shared thresholds
-__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *__restrict__ p, uint32_t v, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
-
 }  // namespace
 
 K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count) {
@@ -446,9 +477,10 @@ K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count) {
   p.q_per_thread = 0;
   p.q_tile = kQT * kBlockM;
   p.n_qtiles = std::max(1, (nq + p.q_tile - 1) / p.q_tile);
+  if (kCtas == 2) p.n_qtiles = (p.n_qtiles + 1) & ~1;  // pairs: an odd last group gets an idle partner (queries OOB)
   const int64_t max_chunks = std::max<int64_t>(1, (shard_rows + kBlockN - 1) / kBlockN);
   // One CTA per SM.  Pick the number of db chunks that fills whole waves of sm_count CTAs best (>= 97% counts as
-  // full; fewer chunks preferred: each chunk restarts the top-k thresholds and adds merge sources).
+  // full; fewer chunks preferred: each chunk adds merge sources and restarts its lists' own thresholds).
   int64_t best_c = 1;
   double best_eff = 0.0;
   const int64_t c_hi = std::min<int64_t>(max_chunks, std::max<int64_t>(16, (4LL * sm_count) / p.n_qtiles));
@@ -479,6 +511,13 @@ cudaError_t launch_expand_pm1(const void *d_bits, void *d_int8, int64_t rows, cu
   return cudaGetLastError();
 }
 
+cudaError_t launch_fill_u32(uint32_t *d_p, uint32_t v, int n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  fill_u32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_p, v, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // 2-D tensor map over an int8-expanded descriptor matrix [rows][256], box = 128 bytes x box_rows, SWIZZLE_128B.
 bool make_desc_tensor_map(void *map_out, const void *d_int8, int64_t rows, int box_rows) {
   EncodeTiledFn fn = encode_fn();
@@ -493,23 +532,31 @@ bool make_desc_tensor_map(void *map_out, const void *d_int8, int64_t rows, int b
 }
 
 int k1_mma_query_box_rows() { return kBlockM; }
-int k1_mma_db_box_rows() { return kBlockN; }
+int k1_mma_db_box_rows() { return kHalfN; }
 size_t tensor_map_bytes() { return sizeof(CUtensorMap); }
 
-cudaError_t launch_fill_u32(uint32_t *d_p, uint32_t v, int n, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
-  fill_u32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_p, v, n);
-  count_launch();
-  return cudaGetLastError();
-}
-
-cudaError_t launch_k1_mma(const K1Plan &plan, const void *d_q8, const void *map_db, int nq, int64_t shard_rows,
+cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
                           cudaStream_t stream) {
   if (k < 1 || k > TOD_MAX_K) return cudaErrorInvalidValue;
   const uint32_t thr_init = radius ? min(radius + 1u, 511u) : 511u;
-  const CUtensorMap &md = *static_cast<const CUtensorMap *>(map_db);
-  return launch_mma_k(plan, d_q8, md, nq, shard_rows, global_row_base, thr_init, k, d_partial, d_gthr, stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMma);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  static const int debug_mode = [] {  // TOD_K1_DEBUG_MODE: profiling knob, never set in production
+    const char *e = getenv("TOD_K1_DEBUG_MODE");
+    return e ? atoi(e) : 0;
+  }();
+  dim3 grid(plan.n_qtiles, plan.n_chunks);  // n_qtiles is even: cluster (2,1,1) pairs neighbouring query groups
+  k1_mma_kernel<<<grid, kThreadsMma, kSmemMma, stream>>>(*static_cast<const CUtensorMap *>(map_q),
+                                                         *static_cast<const CUtensorMap *>(map_db), nq, int(shard_rows),
+                                                         global_row_base, plan.rows_per_chunk, thr_init, k, d_partial,
+                                                         d_gthr, debug_mode);
+  count_launch();
+  return cudaGetLastError();
 }
 
 }  // namespace tod

@@ -32,7 +32,10 @@ struct tod_matcher {
   // tensor-core formulation: +-1 int8 copies (256 B / descriptor) and their TMA tensor maps
   DeviceBuffer d_db8, d_q8, d_gthr;
   alignas(64) unsigned char map_db[128];
+  alignas(64) unsigned char map_q[128];
   bool have_db8 = false;
+  const void *map_q_ptr = nullptr;
+  int64_t map_q_rows = -1;
   const char *last_kernel = "none";
 };
 
@@ -51,11 +54,17 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
     tod::K1Plan plan = tod::k1_mma_plan(nq, m->shard_rows, m->sm_count);
     TOD_CUDA(m->d_partial.reserve(size_t(plan.n_sources) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
     TOD_CUDA(m->d_q8.reserve(size_t(nq) * 256));
+    if (m->map_q_ptr != m->d_q8.ptr || m->map_q_rows != nq) {
+      if (!tod::make_desc_tensor_map(m->map_q, m->d_q8.ptr, nq, tod::k1_mma_query_box_rows()))
+        return fail(TOD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the query matrix");
+      m->map_q_ptr = m->d_q8.ptr;
+      m->map_q_rows = nq;
+    }
     TOD_CUDA(m->d_gthr.reserve(size_t(nq) * sizeof(uint32_t)));
     TOD_CUDA(tod::launch_expand_pm1(d_query, m->d_q8.ptr, nq, st));
     TOD_CUDA(tod::launch_fill_u32(m->d_gthr.as<uint32_t>(), 511u, nq, st));
     TOD_CUDA(cudaEventRecord(m->ev0, st));
-    TOD_CUDA(tod::launch_k1_mma(plan, m->d_q8.ptr, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
+    TOD_CUDA(tod::launch_k1_mma(plan, m->map_q, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
                                 m->p.radius, m->d_partial.as<uint32_t>(), m->d_gthr.as<uint32_t>(), st));
     TOD_CUDA(cudaEventRecord(m->ev1, st));
     m->ev_valid = true;

@@ -90,7 +90,7 @@ int k1_mma_query_box_rows();
 int k1_mma_db_box_rows();
 size_t tensor_map_bytes();
 // d_gthr: nq u32 shared per-query bounds, must hold 511 (no bound) before the launch (launch_fill_u32).
-cudaError_t launch_k1_mma(const K1Plan &plan, const void *d_q8, const void *map_db, int nq, int64_t shard_rows,
+cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
                           cudaStream_t stream);
 cudaError_t launch_fill_u32(uint32_t *d_p, uint32_t v, int n, cudaStream_t stream);
