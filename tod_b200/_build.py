@@ -11,8 +11,12 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "build")
-LIB = os.path.join(PKG, "libtod_b200.so")
+# TOD_B200_VARIANT=<name> + TOD_B200_DEFINES="-DX=1 ..." build an instrumented / experimental copy next to the
+# production library (libtod_b200_<name>.so, loaded when TOD_B200_LIB points at it); the default build has neither.
+VARIANT = os.environ.get("TOD_B200_VARIANT", "")
+DEFINES = os.environ.get("TOD_B200_DEFINES", "").split() if VARIANT else []
+OBJ = os.path.join(PKG, "build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(PKG, "libtod_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -37,7 +41,7 @@ def _headers_mtime():
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src + ".o")
-    cmd = [NVCC] + ARCH + COMMON + EXTRA.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + ARCH + COMMON + DEFINES + EXTRA.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     if src.endswith(".cu"):
         cmd += ["-Xptxas", "-v"] if verbose else []
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtod_b200.so")
+LIB_PATH = os.environ.get("TOD_B200_LIB") or os.path.join(_PKG, "libtod_b200.so")  # override: instrumented builds only
 
 TOD_OK, TOD_ERR_INVALID, TOD_ERR_STATE, TOD_ERR_CUDA, TOD_ERR_LIMIT, TOD_ERR_PARSE = range(6)
 TOD_SEARCH_EXACT, TOD_SEARCH_LSH = 0, 1

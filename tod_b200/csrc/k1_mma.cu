@@ -29,7 +29,7 @@
 //                     list of the same query [non-strict]) — the latter through one u32 per query in global memory
 //                     (atomicMin on publish, one relaxed load per tile).  Exact: a candidate farther than some list's
 //                     k-th best can never be in the global top-k; equal distances are kept for the tie-break.
-// Grid = (2 x query-group pairs, db chunks), cluster (2,1,1).
+// Grid: 1-D, query group fastest (see the kernel); cluster (2,1,1) in pair mode.
 #include <cuda.h>
 
 #include <algorithm>
@@ -42,7 +42,7 @@ namespace tod {
 namespace {
 
 #ifndef TOD_MMA_PAIR
-#define TOD_MMA_PAIR 0                // 1: CTA pairs (tcgen05 cta_group::2), 0: one CTA per tile (cta_group::1)
+#define TOD_MMA_PAIR 1                // 1: CTA pairs (tcgen05 cta_group::2), 0: one CTA per tile (cta_group::1)
 #endif
 constexpr int kCtas = TOD_MMA_PAIR ? 2 : 1;   // CTAs cooperating on one MMA tile
 constexpr int kBlockM = 128;          // queries per tile and CTA (TMEM lanes)
@@ -53,14 +53,30 @@ constexpr int kBStages = TOD_MMA_PAIR ? 4 : 2;  // db ring depth per CTA (4 x 32
 constexpr int kAccStages = 2;         // TMEM accumulator stages (2 x 256 = all 512 columns)
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsMma = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int kEpiCols = kBlockN / (kEpiWarps / 4);  // accumulator columns per epilogue warp (128)
 constexpr int kKBytes = 256;          // int8 elements (= bytes) per descriptor
 constexpr int kSwizzleBytes = 128;    // inner TMA box / swizzle span
 constexpr int kATileBytes = kBlockM * kKBytes;   // 32 KB
 constexpr int kBHalfBytes = kHalfN * kKBytes;    // 32 KB
-constexpr int kListWords = kQT * 2 * TOD_MAX_K * kBlockM;  // top-k lists: [j][half][slot][row]
+constexpr int kListWords = kQT * TOD_MAX_K * kBlockM;  // top-k lists: [query tile][slot][row]
+static_assert(kQT == 2 && kAccStages == 2 && kEpiWarps == 8,
+              "epilogue warp set j (4 warps, one per TMEM lane quarter) serves query tile j = accumulator stage j");
 constexpr int kSmemMma = kQT * kATileBytes + kBStages * kBHalfBytes + 1024 /*align*/ + 256 /*barriers*/ + kListWords * 4;
 constexpr uint32_t kSpinLimit = 1u << 26;  // bounded waits: a protocol bug traps instead of hanging the GPU
+
+#ifndef TOD_K1_STATS
+#define TOD_K1_STATS 0                // 1: instrumented build (tools/k1_stats.py); never the production library
+#endif
+#if TOD_K1_STATS
+// [0] slow calls (warp level) [1] cycles inside slow calls [2] MMA issuer cycles waiting acc_empty [3] ... waiting
+// b_full [4] epilogue cycles waiting acc_full (sum over warps) [5] CTA lifetime cycles [6] epilogue groups (warp
+// level) [7] epilogue busy cycles (sum over warps, excludes acc_full waits) [8] CTAs [9] producer cycles waiting b_empty
+__device__ unsigned long long g_k1_stats[16];
+#define STAT_T0(var) const long long var = clock64()
+#define STAT_ADD(acc, var) acc += (unsigned long long)(clock64() - var)
+#else
+#define STAT_T0(var)
+#define STAT_ADD(acc, var)
+#endif
 
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -194,40 +210,97 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
+// 64 accumulator columns -> 32 registers: register i = (low 16 bits of column 2i+1) << 16 | (low 16 bits of column 2i).
+// The dot products lie in [-256, 256], so the low halves are the values as int16.
+__device__ __forceinline__ void tmem_ld64_pack16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared::cta.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// Slow path of the epilogue, one copy, out of line (keeps the hot loop small enough for the instruction cache).
-// Called warp-uniformly: re-reads 32 accumulator columns (tcgen05.ld is .sync.aligned) and inserts every candidate
-// of this thread's query into its sorted top-k list in shared memory.  Returns the new dot-product threshold.
-//   list[i * kBlockM] (i < k) : ascending packed keys;   n_valid : columns of this group that are real db rows
-__device__ __noinline__ int k1_mma_slow_scan(uint32_t taddr, uint32_t *list, int k, uint32_t thr_init, uint32_t grow,
+// Slow path of the epilogue: one copy, out of line, COMPACT (it runs from a cold instruction cache: the first
+// version, a 32-way unrolled scan with a divergent insert per column, cost ~2900 cycles per call, almost all of it
+// instruction fetch — profiles/r1_k1_stats.md) and fed from REGISTERS: the accumulator stage has already been handed
+// back to the tensor core when it runs.  Called warp-uniformly for one 32-column sub-group in which some lane saw a
+// candidate.  p0..p15 hold the sub-group's dot products as packed int16 pairs (register r = columns 2r, 2r + 1).
+// Builds each lane's hit mask branch-free, then loops over the UNION of the lanes' hit columns (warp-uniform trip
+// count, usually 1) and inserts the candidate into the hitting lanes' sorted top-k lists in shared memory.
+// Returns the new dot-product threshold.
+//   list + i * 4 * kBlockM (i < k), a shared::cta address : ascending packed keys
+//   n_valid : columns of the sub-group that are real db rows (the last tile of a chunk may be partial)
+__device__ __noinline__ int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4,
+                                             uint32_t p5, uint32_t p6, uint32_t p7, uint32_t p8, uint32_t p9,
+                                             uint32_t p10, uint32_t p11, uint32_t p12, uint32_t p13, uint32_t p14,
+                                             uint32_t p15, uint32_t list, int k, uint32_t thr_init, uint32_t grow,
                                              int n_valid, int thr_dot, uint32_t *gthr) {
-  uint32_t v[32];
-  tmem_ld32(taddr, v);
-  tmem_wait_ld();
-  bool inserted = false;
+  constexpr uint32_t kStride = 4u * kBlockM;  // bytes between consecutive slots of one list
+  const uint32_t v[16] = {p0, p1, p2, p3, p4, p5, p6, p7, p8, p9, p10, p11, p12, p13, p14, p15};
+  // dot > thr  <=>  value-in-the-high-half >= (thr + 1) << 16   (the low half only adds [0, 65535])
+  const int th = (thr_dot + 1) << 16;
+  uint32_t mask = 0;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int dot = int(v[i]);
-    if (i < n_valid && dot > thr_dot) {
+  for (int r = 0; r < 16; ++r) {
+    mask |= (int(v[r] << 16) >= th) ? (1u << (2 * r)) : 0u;
+    mask |= (int(v[r]) >= th) ? (2u << (2 * r)) : 0u;
+  }
+  if (n_valid < 32) mask &= (1u << n_valid) - 1u;
+  uint32_t todo = __reduce_or_sync(0xffffffffu, mask);
+#if TOD_K1_STATS
+  if ((threadIdx.x & 31) == 0) atomicAdd(&g_k1_stats[13], (unsigned long long)__popc(todo));
+#endif
+  bool inserted = false;
+#pragma unroll 1
+  while (todo) {
+    const int i = __ffs(int(todo)) - 1;  // warp-uniform column
+    todo &= todo - 1u;
+    // v[i >> 1] through a select tree (static register indices; i is uniform, so are the predicates)
+    uint32_t s8[8], s4[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s8[j] = (i & 16) ? v[8 + j] : v[j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s4[j] = (i & 8) ? s8[4 + j] : s8[j];
+    const uint32_t s2a = (i & 4) ? s4[2] : s4[0], s2b = (i & 4) ? s4[3] : s4[1];
+    const uint32_t x = (i & 2) ? s2b : s2a;
+    const int dot = (i & 1) ? (int(x) >> 16) : (int(x << 16) >> 16);
+    if (((mask >> i) & 1u) && dot > thr_dot) {  // thr_dot may have tightened since the mask was built
       const uint32_t dist = uint32_t(256 - dot) >> 1;
-      uint32_t key = (dist << kKeyRowBits) | (grow + uint32_t(i));
+      const uint32_t key = (dist << kKeyRowBits) | (grow + uint32_t(i));
       // sorted insert: the new key displaces the worst entry and sinks to its place
       int pos = k - 1;
-      while (pos > 0 && list[(pos - 1) * kBlockM] > key) {
-        list[pos * kBlockM] = list[(pos - 1) * kBlockM];
+      while (pos > 0) {
+        const uint32_t prev = lds_u32(list + uint32_t(pos - 1) * kStride);
+        if (prev <= key) break;
+        sts_u32(list + uint32_t(pos) * kStride, prev);
         --pos;
       }
-      list[pos * kBlockM] = key;
-      const uint32_t kth = min(thr_init, list[(k - 1) * kBlockM] >> kKeyRowBits);  // strict bound of this list
+      sts_u32(list + uint32_t(pos) * kStride, key);
+      const uint32_t kth = min(thr_init, lds_u32(list + uint32_t(k - 1) * kStride) >> kKeyRowBits);  // strict bound
       thr_dot = max(thr_dot, 256 - 2 * int(kth));
       inserted = true;
     }
   }
   if (inserted && gthr) {
-    const uint32_t kth = list[(k - 1) * kBlockM] >> kKeyRowBits;   // 511 while the list is not full
+    const uint32_t kth = lds_u32(list + uint32_t(k - 1) * kStride) >> kKeyRowBits;   // 511 while the list is not full
     // publish as a fire-and-forget reduction (RED.MIN): a returning atomic would stall the warp for a full L2
     // round trip on every insert.  Everyone, this list included, picks the bound up at its next per-tile refresh.
     if (kth < 511u) atomicMin(gthr, kth);
@@ -241,7 +314,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsMma, 1)
 __global__ void __launch_bounds__(kThreadsMma, 1)
 #endif
 k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, int nq,
-              int shard_rows, uint32_t global_row_base, int rows_per_chunk, uint32_t thr_init, int K,
+              int shard_rows, uint32_t global_row_base, int rows_per_chunk, int n_chunks, uint32_t thr_init, int K,
               uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, int debug_mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -259,9 +332,18 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  STAT_T0(t_cta);
+#if TOD_K1_STATS
+  unsigned long long st_a = 0, st_b = 0, st_c = 0, st_d = 0, st_e = 0;
+#endif
   const uint32_t rank = cluster_ctarank();                  // 0 = leader
-  const int q_group = blockIdx.x;                           // the pair handles query groups 2p and 2p + 1
-  const int chunk = blockIdx.y;
+  // 1-D grid, query group fastest: the CTAs of db chunk c + 1 start after (most of) chunk c has been scanned for the
+  // same queries, so all but the first chunk's CTAs begin with tight bounds in gthr.  A pair handles query groups
+  // 2p and 2p + 1.  (debug_mode & 32: chunk fastest, for the ablation in profiles/r1_k1_stats.md.)
+  const int unit = int(blockIdx.x) / kCtas;
+  const int n_units_q = int(gridDim.x) / kCtas / n_chunks;
+  const int chunk = (debug_mode & 32) ? unit % n_chunks : unit / n_units_q;
+  const int q_group = ((debug_mode & 32) ? unit / n_chunks : unit % n_units_q) * kCtas + int(blockIdx.x) % kCtas;
   const int q_row0 = q_group * (kQT * kBlockM);
   const int row0 = chunk * rows_per_chunk;
   const int row1 = min(shard_rows, row0 + rows_per_chunk);
@@ -276,7 +358,7 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
     for (int s = 0; s < kAccStages; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
-      ptx::mbar_init(&acc_empty[s], kCtas * kEpiWarps);
+      ptx::mbar_init(&acc_empty[s], kCtas * 4);
     }
     ptx::fence_mbar_init();
   }
@@ -311,13 +393,20 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       for (int t = 0; t < n_tiles; ++t) {
         if ((debug_mode & 2) && t >= kBStages) break;  // profiling only: no db streaming (results are garbage)
         const int s = t % kBStages;
-        mbar_wait_bounded(&b_empty[s], ((t / kBStages) & 1) ^ 1);
+        {
+          STAT_T0(t0);
+          mbar_wait_bounded(&b_empty[s], ((t / kBStages) & 1) ^ 1);
+          STAT_ADD(st_a, t0);
+        }
         if (rank == 0) ptx::mbar_arrive_expect_tx(&b_full[s], kCtas * kBHalfBytes);
         const uint32_t full_addr = mapa_u32(ptx::smem_u32(&b_full[s]), 0);
         for (int kh = 0; kh < 2; ++kh)
           tma_load_2d_pair(b_smem + s * kBHalfBytes + kh * (kHalfN * kSwizzleBytes), &map_db, kh * kSwizzleBytes,
                            row0 + t * kBlockN + int(rank) * kHalfN, full_addr);
       }
+#if TOD_K1_STATS
+      atomicAdd(&g_k1_stats[9], st_a);
+#endif
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =====================================
@@ -327,11 +416,19 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       uint32_t acc_iter = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t % kBStages;
-        if (!((debug_mode & 2) && t >= kBStages)) mbar_wait_bounded(&b_full[s], (t / kBStages) & 1);
+        {
+          STAT_T0(t0);
+          if (!((debug_mode & 2) && t >= kBStages)) mbar_wait_bounded(&b_full[s], (t / kBStages) & 1);
+          STAT_ADD(st_b, t0);
+        }
         tc_fence_after();
         for (int j = 0; j < kQT; ++j, ++acc_iter) {
           const uint32_t as = acc_iter % kAccStages;
-          mbar_wait_bounded(&acc_empty[as], ((acc_iter / kAccStages) & 1) ^ 1);
+          {
+            STAT_T0(t0);
+            mbar_wait_bounded(&acc_empty[as], ((acc_iter / kAccStages) & 1) ^ 1);
+            STAT_ADD(st_a, t0);
+          }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * kBlockN;
 #pragma unroll
@@ -348,84 +445,122 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         umma_commit_pair(&b_empty[s]);      // ring slot of both CTAs may be refilled once these MMAs have read it
       }
+#if TOD_K1_STATS
+      atomicAdd(&g_k1_stats[2], st_a);
+      atomicAdd(&g_k1_stats[3], st_b);
+#endif
     }
   } else {
     // ===================================== epilogue: warps 2..9 (both CTAs) =====================================
+    // Warp set j (warps 2 + 4j .. 5 + 4j, one warp per TMEM lane quarter) serves query tile j, whose accumulators
+    // always land in TMEM stage j.  Thread = one query row, all 256 columns of the tile.
     const int quarter = warp & 3;                         // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
-    const int half = (warp - 2) >> 2;                     // which 128-column half of the accumulator
+    const int j = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
-    const int col0 = half * kEpiCols;
-    int thr_dot[kQT];
-    uint32_t g_next[kQT];                                 // shared bound, loaded one tile ahead of its use
-    uint32_t *my_list[kQT];
-    uint32_t *my_gthr[kQT];
-#pragma unroll
-    for (int j = 0; j < kQT; ++j) {
-      my_list[j] = lists + size_t((j * 2 + half) * TOD_MAX_K) * kBlockM + row_in_tile;
-      for (int i = 0; i < K; ++i) my_list[j][i * kBlockM] = kKeyEmpty;
-      thr_dot[j] = 256 - 2 * int(thr_init);               // distance < thr  <=>  dot > 256 - 2 thr
-      const int qi = q_row0 + j * kBlockM + row_in_tile;
-      my_gthr[j] = (qi < nq && !(debug_mode & 16)) ? gthr + qi : nullptr;
-      g_next[j] = 511u;
-    }
-    const uint32_t acc_empty_leader[kAccStages] = {mapa_u32(ptx::smem_u32(&acc_empty[0]), 0),
-                                                   mapa_u32(ptx::smem_u32(&acc_empty[1]), 0)};
+    const uint32_t my_list = ptx::smem_u32(lists + size_t(j * TOD_MAX_K) * kBlockM + row_in_tile);
+    for (int i = 0; i < K; ++i) sts_u32(my_list + uint32_t(i) * 4u * kBlockM, kKeyEmpty);
+    int thr_dot = 256 - 2 * int(thr_init);                // distance < thr  <=>  dot > 256 - 2 thr
+    const int qi = q_row0 + j * kBlockM + row_in_tile;
+    uint32_t *const my_gthr = (qi < nq && !(debug_mode & 16)) ? gthr + qi : nullptr;
+    uint32_t g_next = 511u;                               // shared bound, loaded one tile ahead of its use
+    const uint32_t acc_empty_leader = mapa_u32(ptx::smem_u32(&acc_empty[j]), 0);
+    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(j * kBlockN);
 
-    // max over 32 accumulator columns (VIMNMX3 tree, depth 4)
-    auto max32 = [](const uint32_t (&v)[32]) -> int {
-      int r[11];
-#pragma unroll
-      for (int i = 0; i < 10; ++i) r[i] = __vimax3_s32(int(v[3 * i]), int(v[3 * i + 1]), int(v[3 * i + 2]));
-      r[10] = max(int(v[30]), int(v[31]));
-      const int a = __vimax3_s32(r[0], r[1], r[2]), b = __vimax3_s32(r[3], r[4], r[5]),
-                c = __vimax3_s32(r[6], r[7], r[8]), d = max(r[9], r[10]);
-      return max(__vimax3_s32(a, b, c), d);
+    // max over 32 accumulator columns held as 16 packed int16 pairs (VIMNMX3.S16x2 tree)
+    auto max32p = [](const uint32_t (&v)[32], int o) -> int {
+      const uint32_t r0 = __vimax3_s16x2(v[o + 0], v[o + 1], v[o + 2]), r1 = __vimax3_s16x2(v[o + 3], v[o + 4], v[o + 5]),
+                     r2 = __vimax3_s16x2(v[o + 6], v[o + 7], v[o + 8]), r3 = __vimax3_s16x2(v[o + 9], v[o + 10], v[o + 11]),
+                     r4 = __vimax3_s16x2(v[o + 12], v[o + 13], v[o + 14]);
+      const uint32_t m = __vmaxs2(__vimax3_s16x2(r0, r1, r2), __vimax3_s16x2(r3, r4, v[o + 15]));
+      return max(int(m << 16) >> 16, int(m) >> 16);
+    };
+    auto slow32 = [&](const uint32_t (&v)[32], int o, uint32_t grow, int n_valid) {
+      thr_dot = k1_mma_slow_scan(v[o + 0], v[o + 1], v[o + 2], v[o + 3], v[o + 4], v[o + 5], v[o + 6], v[o + 7],
+                                 v[o + 8], v[o + 9], v[o + 10], v[o + 11], v[o + 12], v[o + 13], v[o + 14], v[o + 15],
+                                 my_list, K, thr_init, grow, n_valid, thr_dot, my_gthr);
     };
 
-    uint32_t acc_iter = 0;
     for (int t = 0; t < n_tiles; ++t) {
-      const int cols_valid = min(kBlockN, (row1 - row0) - t * kBlockN);
+      const int cols_valid = min(kBlockN, (row1 - row0) - t * kBlockN);  // real db rows in this tile
       const uint32_t grow0 = global_row_base + uint32_t(row0 + t * kBlockN);
-#pragma unroll
-      for (int j = 0; j < kQT; ++j, ++acc_iter) {
-        const uint32_t as = acc_iter % kAccStages;
-        mbar_wait_bounded(&acc_full[as], (acc_iter / kAccStages) & 1);
-        tc_fence_after();
-        // shared bound of this query: use the value loaded during the previous tile, start the next load now
-        thr_dot[j] = max(thr_dot[j], 255 - 2 * int(g_next[j]));
-        if (my_gthr[j]) g_next[j] = *reinterpret_cast<volatile uint32_t *>(my_gthr[j]);
-        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * kBlockN + uint32_t(col0);
-        uint32_t va[32], vb[32];
-        tmem_ld32(taddr, va);
-#pragma unroll
-        for (int cc = 0; cc < kEpiCols / 32; ++cc) {  // software pipeline: next load in flight while scanning
-          uint32_t (&cur)[32] = (cc & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
-          tmem_wait_ld();
-          if (cc + 1 < kEpiCols / 32) tmem_ld32(taddr + uint32_t(32 * (cc + 1)), nxt);
-          const int col = col0 + 32 * cc;
-          const bool hit = !(debug_mode & 4) && col < cols_valid && max32(cur) > thr_dot[j];
-          if (__any_sync(0xffffffffu, hit) && !(debug_mode & 8))
-            thr_dot[j] = k1_mma_slow_scan(taddr + uint32_t(32 * cc), my_list[j], K, thr_init, grow0 + uint32_t(col),
-                                          min(32, cols_valid - col), thr_dot[j], my_gthr[j]);
-        }
-        if (debug_mode & 4) thr_dot[j] = max(thr_dot[j], int(va[0] ^ vb[7]) == 0x7fffffff ? 1 : 0);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
+      {
+        STAT_T0(t0);
+        mbar_wait_bounded(&acc_full[j], t & 1);
+        STAT_ADD(st_c, t0);
       }
+      STAT_T0(t_busy);
+      tc_fence_after();
+      // the whole 128 x 256 accumulator as packed int16: four loads in flight, one wait, then the stage goes straight
+      // back to the MMA warp — everything below works from registers
+      uint32_t va[32], vb[32], vc[32], vd[32];
+      tmem_ld64_pack16(taddr, va);
+      tmem_ld64_pack16(taddr + 64u, vb);
+      tmem_ld64_pack16(taddr + 128u, vc);
+      tmem_ld64_pack16(taddr + 192u, vd);
+      // shared bound of this query: use the value loaded during the previous tile, start the next load now
+      thr_dot = max(thr_dot, 255 - 2 * int(g_next));
+      if (my_gthr) g_next = *reinterpret_cast<volatile uint32_t *>(my_gthr);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+      STAT_ADD(st_e, t_busy);
+
+      uint32_t flags = 0;
+      if (!(debug_mode & 4)) {
+        flags |= (max32p(va, 0) > thr_dot) ? 1u : 0u;
+        flags |= (max32p(va, 16) > thr_dot) ? 2u : 0u;
+        flags |= (max32p(vb, 0) > thr_dot) ? 4u : 0u;
+        flags |= (max32p(vb, 16) > thr_dot) ? 8u : 0u;
+        flags |= (max32p(vc, 0) > thr_dot) ? 16u : 0u;
+        flags |= (max32p(vc, 16) > thr_dot) ? 32u : 0u;
+        flags |= (max32p(vd, 0) > thr_dot) ? 64u : 0u;
+        flags |= (max32p(vd, 16) > thr_dot) ? 128u : 0u;
+        if (cols_valid < kBlockN) flags &= (1u << ((cols_valid + 31) >> 5)) - 1u;
+      } else {
+        thr_dot = max(thr_dot, int(va[0] ^ vb[7] ^ vc[3] ^ vd[9]) == 0x7fffffff ? 1 : 0);
+      }
+      flags = __reduce_or_sync(0xffffffffu, flags);
+      if (debug_mode & 64) flags |= 1u;  // ablation: a (mostly empty) slow call on every tile, i.e. from a warm i-cache
+      if (flags && !(debug_mode & 8)) {
+        STAT_T0(t0);
+        if (flags & 1u) slow32(va, 0, grow0, cols_valid);
+        if (flags & 2u) slow32(va, 16, grow0 + 32u, cols_valid - 32);
+        if (flags & 4u) slow32(vb, 0, grow0 + 64u, cols_valid - 64);
+        if (flags & 8u) slow32(vb, 16, grow0 + 96u, cols_valid - 96);
+        if (flags & 16u) slow32(vc, 0, grow0 + 128u, cols_valid - 128);
+        if (flags & 32u) slow32(vc, 16, grow0 + 160u, cols_valid - 160);
+        if (flags & 64u) slow32(vd, 0, grow0 + 192u, cols_valid - 192);
+        if (flags & 128u) slow32(vd, 16, grow0 + 224u, cols_valid - 224);
+        STAT_ADD(st_b, t0);
+#if TOD_K1_STATS
+        st_a += (unsigned long long)__popc(flags);
+#endif
+      }
+      STAT_ADD(st_d, t_busy);
     }
-#pragma unroll
-    for (int j = 0; j < kQT; ++j) {
-      const int qi = q_row0 + j * kBlockM + row_in_tile;
-      if (qi < nq) {
-        // the two column halves are independent candidate lists: sources 2*chunk and 2*chunk + 1 of the merge
-        uint32_t *o = partial + (size_t(chunk * 2 + half) * nq + qi) * K;
-        for (int i = 0; i < K; ++i) o[i] = my_list[j][i * kBlockM];
-      }
+#if TOD_K1_STATS
+    if (lane == 0) {
+      atomicAdd(&g_k1_stats[0], st_a);
+      atomicAdd(&g_k1_stats[1], st_b);
+      atomicAdd(&g_k1_stats[4], st_c);
+      atomicAdd(&g_k1_stats[7], st_d);
+      atomicAdd(&g_k1_stats[6], (unsigned long long)(n_tiles) * 8);  // 32-column sub-groups
+      atomicAdd(&g_k1_stats[14], st_e);
+    }
+#endif
+    if (qi < nq) {
+      uint32_t *o = partial + (size_t(chunk) * nq + qi) * K;  // one candidate list per (chunk, query): a merge source
+      for (int i = 0; i < K; ++i) o[i] = lds_u32(my_list + uint32_t(i) * 4u * kBlockM);
     }
   }
 
+#if TOD_K1_STATS
+  if (threadIdx.x == 0) {
+    atomicAdd(&g_k1_stats[5], (unsigned long long)(clock64() - t_cta));
+    atomicAdd(&g_k1_stats[8], 1ull);
+  }
+#endif
   tc_fence_before();
   cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal it or read its accumulators
   if (warp == 1) {
@@ -479,12 +614,21 @@ K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count) {
   p.n_qtiles = std::max(1, (nq + p.q_tile - 1) / p.q_tile);
   if (kCtas == 2) p.n_qtiles = (p.n_qtiles + 1) & ~1;  // pairs: an odd last group gets an idle partner (queries OOB)
   const int64_t max_chunks = std::max<int64_t>(1, (shard_rows + kBlockN - 1) / kBlockN);
-  // One CTA per SM.  Pick the number of db chunks that fills whole waves of sm_count CTAs best (>= 97% counts as
-  // full; fewer chunks preferred: each chunk adds merge sources and restarts its lists' own thresholds).
-  int64_t best_c = 1;
+  // One CTA per SM.  The CTAs of different db chunks for the same queries run side by side (chunk-fastest grid) and
+  // share their bounds, so more chunks = faster-converging thresholds = fewer slow-path insertions; each chunk also
+  // adds two merge sources and a fixed per-CTA start-up cost.  Ask for >= 8 chunks when a chunk keeps >= 64 tiles,
+  // then take the first count that fills whole waves of sm_count CTAs to >= 97% (small grids) — for grids of many
+  // waves the tail is short whatever the count.
+  const int64_t c_lo = std::max<int64_t>(1, std::min<int64_t>(8, max_chunks / 64));
+  const int64_t c_hi = std::min<int64_t>(max_chunks, std::max<int64_t>(std::max<int64_t>(16, c_lo),
+                                                                       (4LL * sm_count) / p.n_qtiles));
+  int64_t best_c = c_lo;
   double best_eff = 0.0;
-  const int64_t c_hi = std::min<int64_t>(max_chunks, std::max<int64_t>(16, (4LL * sm_count) / p.n_qtiles));
-  for (int64_t c = 1; c <= std::max<int64_t>(1, c_hi); ++c) {
+  if (const char *e = getenv("TOD_K1_CHUNKS")) {  // experiments only
+    best_c = std::min<int64_t>(max_chunks, std::max(1, atoi(e)));
+    best_eff = 1.0;
+  }
+  for (int64_t c = c_lo; c <= std::max<int64_t>(c_lo, c_hi); ++c) {
     const int64_t ctas = c * p.n_qtiles;
     const int64_t waves = (ctas + sm_count - 1) / sm_count;
     const double eff = double(ctas) / double(waves * sm_count);
@@ -497,7 +641,7 @@ K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count) {
   rpc = std::max<int64_t>(kBlockN, (rpc + kBlockN - 1) / kBlockN * kBlockN);
   p.rows_per_chunk = int(rpc);
   p.n_chunks = int(std::max<int64_t>(1, (shard_rows + rpc - 1) / rpc));
-  p.n_sources = p.n_chunks * (kEpiWarps / 4);
+  p.n_sources = p.n_chunks;
   return p;
 }
 
@@ -531,6 +675,19 @@ bool make_desc_tensor_map(void *map_out, const void *d_int8, int64_t rows, int b
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+#if TOD_K1_STATS
+}  // namespace tod
+extern "C" void tod_debug_k1_stats(unsigned long long *out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, tod::g_k1_stats, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(tod::g_k1_stats, z, sizeof(z));
+  }
+}
+namespace tod {
+#endif
+
 int k1_mma_query_box_rows() { return kBlockM; }
 int k1_mma_db_box_rows() { return kHalfN; }
 size_t tensor_map_bytes() { return sizeof(CUtensorMap); }
@@ -550,10 +707,10 @@ cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map
     const char *e = getenv("TOD_K1_DEBUG_MODE");
     return e ? atoi(e) : 0;
   }();
-  dim3 grid(plan.n_qtiles, plan.n_chunks);  // n_qtiles is even: cluster (2,1,1) pairs neighbouring query groups
+  dim3 grid(unsigned(plan.n_qtiles) * unsigned(plan.n_chunks));  // n_qtiles is even in pair mode (cluster (2,1,1))
   k1_mma_kernel<<<grid, kThreadsMma, kSmemMma, stream>>>(*static_cast<const CUtensorMap *>(map_q),
                                                          *static_cast<const CUtensorMap *>(map_db), nq, int(shard_rows),
-                                                         global_row_base, plan.rows_per_chunk, thr_init, k, d_partial,
+                                                         global_row_base, plan.rows_per_chunk, plan.n_chunks, thr_init, k, d_partial,
                                                          d_gthr, debug_mode);
   count_launch();
   return cudaGetLastError();

@@ -46,7 +46,11 @@ int use_device(const tod_matcher *m) {
   return TOD_OK;
 }
 
-bool use_mma(const tod_matcher *m) { return m->p.kernel == TOD_KERNEL_MMA; }
+// TOD_KERNEL_AUTO picks the tensor-core formulation (5-13x the popc kernel on B200) whenever this
+// shard holds rows; the popc kernel stays selectable and is the cross-check in tests/.
+bool use_mma(const tod_matcher *m) {
+  return m->p.kernel == TOD_KERNEL_MMA || (m->p.kernel == TOD_KERNEL_AUTO && m->shard_rows > 0);
+}
 
 int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1Plan *plan_out) {
   if (use_mma(m)) {
