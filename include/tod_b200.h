@@ -167,6 +167,10 @@ int tod_score_hypotheses(int32_t device, int32_t n, const float *query_pts, cons
                          const uint32_t *physical, const uint32_t *valid, int32_t n_hyp, const uint32_t *triples,
                          double threshold, int32_t *counts, float *R, float *T);
 
+/* Device time (ms, CUDA events on the launch stream) of the K2 / K3 kernel launched by the last tod_fill_adjacency /
+ * tod_score_hypotheses call on this thread; < 0 if unknown. */
+float tod_last_stage_ms(void);
+
 /* ================================================================================================================
  * GuessGenerator  (GuessGenerator.cpp)
  * ============================================================================================================== */
@@ -180,6 +184,9 @@ typedef struct tod_guess_params {
   int32_t device;
   double ransac_threshold;       /* +inf = reference-faithful (sac.h:70, quirk Q3) */
   uint64_t seed;                 /* sampler stream seed; stream is re-seeded per (object, round), see DESIGN.md */
+  int32_t host_threads;          /* host threads for the per-object work (sampler, replay, clique gate, refinement);
+                                    0 = min(16, hardware threads).  Results do not depend on it. */
+  int32_t reserved;
 } tod_guess_params;
 
 void tod_guess_default_params(tod_guess_params *p);
@@ -205,6 +212,12 @@ int32_t tod_rng_next(uint64_t *state);
 
 /* Device time (ms) spent in K2 / K3 kernels and number of K3 hypotheses scored during the last process call. */
 void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_t *n_hypotheses, int32_t *n_rounds);
+/* Host wall-clock profile (ms) of the last process call: [0] ClusterPerObject + upload + K2 + bit-matrix download,
+ * [1] sampler, [2] K3 launches incl. copies and sync, [3] replay + inlier lists + clique gate, [4] refinement +
+ * invalidation, [5] clique-gate evaluations (a count), [6] of those, settled by the exact no-8-clique proof without
+ * running the search (a count), [7] total, [8] gate set-up, [9] gate proof, [10] gate search (summed over the host
+ * threads), [11] gate evaluations settled by the round's 7-core test (a count).  ms12 must hold 12 doubles. */
+void tod_guess_last_profile(const tod_guess *g, double *ms12);
 
 #ifdef __cplusplus
 }

@@ -65,7 +65,8 @@ def test_oracle_restatement_agrees_too():
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libtod_ref.so not built")
-@pytest.mark.parametrize("n_obj,n_per,frac,iters", [(6, 150, 0.5, 300), (10, 300, 0.1, 1000), (3, 40, 0.9, 100)])
+@pytest.mark.parametrize("n_obj,n_per,frac,iters", [(6, 150, 0.5, 300), (10, 300, 0.1, 1000), (3, 40, 0.9, 100),
+                                                    (3, 1000, 0.1, 600)])
 def test_outlier_heavy_clusters_match_reference(n_obj, n_per, frac, iters):
     """BASELINE config C5 shape (scaled): matches injected at the GuessGenerator boundary, 50-90% outliers."""
     gi = synth.make_guess_inputs(n_obj, n_per, frac, seed=1000 + n_per)
@@ -75,6 +76,24 @@ def test_outlier_heavy_clusters_match_reference(n_obj, n_per, frac, iters):
                       iters, 0.01, seed=11)
     compare(got, exp)
     assert len(exp) >= 1
+
+
+def test_result_does_not_depend_on_host_threads():
+    """The per-object host work runs on a thread pool; every object owns its sampler stream, so 1 and 8 threads must
+    give identical poses and inlier sets."""
+    gi = synth.make_guess_inputs(12, 200, 0.3, seed=77)
+    res = []
+    for threads in (1, 8):
+        gg = GuessGenerator(min_inliers=8, n_ransac_iterations=400, sensor_error=0.01, seed=5, host_threads=threads)
+        res.append(gg.process(gi["keypoints_xy"], gi["cloud"], gi["matches"], gi["counts"], gi["points3d"],
+                              gi["spans"]))
+        st = gg.last_stats()
+        assert st["gate_calls"] >= st["gate_proved_empty"] >= 0
+    a, b = res
+    assert len(a["pose_results"]) == len(b["pose_results"]) >= 1
+    assert (a["pose_results"] == b["pose_results"]).all()
+    for x, y in zip(a["inliers"], b["inliers"]):
+        assert list(x) == list(y)
 
 
 def test_edge_cases():

@@ -30,7 +30,7 @@ class MatcherParams(ctypes.Structure):
 class GuessParams(ctypes.Structure):
     _fields_ = [("min_inliers", ctypes.c_uint32), ("n_ransac_iterations", ctypes.c_uint32),
                 ("sensor_error", ctypes.c_float), ("device", ctypes.c_int32), ("ransac_threshold", ctypes.c_double),
-                ("seed", ctypes.c_uint64)]
+                ("seed", ctypes.c_uint64), ("host_threads", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class TodError(RuntimeError):
@@ -69,6 +69,7 @@ SIGNATURES = [
     ("tod_adjacency_row_words", _I32, [_I32]),
     ("tod_fill_adjacency", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _F, _P, _P, _P]),
     ("tod_score_hypotheses", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _I32, _P, _D, _P, _P, _P]),
+    ("tod_last_stage_ms", _F, []),
     ("tod_guess_default_params", None, [ctypes.POINTER(GuessParams)]),
     ("tod_guess_create", ctypes.c_int, [ctypes.POINTER(GuessParams), ctypes.POINTER(_P)]),
     ("tod_guess_destroy", None, [_P]),
@@ -76,6 +77,7 @@ SIGNATURES = [
                                          ctypes.POINTER(_I32), _P, _I32]),
     ("tod_rng_seed", _U64, [_U64, _U32, _U32]),
     ("tod_rng_next", _I32, [ctypes.POINTER(_U64)]),
+    ("tod_guess_last_profile", None, [_P, ctypes.POINTER(_D)]),
     ("tod_guess_last_stats", None, [_P, ctypes.POINTER(_F), ctypes.POINTER(_F), ctypes.POINTER(_I64),
                                     ctypes.POINTER(_I32)]),
 ]

@@ -175,13 +175,13 @@ class GuessGenerator:
     inputs points3d, keypoints, matches, matches_3d, spans, object_ids; outputs pose_results, Rs, Ts."""
 
     def __init__(self, min_inliers=15, n_ransac_iterations=1000, sensor_error=0.01, ransac_threshold=float("inf"),
-                 seed=0, device=0):
+                 seed=0, device=0, host_threads=0):
         lib = capi.load()
         p = capi.GuessParams()
         lib.tod_guess_default_params(ctypes.byref(p))
         p.min_inliers, p.n_ransac_iterations = int(min_inliers), int(n_ransac_iterations)
         p.sensor_error, p.ransac_threshold = float(sensor_error), float(ransac_threshold)
-        p.seed, p.device = int(seed), int(device)
+        p.seed, p.device, p.host_threads = int(seed), int(device), int(host_threads)
         self.params = p
         self._h = ctypes.c_void_p()
         capi.check(lib.tod_guess_create(ctypes.byref(p), ctypes.byref(self._h)))
@@ -231,4 +231,10 @@ class GuessGenerator:
         k2, k3 = ctypes.c_float(), ctypes.c_float()
         nh, nr = ctypes.c_int64(), ctypes.c_int32()
         self._lib.tod_guess_last_stats(self._h, ctypes.byref(k2), ctypes.byref(k3), ctypes.byref(nh), ctypes.byref(nr))
-        return {"k2_ms": k2.value, "k3_ms": k3.value, "n_hypotheses": nh.value, "n_rounds": nr.value}
+        prof = (ctypes.c_double * 12)()
+        self._lib.tod_guess_last_profile(self._h, prof)
+        return {"k2_ms": k2.value, "k3_ms": k3.value, "n_hypotheses": nh.value, "n_rounds": nr.value,
+                "host_ms": {"cluster_k2": prof[0], "sampler": prof[1], "k3_launch_sync": prof[2],
+                            "replay_gate": prof[3], "refine_invalidate": prof[4], "total": prof[7]},
+                "gate_calls": int(prof[5]), "gate_proved_empty": int(prof[6]), "gate_core_rejects": int(prof[11]),
+                "gate_thread_ms": {"setup": prof[8], "proof": prof[9], "search": prof[10]}}

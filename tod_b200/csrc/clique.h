@@ -26,6 +26,16 @@ class CliqueFinder {
       : n_(n_vertices), words_((n_vertices + 31) / 32), bits_(size_t(n_vertices) * size_t((n_vertices + 31) / 32), 0u),
         degree_(size_t(n_vertices), 0u) {}
 
+  // from a dense symmetric n x ceil(n/32) bit-matrix (no self-loops)
+  CliqueFinder(int n_vertices, const uint32_t *adjacency) : CliqueFinder(n_vertices) {
+    std::copy(adjacency, adjacency + bits_.size(), bits_.begin());
+    for (int v = 0; v < n_; ++v) {
+      unsigned d = 0;
+      for (int w = 0; w < words_; ++w) d += unsigned(__builtin_popcount(bits_[size_t(v) * words_ + w]));
+      degree_[size_t(v)] = d;
+    }
+  }
+
   void add_edge(int a, int b) {
     if (a == b || connected(a, b)) return;
     bits_[size_t(a) * words_ + (b >> 5)] |= 1u << (b & 31);

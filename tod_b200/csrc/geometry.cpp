@@ -20,6 +20,27 @@ struct Scratch {  // freed on scope exit
   void own(DeviceBuffer &b) { bufs.push_back(&b); }
 };
 
+thread_local float g_last_stage_ms = -1.f;
+
+// CUDA events around one kernel launch on `st`; the elapsed time lands in g_last_stage_ms once the stream is synced.
+struct StageTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t st;
+  explicit StageTimer(cudaStream_t s) : st(s) {
+    g_last_stage_ms = -1.f;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) e0 = e1 = nullptr;
+  }
+  void begin() { if (e0) cudaEventRecord(e0, st); }
+  void end() { if (e1) cudaEventRecord(e1, st); }
+  void finish() {
+    if (e0 && e1 && cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&g_last_stage_ms, e0, e1);
+  }
+  ~StageTimer() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+};
+
 int check_device(int device) {
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -34,6 +55,8 @@ int check_device(int device) {
 }  // namespace
 
 extern "C" {
+
+float tod_last_stage_ms(void) { return g_last_stage_ms; }
 
 int32_t tod_adjacency_row_words(int32_t n) { return n <= 0 ? 0 : tod::adjacency_row_words(n); }
 
@@ -76,12 +99,16 @@ int tod_fill_adjacency(int32_t device, int32_t n_clusters, const int32_t *offset
   TOD_CUDA(cudaMemcpyAsync(d_t.ptr, train_pts, size_t(N) * 12, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(d_px.ptr, pixels, size_t(N) * 8, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(d_sp.ptr, spans, size_t(n_clusters) * 4, cudaMemcpyHostToDevice, st));
+  StageTimer timer(st);
+  timer.begin();
   TOD_CUDA(tod::launch_fill_adjacency(n_clusters, d_off.as<int32_t>(), d_mo.as<int64_t>(), d_q.as<float>(),
                                       d_t.as<float>(), d_px.as<float>(), d_sp.as<float>(), sensor_error,
                                       d_P.as<uint32_t>(), d_S.as<uint32_t>(), max_cluster, st));
+  timer.end();
   TOD_CUDA(cudaMemcpyAsync(physical, d_P.ptr, mat_bytes, cudaMemcpyDeviceToHost, st));
   TOD_CUDA(cudaMemcpyAsync(sample, d_S.ptr, mat_bytes, cudaMemcpyDeviceToHost, st));
   TOD_CUDA(cudaStreamSynchronize(st));
+  timer.finish();
   return TOD_OK;
 }
 
@@ -135,14 +162,18 @@ int tod_score_hypotheses(int32_t device, int32_t n, const float *query_pts, cons
   TOD_CUDA(cudaMemcpyAsync(d_V.ptr, valid, size_t(W) * 4, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(d_F.ptr, finite.data(), size_t(W) * 4, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(d_h.ptr, hyps.data(), hyps.size() * 4, cudaMemcpyHostToDevice, st));
+  StageTimer timer(st);
+  timer.begin();
   TOD_CUDA(tod::launch_score_hypotheses_batched(d_desc.ptr, d_q.as<float>(), d_t.as<float>(), d_P.as<uint32_t>(),
                                                 d_V.as<uint32_t>(), d_F.as<uint32_t>(), n_hyp, d_h.as<uint32_t>(),
                                                 threshold, d_c.as<int32_t>(), R ? d_R.as<float>() : nullptr,
                                                 T ? d_T.as<float>() : nullptr, st));
+  timer.end();
   TOD_CUDA(cudaMemcpyAsync(counts, d_c.ptr, size_t(n_hyp) * 4, cudaMemcpyDeviceToHost, st));
   if (R) TOD_CUDA(cudaMemcpyAsync(R, d_R.ptr, size_t(n_hyp) * 36, cudaMemcpyDeviceToHost, st));
   if (T) TOD_CUDA(cudaMemcpyAsync(T, d_T.ptr, size_t(n_hyp) * 12, cudaMemcpyDeviceToHost, st));
   TOD_CUDA(cudaStreamSynchronize(st));
+  timer.finish();
   return TOD_OK;
 }
 

@@ -17,11 +17,19 @@
 // mask; the gate can only keep or zero a count, so it is evaluated lazily; the early stop of computeModel is a prefix
 // of the hypothesis list, so hypotheses are generated and scored in growing batches.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <map>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "clique.h"
@@ -41,6 +49,8 @@ struct Cluster {
   std::vector<float> q, t, px;     // n x 3, n x 3, n x 2
   std::vector<uint32_t> qidx;      // query_indices_ (non-decreasing)
   std::vector<uint32_t> valid;     // W words: valid_indices_ as a mask
+  std::vector<uint16_t> sdeg;      // per correspondence: popc(S[v] & valid) for the current round (clique gate :209-213)
+  std::vector<uint32_t> core7;     // W words: 7-core of the valid sample graph this round — every 8-clique lives in it
   std::vector<uint32_t> finite;    // W words: all six coordinates finite
   int n_valid = 0;
   int64_t point_offset = 0, matrix_offset = 0, valid_offset = 0;
@@ -80,24 +90,39 @@ inline int mask_count(const uint32_t *m, int W) {
   return c;
 }
 
-// drawIndexSampleHelper (sac_model_registration_graph.h:102-132) on bit masks.  `cur` is consumed.
-bool draw_samples(const Cluster &c, std::vector<uint32_t> &cur, int count, int n_samples, uint64_t &rng,
-                  std::vector<uint32_t> &out) {
+// Per-thread scratch of the sampler: one candidate mask per recursion level (no allocation per hypothesis).
+struct SamplerScratch {
+  std::vector<uint32_t> level[3];
+  void fit(int W) {
+    for (auto &v : level)
+      if (int(v.size()) < W) v.resize(size_t(W));
+  }
+};
+
+// drawIndexSampleHelper (sac_model_registration_graph.h:102-132) on bit masks.  `cur` (level `depth`'s mask) is
+// consumed.  out[] receives the samples deepest-first, like samples_.push_back in the reference.
+bool draw_samples(const Cluster &c, SamplerScratch &sc, int depth, int count, int n_samples, uint64_t &rng,
+                  uint32_t *out, int &n_out) {
   if (n_samples == 0) return true;
   if (count == 0) return false;
   const int W = c.W;
-  std::vector<uint32_t> next(static_cast<size_t>(W));
+  uint32_t *cur = sc.level[depth].data();
   while (true) {
     const uint32_t r = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count));
-    const uint32_t s = select_bit(cur.data(), W, r);
+    const uint32_t s = select_bit(cur, W, r);
+    if (n_samples == 1) {  // the recursion below would return true at once (n_samples - 1 == 0)
+      out[n_out++] = s;
+      return true;
+    }
     const uint32_t *row = c.S + size_t(s) * W;
+    uint32_t *next = sc.level[depth + 1].data();
     int nc = 0;
     for (int w = 0; w < W; ++w) {
-      next[size_t(w)] = cur[size_t(w)] & row[w];
-      nc += popc32(next[size_t(w)]);
+      next[w] = cur[w] & row[w];
+      nc += popc32(next[w]);
     }
-    if (draw_samples(c, next, nc, n_samples - 1, rng, out)) {
-      out.push_back(s);
+    if (draw_samples(c, sc, depth + 1, nc, n_samples - 1, rng, out, n_out)) {
+      out[n_out++] = s;
       return true;
     }
     cur[s >> 5] &= ~(1u << (s & 31));
@@ -107,20 +132,146 @@ bool draw_samples(const Cluster &c, std::vector<uint32_t> &cur, int count, int n
 
 // getSamples (:141-168).  Returns false when the valid set holds no triangle of the sample graph (every one of the
 // reference's 1000 retries would then fail identically, so one exhaustive attempt decides).
-bool get_samples(const Cluster &c, uint64_t &rng, uint32_t triple[3]) {
+bool get_samples(const Cluster &c, SamplerScratch &sc, uint64_t &rng, uint32_t triple[3]) {
   if (c.n_valid < 3) return false;
-  std::vector<uint32_t> cur(c.valid);
-  std::vector<uint32_t> out;
-  if (!draw_samples(c, cur, c.n_valid, 3, rng, out)) return false;
-  triple[0] = out[0];
-  triple[1] = out[1];
-  triple[2] = out[2];
-  return true;
+  sc.fit(c.W);
+  std::copy(c.valid.begin(), c.valid.end(), sc.level[0].begin());
+  int n_out = 0;
+  return draw_samples(c, sc, 0, c.n_valid, 3, rng, triple, n_out);
+}
+
+// Small persistent pool: the per-cluster host work of a round (sampler, replay + gate, refinement + invalidation) is
+// independent across objects, so it is spread over the host cores.  Results do not depend on the thread count: every
+// cluster owns its sampler stream (tod_rng_seed(seed, object, round)) and its state.
+class HostPool {
+ public:
+  explicit HostPool(int n_threads) {
+    for (int t = 1; t < n_threads; ++t) workers_.emplace_back([this, t] { loop(t); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      quit_ = true;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    for (auto &w : workers_) w.join();
+  }
+  int size() const { return int(workers_.size()) + 1; }
+  // fn(item, thread) for item in [0, n); the caller is thread 0
+  void run(int n, const std::function<void(int, int)> &fn) {
+    if (n <= 0) return;
+    if (workers_.empty() || n == 1) {
+      for (int i = 0; i < n; ++i) fn(i, 0);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &fn;
+      n_ = n;
+      next_.store(0);
+      pending_ = int(workers_.size());
+      ++epoch_;
+    }
+    cv_.notify_all();
+    work(0);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work(int t) {
+    for (;;) {
+      const int i = next_.fetch_add(1);
+      if (i >= n_) break;
+      (*fn_)(i, t);
+    }
+  }
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (quit_) return;
+      }
+      work(t);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int, int)> *fn_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool quit_ = false;
+};
+
+using Clock = std::chrono::steady_clock;
+inline double ms_since(Clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
 }
 
 struct GateScratch {
   std::vector<uint32_t> inliers, filtered, mask;
+  std::vector<uint32_t> adj, alive, uncoloured, cls;  // induced sub-graph as a dense bit-matrix + work masks
+  std::vector<int> deg, rank;
+  long calls = 0, proved_empty = 0;  // gate evaluations / those settled by the no-8-clique proof
+  long core_rejects = 0;             // settled even earlier: fewer than 8 candidates inside the round's 7-core
+  double ms_setup = 0, ms_proof = 0, ms_search = 0;
 };
+
+// Exact early "no": true iff the induced graph provably has NO clique of `size` vertices, so the bounded search of the
+// reference (whatever its order, early stop and step budget) cannot return one and the gate fails
+// (sac_model_registration_graph.h:260-265 needs clique.size() > minimal_size).  Proof = (size-1)-core peeling, then a
+// greedy colouring of the core: fewer than `size` colours bound the clique number.  adj: nv x words bit-matrix.
+bool proves_no_clique(GateScratch &g, int nv, int words, int size) {
+  g.alive.assign(size_t(words), 0u);
+  for (int v = 0; v < nv; ++v) g.alive[size_t(v) >> 5] |= 1u << (v & 31);
+  g.deg.assign(size_t(nv), 0);
+  int n_alive = nv;
+  bool changed = true;
+  while (changed) {  // peel vertices that have fewer than size-1 live neighbours
+    changed = false;
+    for (int v = 0; v < nv; ++v) {
+      if (!((g.alive[size_t(v) >> 5] >> (v & 31)) & 1u)) continue;
+      const uint32_t *row = g.adj.data() + size_t(v) * words;
+      int d = 0;
+      for (int w = 0; w < words; ++w) d += popc32(row[w] & g.alive[size_t(w)]);
+      if (d < size - 1) {
+        g.alive[size_t(v) >> 5] &= ~(1u << (v & 31));
+        --n_alive;
+        changed = true;
+      }
+    }
+  }
+  if (n_alive < size) return true;
+  // greedy colouring of the core with independent sets built on bit masks
+  g.uncoloured = g.alive;
+  int colours = 0, left = n_alive;
+  while (left > 0) {
+    if (++colours >= size) return false;  // bound not good enough: run the real search
+    g.cls = g.uncoloured;                 // candidates for this colour class
+    for (int w = 0; w < words; ++w) {
+      while (g.cls[size_t(w)]) {
+        const int v = w * 32 + __builtin_ctz(g.cls[size_t(w)]);
+        g.uncoloured[size_t(v) >> 5] &= ~(1u << (v & 31));
+        --left;
+        const uint32_t *row = g.adj.data() + size_t(v) * words;
+        for (int x = w; x < words; ++x) g.cls[size_t(x)] &= ~row[x];  // neighbours cannot share the colour
+        g.cls[size_t(w)] &= ~(1u << (v & 31));
+      }
+    }
+  }
+  return colours < size;
+}
 
 // Inlier list of one hypothesis exactly as selectWithinDistance builds it before the gate (:178-200): common valid
 // physical neighbours in ascending order, then the samples; each kept if it passes the distance test.
@@ -159,14 +310,22 @@ void hypothesis_inliers(const Cluster &c, const uint32_t s[3], bool inf_threshol
 bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScratch &g) {
   const size_t minimal = 7;  // std::min(best_inlier_number_, 7) with best_inlier_number_ >= 8 always (:85, :203)
   const int W = c.W;
+  const Clock::time_point t0 = Clock::now();
   g.filtered.clear();
-  for (uint32_t v : inliers) {  // :209-213 — sample-degree inside the current valid set
-    const uint32_t *row = c.S + size_t(v) * W;
-    int deg = 0;
-    for (int w = 0; w < W; ++w) deg += popc32(row[w] & c.valid[size_t(w)]);
-    if (size_t(deg) >= minimal) g.filtered.push_back(v);
-  }
+  for (uint32_t v : inliers)  // :209-213 — sample-degree inside the current valid set (precomputed per round)
+    if (size_t(c.sdeg[v]) >= minimal) g.filtered.push_back(v);
   if (g.filtered.size() <= minimal) return false;
+  // Exact early "no": a clique of 8 vertices has minimum degree 7, so it lies inside the 7-core of the round's valid
+  // sample graph; with fewer than 8 candidates there the search below cannot return one and the gate fails (:260-265).
+  {
+    size_t in_core = 0;
+    for (uint32_t v : g.filtered) in_core += (c.core7[v >> 5] >> (v & 31)) & 1u;
+    if (in_core <= minimal) {
+      ++g.calls;
+      ++g.core_rejects;
+      return false;
+    }
+  }
   std::sort(g.filtered.begin(), g.filtered.end());
   g.mask.assign(size_t(W), 0u);
   for (uint32_t v : g.filtered) g.mask[v >> 5] |= 1u << (v & 31);
@@ -179,17 +338,42 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
     if (reach > minimal) break;
   }
   if (reach <= minimal) return false;
-  // induced sample sub-graph on `filtered` (:241-255), then the bounded clique search (:258-265)
+  // induced sample sub-graph on `filtered` (:241-255) as a dense nv x words bit-matrix: vertex a = a-th smallest
+  // member of `filtered`, i.e. its rank inside the mask
   const int nv = int(g.filtered.size());
-  tod::CliqueFinder finder(nv);
-  for (int a = 0; a < nv - 1; ++a) {
+  const int words = (nv + 31) / 32;
+  ++g.calls;
+  g.rank.resize(size_t(W) + 1);
+  g.rank[0] = 0;
+  for (int w = 0; w < W; ++w) g.rank[size_t(w) + 1] = g.rank[size_t(w)] + popc32(g.mask[size_t(w)]);
+  g.adj.assign(size_t(nv) * words, 0u);
+  for (int a = 0; a < nv; ++a) {
     const uint32_t *row = c.S + size_t(g.filtered[size_t(a)]) * W;
-    for (int b = a + 1; b < nv; ++b) {
-      const uint32_t v = g.filtered[size_t(b)];
-      if ((row[v >> 5] >> (v & 31)) & 1u) finder.add_edge(a, b);
+    uint32_t *out = g.adj.data() + size_t(a) * words;
+    for (int w = 0; w < W; ++w) {
+      uint32_t m = row[w] & g.mask[size_t(w)];
+      while (m) {
+        const int bit = __builtin_ctz(m);
+        m &= m - 1;
+        const int b = g.rank[size_t(w)] + popc32(g.mask[size_t(w)] & ((1u << bit) - 1u));
+        out[b >> 5] |= 1u << (b & 31);
+      }
     }
   }
-  return finder.find(unsigned(minimal)).size() > minimal;
+  const Clock::time_point t1 = Clock::now();
+  g.ms_setup += std::chrono::duration<double, std::milli>(t1 - t0).count();
+  const bool none = proves_no_clique(g, nv, words, int(minimal) + 1);
+  const Clock::time_point t2 = Clock::now();
+  g.ms_proof += std::chrono::duration<double, std::milli>(t2 - t1).count();
+  if (none) {
+    ++g.proved_empty;
+    return false;
+  }
+  // the bounded clique search (:258-265)
+  tod::CliqueFinder finder(nv, g.adj.data());
+  const bool ok = finder.find(unsigned(minimal)).size() > minimal;
+  g.ms_search += ms_since(t2);
+  return ok;
 }
 
 }  // namespace
@@ -203,6 +387,9 @@ struct tod_guess {
   float k2_ms = 0, k3_ms = 0;
   int64_t n_hyp_total = 0;
   int32_t n_rounds = 0;
+  // host wall-clock profile of the last process call (ms): see tod_guess_last_profile
+  double prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  HostPool *pool = nullptr;
 };
 
 extern "C" {
@@ -246,7 +433,13 @@ void tod_guess_destroy(tod_guess *g) {
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->stream) cudaStreamDestroy(g->stream);
+  delete g->pool;
   delete g;
+}
+
+void tod_guess_last_profile(const tod_guess *g, double *ms12) {
+  if (!ms12) return;
+  for (int i = 0; i < 12; ++i) ms12[i] = g ? g->prof[i] : 0.0;
 }
 
 void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_t *n_hyp, int32_t *n_rounds) {
@@ -265,6 +458,9 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
   g->k2_ms = g->k3_ms = 0.f;
   g->n_hyp_total = 0;
   g->n_rounds = 0;
+  for (double &v : g->prof) v = 0.0;
+  const Clock::time_point t_total = Clock::now();
+  Clock::time_point t_phase = t_total;
   TOD_REQUIRE(n_kp >= 0 && k >= 1 && n_objects >= 0 && max_poses >= 0, "bad sizes");
   if (n_kp == 0) return TOD_OK;
   TOD_REQUIRE(keypoints && matches && counts && points3d && spans && (poses || max_poses == 0), "null input buffer");
@@ -383,6 +579,7 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
     c->S = g->h_S.data() + c->matrix_offset;
   }
   // "InvalidateIndices({})" at the end of FillAdjacency is a no-op (quirk Q4): no pruning before the first round.
+  g->prof[0] = ms_since(t_phase);  // ClusterPerObject + upload + K2 + bit-matrix download
 
   // ---- RANSAC rounds, all active objects in lock-step ------------------------------------------------------------------
   struct Found {
@@ -391,18 +588,33 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
     tod_pose pose;
     std::vector<uint32_t> kp;
   };
-  std::vector<Found> found;
   const int max_iter = int(g->p.n_ransac_iterations);
-  GateScratch scratch;
-  std::vector<uint32_t> tmp_inliers;
+  // host threads: the per-cluster work is independent (see HostPool); small frames stay on the calling thread
+  if (!g->pool) {
+    int want = g->p.host_threads > 0 ? g->p.host_threads : int(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+    if (const char *e = getenv("TOD_HOST_THREADS")) want = std::max(1, atoi(e));
+    g->pool = new HostPool(want);
+  }
+  HostPool &pool = *g->pool;
+  const int n_thr = pool.size();
+  struct ThreadScratch {
+    GateScratch gate;
+    SamplerScratch sampler;
+    std::vector<uint32_t> inliers;
+    std::string error;
+  };
+  std::vector<ThreadScratch> ts(static_cast<size_t>(n_thr));
+  std::vector<std::vector<Found>> found_by_cluster(clusters.size());
   std::vector<uint32_t> batch_hyps;
   std::vector<int32_t> batch_counts;
   std::vector<float> batch_R, batch_T;
+  std::vector<int> active_idx;
 
   while (true) {
     // start a round on every active cluster (AdjacencyRansac::Ransac, adjacency_ransac.cpp:234-253)
-    bool any = false;
-    for (Cluster *c : clusters) {
+    active_idx.clear();
+    for (size_t ci = 0; ci < clusters.size(); ++ci) {
+      Cluster *c = clusters[ci];
       if (!c->active) continue;
       if (c->n_valid < 3) {  // :238-241 -> no inliers -> below min_inliers -> object finished
         c->active = false;
@@ -415,32 +627,78 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
       c->stopped = false;
       c->best_inliers.clear();
       std::copy(c->valid.begin(), c->valid.end(), all_valid.begin() + c->valid_offset);
-      any = true;
+      active_idx.push_back(int(ci));
     }
-    if (!any) break;
+    if (active_idx.empty()) break;
     ++g->n_rounds;
+    t_phase = Clock::now();
+    pool.run(int(active_idx.size()), [&](int ai, int) {  // sample-degrees inside this round's valid set
+      Cluster *c = clusters[size_t(active_idx[size_t(ai)])];
+      c->sdeg.assign(size_t(c->n), 0);
+      for (int v = 0; v < c->n; ++v) {
+        const uint32_t *row = c->S + size_t(v) * c->W;
+        int d = 0;
+        for (int w = 0; w < c->W; ++w) d += popc32(row[w] & c->valid[size_t(w)]);
+        c->sdeg[size_t(v)] = uint16_t(std::min(d, 65535));
+      }
+      // 7-core of the valid sample graph (peel vertices with fewer than 7 live neighbours until a fixed point)
+      c->core7 = c->valid;
+      std::vector<uint32_t> &core = c->core7;
+      bool changed = true;
+      while (changed) {
+        changed = false;
+        for (int w0 = 0; w0 < c->W; ++w0) {
+          uint32_t m = core[size_t(w0)];
+          while (m) {
+            const int v = w0 * 32 + __builtin_ctz(m);
+            m &= m - 1;
+            const uint32_t *row = c->S + size_t(v) * c->W;
+            int d = 0;
+            for (int w = 0; w < c->W; ++w) d += popc32(row[w] & core[size_t(w)]);
+            if (d < 7) {
+              core[size_t(v) >> 5] &= ~(1u << (v & 31));
+              changed = true;
+            }
+          }
+        }
+      }
+    });
+    g->prof[4] += ms_since(t_phase);
     TOD_CUDA(cudaMemcpyAsync(g->d_valid.ptr, all_valid.data(), all_valid.size() * 4, cudaMemcpyHostToDevice, st));
 
     // computeModel (ransac.h:80-143): hypotheses are drawn and scored in growing batches; the replay below consumes
     // them in order and stops exactly where the reference's loop would.
     int batch_size = 64;
     while (true) {
-      batch_hyps.clear();
-      for (size_t ci = 0; ci < clusters.size(); ++ci) {
-        Cluster *c = clusters[ci];
+      // -- sampler (getSamples, sac_model_registration_graph.h:141-168), clusters in parallel ---------------------------
+      t_phase = Clock::now();
+      pool.run(int(active_idx.size()), [&](int ai, int t) {
+        Cluster *c = clusters[size_t(active_idx[size_t(ai)])];
         c->hyps.clear();
-        if (!c->active || c->stopped) continue;
+        if (c->stopped) return;
         // the loop can run at most until iterations_ exceeds max_iterations_ (ransac.h:132-134)
         const int room = std::min(batch_size, max_iter + 1 - c->iterations);
-        c->batch_begin = int(batch_hyps.size() / 4);
         for (int h = 0; h < room; ++h) {
           uint32_t tr[3];
-          if (!get_samples(*c, c->rng, tr)) break;  // empty selection -> loop breaks (ransac.h:100-101)
+          if (!get_samples(*c, ts[size_t(t)].sampler, c->rng, tr)) break;  // empty selection -> break (ransac.h:100-101)
           c->hyps.insert(c->hyps.end(), tr, tr + 3);
-          batch_hyps.insert(batch_hyps.end(), tr, tr + 3);
+        }
+      });
+      batch_hyps.clear();
+      for (int ci : active_idx) {
+        Cluster *c = clusters[size_t(ci)];
+        c->batch_begin = int(batch_hyps.size() / 4);
+        for (size_t h = 0; h + 2 < c->hyps.size(); h += 3) {
+          batch_hyps.push_back(c->hyps[h]);
+          batch_hyps.push_back(c->hyps[h + 1]);
+          batch_hyps.push_back(c->hyps[h + 2]);
           batch_hyps.push_back(uint32_t(ci));
         }
       }
+      g->prof[1] += ms_since(t_phase);
+
+      // -- K3: one launch for every hypothesis of every object ----------------------------------------------------------
+      t_phase = Clock::now();
       const int H = int(batch_hyps.size() / 4);
       if (H > 0) {
         batch_counts.resize(size_t(H));
@@ -470,14 +728,18 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
         g->k3_ms += ms;
         g->n_hyp_total += H;
       }
+      g->prof[2] += ms_since(t_phase);
 
-      bool more = false;
-      for (Cluster *c : clusters) {
-        if (!c->active || c->stopped) continue;
+      // -- replay of computeModel's scan (ransac.h:95-135) + lazy clique gate, clusters in parallel ----------------------
+      t_phase = Clock::now();
+      std::atomic<int> more{0};
+      pool.run(int(active_idx.size()), [&](int ai, int t) {
+        Cluster *c = clusters[size_t(active_idx[size_t(ai)])];
+        if (c->stopped) return;
+        ThreadScratch &sc = ts[size_t(t)];
         const int nh = int(c->hyps.size() / 3);
         const int room = std::min(batch_size, max_iter + 1 - c->iterations);
-        int h = 0;
-        for (; h < nh; ++h) {
+        for (int h = 0; h < nh; ++h) {
           if (!(double(c->iterations) < c->k)) {  // while (iterations_ < k)
             c->stopped = true;
             break;
@@ -488,18 +750,23 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
             const uint32_t *s = c->hyps.data() + size_t(h) * 3;
             const float *R = inf_thr ? nullptr : batch_R.data() + size_t(c->batch_begin + h) * 9;
             const float *T = inf_thr ? nullptr : batch_T.data() + size_t(c->batch_begin + h) * 3;
-            hypothesis_inliers(*c, s, inf_thr, thr2, R, T, tmp_inliers);
-            if (int(tmp_inliers.size()) != pre)
-              return fail(TOD_ERR_STATE, "K3 count %d disagrees with the host candidate list %zu (object %d)", pre,
-                          tmp_inliers.size(), c->object);
+            hypothesis_inliers(*c, s, inf_thr, thr2, R, T, sc.inliers);
+            if (int(sc.inliers.size()) != pre) {
+              char buf[160];
+              snprintf(buf, sizeof(buf), "K3 count %d disagrees with the host candidate list %zu (object %d)", pre,
+                       sc.inliers.size(), c->object);
+              sc.error = buf;
+              c->stopped = true;
+              return;
+            }
             int final_count = pre;
-            if (tmp_inliers.size() > 7 && !clique_gate(*c, tmp_inliers, scratch)) {
-              tmp_inliers.clear();
+            if (sc.inliers.size() > 7 && !clique_gate(*c, sc.inliers, sc.gate)) {
+              sc.inliers.clear();
               final_count = 0;
             }
             if (final_count > c->n_best) {  // ransac.h:115-130
               c->n_best = final_count;
-              c->best_inliers = tmp_inliers;
+              c->best_inliers = sc.inliers;
               if (R) std::memcpy(c->best_R, R, sizeof(c->best_R));
               if (T) std::memcpy(c->best_T, T, sizeof(c->best_T));
               const double w = double(c->n_best) / double(c->n_valid);
@@ -512,26 +779,31 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
           ++c->iterations;
           if (c->iterations > max_iter) {
             c->stopped = true;
-            ++h;
             break;
           }
         }
         if (!c->stopped) {
           if (nh < room) c->stopped = true;                        // sampler ran dry: selection.empty() -> break
           else if (!(double(c->iterations) < c->k)) c->stopped = true;
-          else more = true;
+          else more.store(1, std::memory_order_relaxed);
         }
-      }
-      if (!more) break;
+      });
+      g->prof[3] += ms_since(t_phase);
+      for (const ThreadScratch &sc : ts)
+        if (!sc.error.empty()) return fail(TOD_ERR_STATE, "%s", sc.error.c_str());
+      if (!more.load()) break;
       batch_size = std::min(batch_size * 4, 4096);
     }
 
-    // finish the round per cluster: refinement, pose, invalidation (adjacency_ransac.cpp:255-308, GuessGenerator.cpp:205-230)
-    for (Cluster *c : clusters) {
-      if (!c->active) continue;
+    // finish the round per cluster: refinement, pose, invalidation (adjacency_ransac.cpp:255-308,
+    // GuessGenerator.cpp:205-230), clusters in parallel
+    t_phase = Clock::now();
+    pool.run(int(active_idx.size()), [&](int ai, int) {
+      const int ci = active_idx[size_t(ai)];
+      Cluster *c = clusters[size_t(ci)];
       if (c->best_inliers.empty()) {  // computeModel() returned false -> inliers_in stays empty -> below min_inliers
         c->active = false;
-        continue;
+        return;
       }
       std::vector<uint32_t> inliers(c->best_inliers);
       std::sort(inliers.begin(), inliers.end());
@@ -591,7 +863,7 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
       kp.erase(std::unique(kp.begin(), kp.end()), kp.end());
       if (kp.size() < g->p.min_inliers) {  // GuessGenerator.cpp:205-206
         c->active = false;
-        continue;
+        return;
       }
       // InvalidateQueryIndices (:93-123): drop every still-valid match whose keypoint is an inlier, then cascade
       std::vector<uint32_t> todo;
@@ -627,15 +899,26 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
       f.pose.object_index = c->object;
       f.pose.n_inliers = int32_t(kp.size());
       f.kp.swap(kp);
-      found.push_back(std::move(f));
+      found_by_cluster[size_t(ci)].push_back(std::move(f));
       ++c->round;
-    }
+    });
+    g->prof[4] += ms_since(t_phase);
   }
 
-  // emission order of the reference: objects ascending (std::map), rounds in order (GuessGenerator.cpp:170-235)
-  std::stable_sort(found.begin(), found.end(), [](const Found &a, const Found &b) {
-    return a.object != b.object ? a.object < b.object : a.round < b.round;
-  });
+  // emission order of the reference: objects ascending (std::map), rounds in order (GuessGenerator.cpp:170-235);
+  // `clusters` is already in ascending object order and every cluster appended its rounds in order
+  std::vector<Found> found;
+  for (auto &v : found_by_cluster)
+    for (auto &f : v) found.push_back(std::move(f));
+  for (const ThreadScratch &sc : ts) {
+    g->prof[5] += double(sc.gate.calls);
+    g->prof[6] += double(sc.gate.proved_empty);
+    g->prof[11] += double(sc.gate.core_rejects);
+    g->prof[8] += sc.gate.ms_setup;
+    g->prof[9] += sc.gate.ms_proof;
+    g->prof[10] += sc.gate.ms_search;
+  }
+  g->prof[7] = ms_since(t_total);
   if (int64_t(found.size()) > max_poses)
     return fail(TOD_ERR_LIMIT, "%zu poses found but max_poses = %d", found.size(), max_poses);
   int64_t n_inl = 0;
