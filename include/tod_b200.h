@@ -125,6 +125,12 @@ int32_t tod_matcher_k(const tod_matcher *m);
 int tod_matcher_knn(tod_matcher *m, const uint8_t *descriptors, int32_t nq, tod_match *matches, int32_t *counts,
                     float *points3d);
 
+/* Sharding of the concatenated DB over `shard_count` GPUs (host-only, no device needed): rank r holds the contiguous
+ * global rows [*begin, *begin + *rows), ceil(total/shard_count) rows each except the last ranks.  tod_matcher_train
+ * uses exactly this split.  tod_pack_key builds the u32 candidate key that travels between ranks. */
+int tod_shard_range(int64_t total_rows, int32_t shard_rank, int32_t shard_count, int64_t *begin, int64_t *rows);
+uint32_t tod_pack_key(uint32_t distance, uint32_t global_row);
+
 /* Device-resident stages of the same call, for the sharded (one process per GPU) path. All pointers are device
  * pointers on the handle's device; `stream` is a cudaStream_t (NULL = the handle's own stream).
  *   knn_keys: this shard's top-k per query as packed keys (distance << 23 | global_row), ascending, padded with

@@ -139,3 +139,45 @@ def test_empty_and_error_paths():
     with pytest.raises(capi.TodError):
         DescriptorMatcher(k=9)
     m.close()
+
+
+@both_kernels
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_db_merge_equals_unsharded(world, kernel):
+    """The multi-GPU path on one device: `world` matcher handles, each holding one row range of the DB, produce packed
+    keys (knn_keys_device); the concatenation (what the NCCL all-gather delivers) goes through merge_device.  Must
+    equal the single-handle result bit for bit — shard boundaries cut through objects and through runs of ties."""
+    import torch
+    rng = np.random.default_rng(world)
+    descs, points = synth.make_db(5, [1500, 700, 2300, 41, 999], seed=60 + world)
+    descs[1][:, :] = 0
+    descs[1][:, 7] = rng.integers(0, 4, descs[1].shape[0])           # a tie-heavy object in the middle
+    q, _, _ = synth.make_queries(descs, 333, seed=61)
+    q[:50] = 0
+    k, radius = 5, 0
+    dev = torch.device("cuda", 0)
+    nq = q.shape[0]
+    q_dev = torch.from_numpy(q).to(dev)
+    keys_all = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
+    handles = []
+    for r in range(world):
+        m = DescriptorMatcher(k=k, radius=radius, kernel=KERNELS[kernel], shard_rank=r, shard_count=world)
+        for i, (d, p) in enumerate(zip(descs, points)):
+            m.add_object("o%d" % i, d, p)
+        m.train()
+        m.knn_keys_device(q_dev.data_ptr(), nq, keys_all[r].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        handles.append(m)
+    assert sum(h.shard_rows for h in handles) == sum(d.shape[0] for d in descs)
+    matches = torch.empty((nq, k, 4), dtype=torch.int32, device=dev)
+    counts = torch.empty((nq,), dtype=torch.int32, device=dev)
+    pts = torch.empty((nq, k, 3), dtype=torch.float32, device=dev)
+    handles[0].merge_device(keys_all.data_ptr(), world, nq, matches.data_ptr(), counts.data_ptr(), pts.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = matches.cpu().numpy().view(capi.MATCH_DTYPE).reshape(nq, k)
+    em, ec = hk.knn_c(q, descs, k, radius)
+    assert_matches_equal(got, counts.cpu().numpy(), em["trainIdx"], em["imgIdx"], em["distance"], ec)
+    e3 = hk.gather_points3d(em, ec, points)
+    assert (pts.cpu().numpy() == e3).all()
+    for h in handles:
+        h.close()

@@ -62,6 +62,8 @@ SIGNATURES = [
     ("tod_matcher_span", _F, [_P, _I32]),
     ("tod_matcher_k", _I32, [_P]),
     ("tod_matcher_knn", ctypes.c_int, [_P, _P, _I32, _P, _P, _P]),
+    ("tod_shard_range", ctypes.c_int, [_I64, _I32, _I32, ctypes.POINTER(_I64), ctypes.POINTER(_I64)]),
+    ("tod_pack_key", _U32, [_U32, _U32]),
     ("tod_matcher_knn_keys_device", ctypes.c_int, [_P, _P, _I32, _P, _P]),
     ("tod_matcher_merge_device", ctypes.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P]),
     ("tod_matcher_last_k1_ms", _F, [_P]),

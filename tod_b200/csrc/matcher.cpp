@@ -128,6 +128,20 @@ int tod_matcher_params_from_json(const char *search_json_params, tod_matcher_par
   return TOD_OK;
 }
 
+int tod_shard_range(int64_t total_rows, int32_t shard_rank, int32_t shard_count, int64_t *begin, int64_t *rows) {
+  TOD_REQUIRE(begin && rows, "null argument");
+  TOD_REQUIRE(total_rows >= 0 && shard_count >= 1 && shard_rank >= 0 && shard_rank < shard_count, "bad shard %d/%d",
+              shard_rank, shard_count);
+  const int64_t per = (total_rows + shard_count - 1) / shard_count;
+  *begin = std::min<int64_t>(total_rows, per * shard_rank);
+  *rows = std::min<int64_t>(total_rows, *begin + per) - *begin;
+  return TOD_OK;
+}
+
+uint32_t tod_pack_key(uint32_t distance, uint32_t global_row) {
+  return (std::min<uint32_t>(distance, 511u) << tod::kKeyRowBits) | (global_row & tod::kKeyRowMask);
+}
+
 int tod_matcher_create(const tod_matcher_params *p, tod_matcher **out) {
   TOD_REQUIRE(p && out, "null argument");
   TOD_REQUIRE(p->k >= 1 && p->k <= TOD_MAX_K, "k must be in 1..%d (got %d)", TOD_MAX_K, p->k);
@@ -210,9 +224,7 @@ int tod_matcher_train(tod_matcher *m) {
   TOD_REQUIRE(m, "null argument");
   if (int rc = use_device(m)) return rc;
   const int64_t total = m->offsets.back();
-  const int64_t per = (total + m->p.shard_count - 1) / m->p.shard_count;
-  m->shard_begin = std::min<int64_t>(total, per * m->p.shard_rank);
-  m->shard_rows = std::min<int64_t>(total, m->shard_begin + per) - m->shard_begin;
+  if (int rc = tod_shard_range(total, m->p.shard_rank, m->p.shard_count, &m->shard_begin, &m->shard_rows)) return rc;
   TOD_CUDA(m->d_db.reserve(std::max<size_t>(size_t(m->shard_rows) * 32, 256)));
   TOD_CUDA(m->d_pts.reserve(std::max<size_t>(size_t(total) * 3 * sizeof(float), 256)));
   TOD_CUDA(m->d_offsets.reserve(m->offsets.size() * sizeof(uint32_t)));
