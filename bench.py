@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=8, help="frames per step (batch)")
+    ap.add_argument("--frames", type=int, default=32, help="frames per step (batch)")
     ap.add_argument("--keypoints", type=int, default=2000)
     ap.add_argument("--objects", type=int, default=100)
     ap.add_argument("--rows", type=int, default=10000, help="descriptors per object")
@@ -222,7 +222,8 @@ def run_ours(args):
 
     k = args.k
     nqt = queries.shape[0]
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)     # explicit, non-legacy: K1 / NCCL / merge are all ordered on it
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     q_dev = torch.from_numpy(queries).to(dev)
     keys = torch.empty((nqt, k), dtype=torch.int32, device=dev)

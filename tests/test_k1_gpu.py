@@ -159,20 +159,26 @@ def test_sharded_db_merge_equals_unsharded(world, kernel):
     nq = q.shape[0]
     q_dev = torch.from_numpy(q).to(dev)
     keys_all = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    # one explicit stream for every handle: a NULL stream argument means "the handle's own stream", and the handles'
+    # streams are not ordered with respect to each other
+    stream = torch.cuda.Stream()
+    sptr = stream.cuda_stream
+    assert sptr != 0
     handles = []
     for r in range(world):
         m = DescriptorMatcher(k=k, radius=radius, kernel=KERNELS[kernel], shard_rank=r, shard_count=world)
         for i, (d, p) in enumerate(zip(descs, points)):
             m.add_object("o%d" % i, d, p)
         m.train()
-        m.knn_keys_device(q_dev.data_ptr(), nq, keys_all[r].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        m.knn_keys_device(q_dev.data_ptr(), nq, keys_all[r].data_ptr(), sptr)
         handles.append(m)
     assert sum(h.shard_rows for h in handles) == sum(d.shape[0] for d in descs)
     matches = torch.empty((nq, k, 4), dtype=torch.int32, device=dev)
     counts = torch.empty((nq,), dtype=torch.int32, device=dev)
     pts = torch.empty((nq, k, 3), dtype=torch.float32, device=dev)
     handles[0].merge_device(keys_all.data_ptr(), world, nq, matches.data_ptr(), counts.data_ptr(), pts.data_ptr(),
-                            torch.cuda.current_stream().cuda_stream)
+                            sptr)
     torch.cuda.synchronize()
     got = matches.cpu().numpy().view(capi.MATCH_DTYPE).reshape(nq, k)
     em, ec = hk.knn_c(q, descs, k, radius)

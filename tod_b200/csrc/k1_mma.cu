@@ -243,8 +243,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // instruction fetch — profiles/r1_k1_stats.md) and fed from REGISTERS: the accumulator stage has already been handed
 // back to the tensor core when it runs.  Called warp-uniformly for one 32-column sub-group in which some lane saw a
 // candidate.  p0..p15 hold the sub-group's dot products as packed int16 pairs (register r = columns 2r, 2r + 1).
-// Builds each lane's hit mask branch-free, then loops over the UNION of the lanes' hit columns (warp-uniform trip
-// count, usually 1) and inserts the candidate into the hitting lanes' sorted top-k lists in shared memory.
+// Builds each lane's hit mask branch-free; every lane then walks its own hit columns (usually none or one) and inserts
+// the candidates into its sorted top-k list in shared memory.
 // Returns the new dot-product threshold.
 //   list + i * 4 * kBlockM (i < k), a shared::cta address : ascending packed keys
 //   n_valid : columns of the sub-group that are real db rows (the last tile of a chunk may be partial)
@@ -255,36 +255,53 @@ __device__ __noinline__ int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t 
                                              int n_valid, int thr_dot, uint32_t *gthr) {
   constexpr uint32_t kStride = 4u * kBlockM;  // bytes between consecutive slots of one list
   const uint32_t v[16] = {p0, p1, p2, p3, p4, p5, p6, p7, p8, p9, p10, p11, p12, p13, p14, p15};
-  // dot > thr  <=>  value-in-the-high-half >= (thr + 1) << 16   (the low half only adds [0, 65535])
-  const int th = (thr_dot + 1) << 16;
-  uint32_t mask = 0;
+  // Hit mask, 3 instructions per register: d = v - (thr + 1) per int16 half (VIADD.16x2, no carry between halves;
+  // |d| < 1100 so no wrap) is non-negative exactly where dot > thr.  Bit r of the mask <- low half of register r
+  // (column 2r), bit 16 + r <- high half (column 2r + 1).
+  const uint32_t neg = uint32_t(-(thr_dot + 1)) & 0xFFFFu;
+  const uint32_t neg2 = neg | (neg << 16);
+  uint32_t m0 = 0, m1 = 0;
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    mask |= (int(v[r] << 16) >= th) ? (1u << (2 * r)) : 0u;
-    mask |= (int(v[r]) >= th) ? (2u << (2 * r)) : 0u;
+    const uint32_t d = __vadd2(v[r], neg2);
+    const uint32_t sh = r < 15 ? (d >> (15 - r)) : d;          // sign bits of the halves -> bits r and 16 + r
+    const uint32_t sel = 0x00010001u << r;
+    if (r & 1) m1 |= ~sh & sel;
+    else m0 |= ~sh & sel;
   }
-  if (n_valid < 32) mask &= (1u << n_valid) - 1u;
-  uint32_t todo = __reduce_or_sync(0xffffffffu, mask);
+  uint32_t mask = m0 | m1;
+  if (n_valid < 32) {
+    const int lo = (n_valid + 1) >> 1, hi = n_valid >> 1;     // valid even / odd columns
+    mask &= ((1u << lo) - 1u) | (((1u << hi) - 1u) << 16);
+  }
 #if TOD_K1_STATS
-  if ((threadIdx.x & 31) == 0) atomicAdd(&g_k1_stats[13], (unsigned long long)__popc(todo));
+  {
+    const unsigned trips = __reduce_max_sync(0xffffffffu, unsigned(__popc(mask)));
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_k1_stats[13], (unsigned long long)trips);
+  }
 #endif
+  // Every lane walks ITS OWN hit columns: the warp runs max-over-lanes trips, not one per distinct column — in the
+  // cold first tiles of a list, where every lane has hits, that is up to 32x fewer trips.  The walk visits even
+  // columns before odd ones, so inside the call candidates are compared by their full key (distance, row), which
+  // makes the result independent of the visiting order; across calls rows only grow.
   bool inserted = false;
+  uint32_t worst = lds_u32(list + uint32_t(k - 1) * kStride);   // k-th best key (0xFFFFFFFF while the list is not full)
 #pragma unroll 1
-  while (todo) {
-    const int i = __ffs(int(todo)) - 1;  // warp-uniform column
-    todo &= todo - 1u;
-    // v[i >> 1] through a select tree (static register indices; i is uniform, so are the predicates)
+  while (mask) {
+    const int b = __ffs(int(mask)) - 1;
+    mask &= mask - 1u;
+    // v[b & 15] through a select tree (static register indices, per-lane predicates)
     uint32_t s8[8], s4[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s8[j] = (i & 16) ? v[8 + j] : v[j];
+    for (int j = 0; j < 8; ++j) s8[j] = (b & 8) ? v[8 + j] : v[j];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) s4[j] = (i & 8) ? s8[4 + j] : s8[j];
-    const uint32_t s2a = (i & 4) ? s4[2] : s4[0], s2b = (i & 4) ? s4[3] : s4[1];
-    const uint32_t x = (i & 2) ? s2b : s2a;
-    const int dot = (i & 1) ? (int(x) >> 16) : (int(x << 16) >> 16);
-    if (((mask >> i) & 1u) && dot > thr_dot) {  // thr_dot may have tightened since the mask was built
-      const uint32_t dist = uint32_t(256 - dot) >> 1;
-      const uint32_t key = (dist << kKeyRowBits) | (grow + uint32_t(i));
+    for (int j = 0; j < 4; ++j) s4[j] = (b & 4) ? s8[4 + j] : s8[j];
+    const uint32_t s2a = (b & 2) ? s4[2] : s4[0], s2b = (b & 2) ? s4[3] : s4[1];
+    const uint32_t x = (b & 1) ? s2b : s2a;
+    const int dot = (b & 16) ? (int(x) >> 16) : (int(x << 16) >> 16);
+    const uint32_t dist = uint32_t(256 - dot) >> 1;
+    const uint32_t key = (dist << kKeyRowBits) | (grow + uint32_t(2 * (b & 15) + (b >> 4)));
+    if (key < worst) {
       // sorted insert: the new key displaces the worst entry and sinks to its place
       int pos = k - 1;
       while (pos > 0) {
@@ -294,13 +311,16 @@ __device__ __noinline__ int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t 
         --pos;
       }
       sts_u32(list + uint32_t(pos) * kStride, key);
-      const uint32_t kth = min(thr_init, lds_u32(list + uint32_t(k - 1) * kStride) >> kKeyRowBits);  // strict bound
-      thr_dot = max(thr_dot, 256 - 2 * int(kth));
+      worst = lds_u32(list + uint32_t(k - 1) * kStride);
       inserted = true;
     }
   }
+  if (inserted) {
+    const uint32_t kth = min(thr_init, worst >> kKeyRowBits);  // strict bound of this list (511 while not full)
+    thr_dot = max(thr_dot, 256 - 2 * int(kth));
+  }
   if (inserted && gthr) {
-    const uint32_t kth = lds_u32(list + uint32_t(k - 1) * kStride) >> kKeyRowBits;   // 511 while the list is not full
+    const uint32_t kth = worst >> kKeyRowBits;   // 511 while the list is not full
     // publish as a fire-and-forget reduction (RED.MIN): a returning atomic would stall the warp for a full L2
     // round trip on every insert.  Everyone, this list included, picks the bound up at its next per-tile refresh.
     if (kth < 511u) atomicMin(gthr, kth);
@@ -614,29 +634,25 @@ K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count) {
   p.n_qtiles = std::max(1, (nq + p.q_tile - 1) / p.q_tile);
   if (kCtas == 2) p.n_qtiles = (p.n_qtiles + 1) & ~1;  // pairs: an odd last group gets an idle partner (queries OOB)
   const int64_t max_chunks = std::max<int64_t>(1, (shard_rows + kBlockN - 1) / kBlockN);
-  // One CTA per SM.  The CTAs of different db chunks for the same queries run side by side (chunk-fastest grid) and
-  // share their bounds, so more chunks = faster-converging thresholds = fewer slow-path insertions; each chunk also
-  // adds two merge sources and a fixed per-CTA start-up cost.  Ask for >= 8 chunks when a chunk keeps >= 64 tiles,
-  // then take the first count that fills whole waves of sm_count CTAs to >= 97% (small grids) — for grids of many
-  // waves the tail is short whatever the count.
-  const int64_t c_lo = std::max<int64_t>(1, std::min<int64_t>(8, max_chunks / 64));
-  const int64_t c_hi = std::min<int64_t>(max_chunks, std::max<int64_t>(std::max<int64_t>(16, c_lo),
-                                                                       (4LL * sm_count) / p.n_qtiles));
-  int64_t best_c = c_lo;
-  double best_eff = 0.0;
-  if (const char *e = getenv("TOD_K1_CHUNKS")) {  // experiments only
-    best_c = std::min<int64_t>(max_chunks, std::max(1, atoi(e)));
-    best_eff = 1.0;
-  }
-  for (int64_t c = c_lo; c <= std::max<int64_t>(c_lo, c_hi); ++c) {
+  // One CTA per SM, so the launch takes about waves(c) x (time of one CTA).  A CTA costs its db tiles plus a fixed
+  // start-up: pipeline fill and, mostly, the cold top-k lists of its first tiles — ~28 tile periods measured with
+  // tools/k1_stats.py (profiles/r1_k1_stats_*.jsonl).  More chunks fill the last wave better but pay the start-up
+  // more often (and add merge sources); pick the chunk count that minimises the modelled time.
+  constexpr double kStartupTiles = 28.0;
+  const int64_t tiles_total = max_chunks;
+  const int64_t c_hi = std::min<int64_t>(max_chunks, 64);
+  int64_t best_c = 1;
+  double best_t = 1e300;
+  for (int64_t c = 1; c <= std::max<int64_t>(1, c_hi); ++c) {
     const int64_t ctas = c * p.n_qtiles;
     const int64_t waves = (ctas + sm_count - 1) / sm_count;
-    const double eff = double(ctas) / double(waves * sm_count);
-    if (eff > best_eff + 1e-9 && best_eff < 0.97) {
-      best_eff = eff;
+    const double t = double(waves) * (kStartupTiles + double((tiles_total + c - 1) / c));
+    if (t < best_t * (1.0 - 1e-9)) {
+      best_t = t;
       best_c = c;
     }
   }
+  if (const char *e = getenv("TOD_K1_CHUNKS")) best_c = std::min<int64_t>(max_chunks, std::max(1, atoi(e)));  // experiments
   int64_t rpc = (shard_rows + best_c - 1) / best_c;
   rpc = std::max<int64_t>(kBlockN, (rpc + kBlockN - 1) / kBlockN * kBlockN);
   p.rows_per_chunk = int(rpc);

@@ -18,9 +18,10 @@ from tod_b200 import DescriptorMatcher, capi, synth  # noqa: E402
 def main():
     frames_list = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1,8,64").split(",")]
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    shards = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # time rank 0 of `shards` (the per-GPU work at N GPUs)
     lib = capi.load()
     descs, points = synth.make_db(100, 10000, seed=synth.BASE_SEED + 2)
-    m = DescriptorMatcher(k=k, radius=0, kernel=capi.TOD_KERNEL_MMA)
+    m = DescriptorMatcher(k=k, radius=0, kernel=capi.TOD_KERNEL_MMA, shard_rank=0, shard_count=shards)
     for i, (d, p) in enumerate(zip(descs, points)):
         m.add_object("o%d" % i, d, p)
     m.train()
@@ -43,8 +44,8 @@ def main():
         s = dict(zip(names, [int(x) for x in out]))
         ctas = max(s["ctas"], 1)
         per_cta = s["cta_cycles"] / ctas
-        d = {"frames": F, "k": k, "k1_ms": ms, "gcmp_s": q.shape[0] * 1e6 / ms / 1e6 * 1e-3 * 1e3 / 1e3 if False else
-             q.shape[0] * 1.0e6 / (ms * 1e-3) / 1e9, "ctas": ctas, "cycles_per_cta": per_cta,
+        d = {"frames": F, "k": k, "shards": shards, "k1_ms": ms,
+             "gcmp_s": q.shape[0] * float(m.shard_rows) / (ms * 1e-3) / 1e9, "ctas": ctas, "cycles_per_cta": per_cta,
              "slow_call_rate": s["slow_calls"] / max(s["epi_groups"], 1),
              "cycles_per_slow_call": s["slow_cycles"] / max(s["slow_calls"], 1),
              "mma_wait_acc_empty_frac": s["mma_wait_acc_empty"] / max(s["cta_cycles"], 1),
