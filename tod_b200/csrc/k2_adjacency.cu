@@ -101,11 +101,20 @@ k2_adjacency_kernel(const int32_t *__restrict__ offsets, const int64_t *__restri
           const float dq2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
           if (!(dq2 > thr_span)) {
             const float dq = __fsqrt_rn(dq2);
-            const double ux = double(__fsub_rn(rt[r][0], tx)), uy = double(__fsub_rn(rt[r][1], ty)),
-                         uz = double(__fsub_rn(rt[r][2], tz));
-            const double s2 = __dadd_rn(__dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)), __dmul_rn(uz, uz));
-            const float dt = __double2float_rn(__dsqrt_rn(s2));
-            const float diff = fabsf(__fsub_rn(dt, dq));
+            const float ux = __fsub_rn(rt[r][0], tx), uy = __fsub_rn(rt[r][1], ty), uz = __fsub_rn(rt[r][2], tz);
+            // dt in single precision first: it differs from the reference's double-accumulated norm by at most
+            // 3.5 * 2^-24 * dt (three rounded products, two rounded adds, one rounded sqrt vs. one final rounding),
+            // so the two comparisons below are already decided unless |dt - dq| is within `tol` (4x that bound) of
+            // a threshold; only then — about one pair in 10^5 — is the reference's exact arithmetic replayed.
+            float dt = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz)));
+            float diff = fabsf(__fsub_rn(dt, dq));
+            const float tol = __fmul_rn(1e-6f, fmaxf(dt, dq));
+            if (!(fabsf(__fsub_rn(diff, e4)) > tol && fabsf(__fsub_rn(diff, e2)) > tol)) {  // also taken for NaNs
+              const double vx = double(ux), vy = double(uy), vz = double(uz);
+              const double s2 = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
+              dt = __double2float_rn(__dsqrt_rn(s2));
+              diff = fabsf(__fsub_rn(dt, dq));
+            }
             if (!(diff > e4)) {
               isP = true;
               const float ax = __fsub_rn(rp[r][0], px), ay = __fsub_rn(rp[r][1], py);

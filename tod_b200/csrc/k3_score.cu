@@ -3,7 +3,7 @@
 // Replaces, per hypothesis, the body of pcl::RandomSampleConsensus::computeModel's loop (src/common/ransac.h:105-113
 // of the reference): computeModelCoefficients -> estimateRigidTransformationSVD
 // (sac_model_registration_graph.h:271-288, :304-347) and the candidate/inlier part of selectWithinDistance
-// (:171-200).  One warp per hypothesis:
+// (:171-200).  One warp per 32 hypotheses (see the kernel); per hypothesis:
 //   candidates = physical[s0] & physical[s1] & physical[s2] & valid            (:178-184, bit-rows instead of lists)
 //   count      = #candidates (+ the 3 samples, :185-186) passing distSq(R q + T, t) < threshold^2   (:192-200)
 // With the reference's never-set threshold (DBL_MAX, sac.h:70) threshold^2 is +inf and the count
@@ -137,6 +137,12 @@ struct K3Cluster {
   int64_t valid_offset;   // in u32 words (offset into both the `valid` and the `finite` bit-vectors)
 };
 
+// One warp scores 32 consecutive hypotheses.
+//   phase 1: lane l fits ITS OWN hypothesis h0 + l (32 different Kabsch solves per warp instruction instead of the same
+//            one 32 times — the double-precision Jacobi is the expensive part of this kernel);
+//   phase 2: for each of the 32 hypotheses in turn, the whole warp ANDs the three physical rows with the valid (and
+//            finite) masks, 128 coalesced bytes per row and step, and reduces the popcounts with one REDUX; with a
+//            finite threshold the owner's (R, T) is broadcast and the set bits are distance-tested, one per lane.
 __global__ void __launch_bounds__(256)
 k3_score_kernel(const K3Cluster *__restrict__ clusters, const float *__restrict__ query,
                 const float *__restrict__ train, const uint32_t *__restrict__ physical,
@@ -144,98 +150,76 @@ k3_score_kernel(const K3Cluster *__restrict__ clusters, const float *__restrict_
                 const uint4 *__restrict__ hyps, double thr2,
                 int exact_inf, int32_t *__restrict__ counts, float *__restrict__ Rout, float *__restrict__ Tout) {
   const int lane = threadIdx.x & 31;
-  const int h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (h >= n_hyp) return;
-  const uint4 hy = __ldg(hyps + h);
-  const K3Cluster cl = clusters[hy.w];
-  const float *q = query + cl.point_offset * 3;
-  const float *t = train + cl.point_offset * 3;
-  const uint32_t s[3] = {hy.x, hy.y, hy.z};
+  const int h0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (h0 >= n_hyp) return;
+  const int h = h0 + lane;
+  const bool mine = h < n_hyp;
+  const uint4 hy = mine ? __ldg(hyps + h) : make_uint4(0, 0, 0, 0);
+  const K3Cluster cl = clusters[mine ? hy.w : __ldg(hyps + h0).w];
 
-  // ---- rigid fit from the 3 samples (every lane computes it: no divergence, no shuffles) ----
-  float ct[3] = {0.f, 0.f, 0.f}, cq[3] = {0.f, 0.f, 0.f};
-  float st[3][3], sq[3][3];
+  // ---- phase 1: rigid fit of this lane's own 3 samples ----
+  float R[9], T[3];
+  bool rt_finite = true;
+  int add = 0;  // the 3 samples themselves (sac_model_registration_graph.h:185-186, :192-200)
+  if (mine) {
+    const float *q = query + cl.point_offset * 3;
+    const float *t = train + cl.point_offset * 3;
+    const uint32_t s[3] = {hy.x, hy.y, hy.z};
+    float ct[3] = {0.f, 0.f, 0.f}, cq[3] = {0.f, 0.f, 0.f};
+    float st[3][3], sq[3][3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      st[i][d] = __ldg(t + size_t(s[i]) * 3 + d);
-      sq[i][d] = __ldg(q + size_t(s[i]) * 3 + d);
-      ct[d] += st[i][d];
-      cq[d] += sq[i][d];
-    }
-  const float third = 1.f / 3.f;  // cv::Vec operator/= multiplies by 1.f/alpha
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    ct[d] *= third;
-    cq[d] *= third;
-  }
-  float Hf[3][3];
-  {
-    double Hd[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      float a[3], b[3];
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        a[d] = st[i][d] - ct[d];
-        b[d] = sq[i][d] - cq[d];
+        st[i][d] = __ldg(t + size_t(s[i]) * 3 + d);
+        sq[i][d] = __ldg(q + size_t(s[i]) * 3 + d);
+        ct[d] += st[i][d];
+        cq[d] += sq[i][d];
+      }
+    const float third = 1.f / 3.f;  // cv::Vec operator/= multiplies by 1.f/alpha
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      ct[d] *= third;
+      cq[d] *= third;
+    }
+    float Hf[3][3];
+    {
+      double Hd[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        float a[3], b[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          a[d] = st[i][d] - ct[d];
+          b[d] = sq[i][d] - cq[d];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Hd[r][c] += double(a[r]) * double(b[c]);
       }
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Hd[r][c] += double(a[r]) * double(b[c]);
+        for (int c = 0; c < 3; ++c) Hf[r][c] = float(Hd[r][c]);
     }
+    kabsch_from_H(Hf, R);
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int d = 0; d < 3; ++d) T[d] = ct[d] - (R[d * 3] * cq[0] + R[d * 3 + 1] * cq[1] + R[d * 3 + 2] * cq[2]);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) Hf[r][c] = float(Hd[r][c]);
-  }
-  float R[9], T[3];
-  kabsch_from_H(Hf, R);
+    for (int i = 0; i < 9; ++i) rt_finite = rt_finite && isfinite(R[i]);
 #pragma unroll
-  for (int d = 0; d < 3; ++d) T[d] = ct[d] - (R[d * 3] * cq[0] + R[d * 3 + 1] * cq[1] + R[d * 3 + 2] * cq[2]);
-
-  // ---- inlier count over the common physical neighbourhood ----
-  const uint32_t *P = physical + cl.matrix_offset;
-  const uint32_t *V = valid + cl.valid_offset;
-  // finite[i] = all six coordinates of correspondence i are finite.  With threshold^2 == +inf the reference's test
-  // `distSq < inf` only fails for NaN/inf distances, i.e. for non-finite points or a non-finite (R, T).
-  const uint32_t *F = finite ? finite + cl.valid_offset : nullptr;
-  bool rt_finite = true;
-#pragma unroll
-  for (int i = 0; i < 9; ++i) rt_finite = rt_finite && isfinite(R[i]);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) rt_finite = rt_finite && isfinite(T[i]);
-  const uint32_t *r0 = P + size_t(s[0]) * cl.W, *r1 = P + size_t(s[1]) * cl.W, *r2 = P + size_t(s[2]) * cl.W;
-  int cnt = 0;
-  for (int w = lane; w < cl.W; w += 32) {
-    uint32_t m = __ldg(r0 + w) & __ldg(r1 + w) & __ldg(r2 + w) & __ldg(V + w);
-    if (exact_inf) {
-      if (F) m &= __ldg(F + w);
-      cnt += __popc(m);
-    } else {
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const int idx = w * 32 + b;
-        cnt += within(R, T, q + size_t(idx) * 3, t + size_t(idx) * 3, thr2) ? 1 : 0;
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) {
-    int add = 0;
+    for (int i = 0; i < 3; ++i) rt_finite = rt_finite && isfinite(T[i]);
+    // finite[i] = all six coordinates of correspondence i are finite.  With threshold^2 == +inf the reference's test
+    // `distSq < inf` only fails for NaN/inf distances, i.e. for non-finite points or a non-finite (R, T).
+    const uint32_t *F = finite ? finite + cl.valid_offset : nullptr;
     if (exact_inf) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) add += F ? int((__ldg(F + (s[i] >> 5)) >> (s[i] & 31)) & 1u) : 1;
-      if (!rt_finite) { cnt = 0; add = 0; }
     } else {
 #pragma unroll
       for (int i = 0; i < 3; ++i) add += within(R, T, q + size_t(s[i]) * 3, t + size_t(s[i]) * 3, thr2) ? 1 : 0;
     }
-    counts[h] = cnt + add;
     if (Rout) {
 #pragma unroll
       for (int i = 0; i < 9; ++i) Rout[size_t(h) * 9 + i] = R[i];
@@ -244,6 +228,58 @@ k3_score_kernel(const K3Cluster *__restrict__ clusters, const float *__restrict_
 #pragma unroll
       for (int i = 0; i < 3; ++i) Tout[size_t(h) * 3 + i] = T[i];
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) T[i] = 0.f;
+  }
+
+  // ---- phase 2: inlier count over the common physical neighbourhood, hypothesis by hypothesis ----
+  int my_cnt = 0;
+  const int n_here = min(32, n_hyp - h0);
+  for (int j = 0; j < n_here; ++j) {
+    const uint32_t s0 = __shfl_sync(0xffffffffu, hy.x, j), s1 = __shfl_sync(0xffffffffu, hy.y, j),
+                   s2 = __shfl_sync(0xffffffffu, hy.z, j), ci = __shfl_sync(0xffffffffu, hy.w, j);
+    const K3Cluster cj = clusters[ci];
+    const uint32_t *P = physical + cj.matrix_offset;
+    const uint32_t *V = valid + cj.valid_offset;
+    const uint32_t *F = finite ? finite + cj.valid_offset : nullptr;
+    const uint32_t *r0 = P + size_t(s0) * cj.W, *r1 = P + size_t(s1) * cj.W, *r2 = P + size_t(s2) * cj.W;
+    int cnt = 0;
+    if (exact_inf) {
+      for (int w = lane; w < cj.W; w += 32) {
+        uint32_t m = __ldg(r0 + w) & __ldg(r1 + w) & __ldg(r2 + w) & __ldg(V + w);
+        if (F) m &= __ldg(F + w);
+        cnt += __popc(m);
+      }
+    } else {
+      float Rj[9], Tj[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rj[i] = __shfl_sync(0xffffffffu, R[i], j);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Tj[i] = __shfl_sync(0xffffffffu, T[i], j);
+      const float *q = query + cj.point_offset * 3;
+      const float *t = train + cj.point_offset * 3;
+      for (int w = lane; w < cj.W; w += 32) {
+        uint32_t m = __ldg(r0 + w) & __ldg(r1 + w) & __ldg(r2 + w) & __ldg(V + w);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int idx = w * 32 + b;
+          cnt += within(Rj, Tj, q + size_t(idx) * 3, t + size_t(idx) * 3, thr2) ? 1 : 0;
+        }
+      }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == j) my_cnt = cnt;
+  }
+  if (mine) {
+    if (exact_inf && !rt_finite) {
+      my_cnt = 0;
+      add = 0;
+    }
+    counts[h] = my_cnt + add;
   }
 }
 
@@ -256,8 +292,8 @@ cudaError_t launch_score_hypotheses_batched(const void *d_clusters, const float 
   if (n_hyp <= 0) return cudaSuccess;
   const bool inf = !(threshold < 1e150);  // DBL_MAX * DBL_MAX == +inf in the reference
   const double thr2 = inf ? __builtin_inf() : threshold * threshold;
-  const int warps_per_cta = 8;
-  const int blocks = (n_hyp + warps_per_cta - 1) / warps_per_cta;
+  const int warps_per_cta = 8;  // a warp scores 32 hypotheses
+  const int blocks = (n_hyp + warps_per_cta * 32 - 1) / (warps_per_cta * 32);
   k3_score_kernel<<<blocks, warps_per_cta * 32, 0, stream>>>(
       static_cast<const K3Cluster *>(d_clusters), d_query, d_train, d_physical, d_valid, d_finite, n_hyp,
       reinterpret_cast<const uint4 *>(d_hyps), thr2, inf ? 1 : 0, d_counts, d_R, d_T);
