@@ -211,6 +211,18 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
                       const float *points3d, const float *spans, int32_t n_objects, tod_pose *poses,
                       int32_t max_poses, int32_t *n_poses, int32_t *inlier_keypoints, int32_t max_inlier_total);
 
+/* The same for a BATCH of frames in one call (BASELINE config C4: a 64-frame stream): frame f owns keypoints
+ * [kp_offsets[f], kp_offsets[f+1]) of the concatenated keypoints / matches / counts / points3d arrays and the f-th
+ * height x width x 3 cloud of `clouds`.  All (frame, object) clusters go through K2 in one launch and through every
+ * K3 round together, and their host work is spread over the handle's threads.  Results equal n_frames separate
+ * tod_guess_process calls (the sampler stream depends on (seed, object, round) only): poses in (frame, object, round)
+ * order, pose_frames[i] (may be NULL) = frame of pose i, inlier keypoint indices relative to the pose's frame. */
+int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_offsets, const tod_keypoint *keypoints,
+                            const float *clouds, int32_t height, int32_t width, const tod_match *matches,
+                            const int32_t *counts, int32_t k, const float *points3d, const float *spans,
+                            int32_t n_objects, tod_pose *poses, int32_t *pose_frames, int32_t max_poses,
+                            int32_t *n_poses, int32_t *inlier_keypoints, int32_t max_inlier_total);
+
 /* Sampler stream used by tod_guess_process (public so a test harness can drive the reference's rand() with the
  * same numbers): state = tod_rng_seed(seed, object_index, round); tod_rng_next(&state) in [0, 2^31). */
 uint64_t tod_rng_seed(uint64_t seed, uint32_t object_index, uint32_t round);

@@ -116,3 +116,36 @@ def test_edge_cases():
     gg2 = GuessGenerator(min_inliers=1000, n_ransac_iterations=100, seed=1)
     got = gg2.process(gi["keypoints_xy"], gi["cloud"], gi["matches"], gi["counts"], gi["points3d"], gi["spans"])
     assert len(got["pose_results"]) == 0
+
+
+def test_batched_frames_equal_single_frame_calls():
+    """tod_guess_process_batch (BASELINE config C4 shape, scaled down): all (frame, object) clusters share the K2 launch
+    and every K3 round, yet the result must equal frame-by-frame calls exactly."""
+    descs, points = synth.make_db(6, 500, seed=90)
+    frames = [synth.make_frame(descs, points, vis, 350, seed=91 + i, duplicate_outliers=0.2)
+              for i, vis in enumerate([(0, 3), (1,), (2, 4, 5), (), (0, 1, 2)])]
+    m = DescriptorMatcher(k=5, radius=35)
+    for i, (d, p) in enumerate(zip(descs, points)):
+        m.add_object("o%d" % i, d, p)
+    m.train()
+    out = m.process(np.concatenate([f["descriptors"] for f in frames]))
+    spans = m.spans_by_index
+    m.close()
+    gg = GuessGenerator(min_inliers=8, n_ransac_iterations=400, sensor_error=0.01, seed=21)
+    batch = gg.process_batch([f["keypoints_xy"] for f in frames], np.stack([f["cloud"] for f in frames]),
+                             out["matches"], out["counts"], out["matches_3d"], spans)
+    assert len(batch) == len(frames)
+    o = 0
+    total = 0
+    for f, got in zip(frames, batch):
+        n = f["keypoints_xy"].shape[0]
+        mt = out["matches"][o:o + n].copy()
+        mt["queryIdx"] = np.where(mt["queryIdx"] >= 0, mt["queryIdx"] - o, mt["queryIdx"])
+        one = gg.process(f["keypoints_xy"], f["cloud"], mt, out["counts"][o:o + n], out["matches_3d"][o:o + n], spans)
+        assert len(one["pose_results"]) == len(got["pose_results"])
+        assert (one["pose_results"] == got["pose_results"]).all()
+        for a, b in zip(one["inliers"], got["inliers"]):
+            assert list(a) == list(b)
+        total += len(got["pose_results"])
+        o += n
+    assert total >= 6 and len(batch[3]["pose_results"]) == 0     # the empty frame yields nothing

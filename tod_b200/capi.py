@@ -77,6 +77,8 @@ SIGNATURES = [
     ("tod_guess_destroy", None, [_P]),
     ("tod_guess_process", ctypes.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _P, _I32, _P, _I32,
                                          ctypes.POINTER(_I32), _P, _I32]),
+    ("tod_guess_process_batch", ctypes.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _P, _P, _I32, _P, _P, _I32, _P, _P, _I32,
+                                               ctypes.POINTER(_I32), _P, _I32]),
     ("tod_rng_seed", _U64, [_U64, _U32, _U32]),
     ("tod_rng_next", _I32, [ctypes.POINTER(_U64)]),
     ("tod_guess_last_profile", None, [_P, ctypes.POINTER(_D)]),

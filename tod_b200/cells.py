@@ -227,6 +227,56 @@ class GuessGenerator:
         return {"pose_results": poses, "Rs": poses["R"].reshape(-1, 3, 3).copy(), "Ts": poses["T"].copy(),
                 "inliers": inliers}
 
+    def process_batch(self, keypoints_list, clouds, matches, counts, matches_3d, spans_by_index, max_poses=None):
+        """A batch of frames in one call (tod_guess_process_batch).  keypoints_list: per frame (n_f, 2) pixel coords or
+        KEYPOINT_DTYPE arrays; clouds: F x H x W x 3 f32; matches / counts / matches_3d: concatenated over the frames'
+        keypoints (the matcher's output for the concatenated descriptors).  Returns a list of per-frame dicts like
+        process()."""
+        kps = []
+        for kpf in keypoints_list:
+            if kpf.dtype != capi.KEYPOINT_DTYPE:
+                xy = np.asarray(kpf, np.float32).reshape(-1, 2)
+                kk = np.zeros(xy.shape[0], capi.KEYPOINT_DTYPE)
+                kk["x"], kk["y"] = xy[:, 0], xy[:, 1]
+                kps.append(kk)
+            else:
+                kps.append(np.ascontiguousarray(kpf))
+        off = np.concatenate([[0], np.cumsum([a.shape[0] for a in kps])]).astype(np.int32)
+        kp = np.ascontiguousarray(np.concatenate(kps)) if kps else np.zeros(0, capi.KEYPOINT_DTYPE)
+        clouds = np.ascontiguousarray(clouds, np.float32)
+        F, H, W = clouds.shape[0], clouds.shape[1], clouds.shape[2]
+        assert F == len(kps)
+        m = np.ascontiguousarray(matches)
+        assert m.dtype == capi.MATCH_DTYPE and m.shape[0] == kp.shape[0]
+        k = m.shape[1]
+        c = np.ascontiguousarray(counts, np.int32)
+        p3 = np.ascontiguousarray(matches_3d, np.float32)
+        sp = np.ascontiguousarray(spans_by_index, np.float32)
+        if max_poses is None:
+            max_poses = 64 * F
+        poses = np.zeros(max_poses, capi.POSE_DTYPE)
+        frames = np.zeros(max_poses, np.int32)
+        n_poses = ctypes.c_int32(0)
+        cap = max(1, kp.shape[0] * 2)
+        inl = np.zeros(cap, np.int32)
+        capi.check(self._lib.tod_guess_process_batch(self._h, F, capi._ptr(off), capi._ptr(kp), capi._ptr(clouds), H, W,
+                                                     capi._ptr(m), capi._ptr(c), k, capi._ptr(p3), capi._ptr(sp),
+                                                     sp.shape[0], capi._ptr(poses), capi._ptr(frames), max_poses,
+                                                     ctypes.byref(n_poses), capi._ptr(inl), cap))
+        poses, frames = poses[:n_poses.value], frames[:n_poses.value]
+        out = [{"pose_results": [], "inliers": []} for _ in range(F)]
+        o = 0
+        for p, f in zip(poses, frames):
+            out[int(f)]["pose_results"].append(p)
+            out[int(f)]["inliers"].append(inl[o:o + int(p["n_inliers"])].copy())
+            o += int(p["n_inliers"])
+        for d in out:
+            pr = np.array(d["pose_results"], capi.POSE_DTYPE) if d["pose_results"] else np.zeros(0, capi.POSE_DTYPE)
+            d["pose_results"] = pr
+            d["Rs"] = pr["R"].reshape(-1, 3, 3).copy()
+            d["Ts"] = pr["T"].copy()
+        return out
+
     def last_stats(self):
         k2, k3 = ctypes.c_float(), ctypes.c_float()
         nh, nr = ctypes.c_int64(), ctypes.c_int32()

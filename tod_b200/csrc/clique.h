@@ -69,57 +69,79 @@ class CliqueFinder {
   }
 
  private:
-  // descending by (degree inside `r`, vertex id): std::sort of (degree, vertex) pairs read backwards
-  void sort_by_degree(std::vector<int> &r) const {
+  // descending by (degree inside `r`, vertex id): std::sort of (degree, vertex) pairs read backwards.
+  // degree inside r = popcount(row & mask of r) — the same numbers the reference gets from pairwise tests.
+  void sort_by_degree(std::vector<int> &r) {
     const size_t m = r.size();
-    std::vector<std::pair<unsigned, int> > d(m);
+    set_mask_.assign(size_t(words_), 0u);
+    for (int v : r) set_mask_[size_t(v) >> 5] |= 1u << (v & 31);
+    pairs_.resize(m);
     for (size_t i = 0; i < m; ++i) {
-      d[i] = std::make_pair(0u, r[i]);
-      for (size_t j = 0; j < i; ++j)
-        if (connected(r[i], r[j])) {
-          ++d[i].first;
-          ++d[j].first;
-        }
+      const uint32_t *row = bits_.data() + size_t(r[i]) * words_;
+      unsigned d = 0;
+      for (int w = 0; w < words_; ++w) d += unsigned(__builtin_popcount(row[w] & set_mask_[size_t(w)]));
+      pairs_[i] = std::make_pair(d, r[i]);
     }
-    std::sort(d.begin(), d.end());
-    for (size_t i = 0; i < m; ++i) r[i] = d[m - 1 - i].second;
+    std::sort(pairs_.begin(), pairs_.end());
+    for (size_t i = 0; i < m; ++i) r[i] = pairs_[m - 1 - i].second;
   }
 
-  // greedy sequential colouring; vertices whose colour cannot extend the incumbent go first with colour 0
+  // greedy sequential colouring; vertices whose colour cannot extend the incumbent go first with colour 0.
+  // "first class without a neighbour of p" is found from p's side: walk p's already-coloured neighbours (row AND
+  // placed mask) and stamp their classes — O(degree) instead of O(classes x class size), same class as the
+  // reference's sequential scan picks.
   void colour_sort(std::vector<int> &r) {
     const int gap = int(best_.size()) - int(current_.size()) + 1;
     const unsigned min_k = unsigned(std::max(1, gap));
-    std::vector<std::vector<int> > classes(2);
-    size_t keep = 0;
     size_t n_classes = 2;
-    const std::vector<int> snapshot(r);
-    for (int p : snapshot) {
+    if (classes_.size() < 2) classes_.resize(2);
+    classes_[0].clear();
+    classes_[1].clear();
+    set_mask_.assign(size_t(words_), 0u);            // vertices already pushed into a class
+    if (class_of_.size() < size_t(n_)) class_of_.resize(size_t(n_));
+    if (used_.size() < r.size() + 3) used_.resize(r.size() + 3, 0u);
+    size_t keep = 0;
+    snapshot_.assign(r.begin(), r.end());
+    for (int p : snapshot_) {
+      const uint32_t *row = bits_.data() + size_t(p) * words_;
+      if (++stamp_ == 0u) {  // wrapped: start over with clean stamps
+        std::fill(used_.begin(), used_.end(), 0u);
+        stamp_ = 1u;
+      }
+      for (int w = 0; w < words_; ++w) {
+        uint32_t m = row[w] & set_mask_[size_t(w)];
+        while (m) {
+          const int v = w * 32 + __builtin_ctz(m);
+          m &= m - 1;
+          used_[size_t(class_of_[size_t(v)])] = stamp_;
+        }
+      }
       size_t k = 1;
-      while (touches(p, classes[k])) {
+      while (used_[k] == stamp_) {
         ++k;
         if (k >= n_classes) {
           ++n_classes;
-          classes.resize(n_classes);
+          if (classes_.size() < n_classes) classes_.resize(n_classes);
+          classes_[n_classes - 1].clear();
           break;
         }
       }
-      if (k < min_k) r[keep++] = p;
-      else classes[k].push_back(p);
+      if (k < min_k) {
+        r[keep++] = p;
+      } else {
+        classes_[k].push_back(p);
+        class_of_[size_t(p)] = int(k);
+        set_mask_[size_t(p) >> 5] |= 1u << (p & 31);
+      }
     }
     if (keep > 0) colour_[keep - 1] = 0;
     size_t pos = keep;
     for (size_t k = min_k; k < n_classes; ++k)
-      for (int v : classes[k]) {
+      for (int v : classes_[k]) {
         r[pos] = v;
         colour_[pos] = unsigned(k);
         ++pos;
       }
-  }
-
-  bool touches(int p, const std::vector<int> &cls) const {
-    for (int v : cls)
-      if (connected(p, v)) return true;
-    return false;
   }
 
   unsigned colour_back() const {
@@ -169,6 +191,12 @@ class CliqueFinder {
 
   int n_;
   int words_;
+  std::vector<uint32_t> set_mask_, used_;
+  std::vector<int> class_of_;
+  uint32_t stamp_ = 0u;
+  std::vector<std::pair<unsigned, int> > pairs_;
+  std::vector<std::vector<int> > classes_;
+  std::vector<int> snapshot_;
   std::vector<uint32_t> bits_;
   std::vector<unsigned> degree_;
   std::vector<unsigned> colour_;

@@ -32,6 +32,10 @@
 #include <thread>
 #include <vector>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include "clique.h"
 #include "host_geometry.h"
 #include "tod_internal.h"
@@ -44,6 +48,7 @@ namespace {
 inline int popc32(uint32_t x) { return __builtin_popcount(x); }
 
 struct Cluster {
+  int frame = 0;
   int object = 0;
   int n = 0, W = 0;
   std::vector<float> q, t, px;     // n x 3, n x 3, n x 2
@@ -306,6 +311,44 @@ void hypothesis_inliers(const Cluster &c, const uint32_t s[3], bool inf_threshol
     if (passes(s[k])) out.push_back(s[k]);
 }
 
+// Row of the induced sub-graph: the bits of `row` at the positions set in `mask`, packed in rank order into out
+// (`words` u32, zeroed by the caller).  Portable version: walk the set bits.
+inline void compress_row_generic(const uint32_t *row, const uint32_t *mask, const int *rank, int W, uint32_t *out) {
+  for (int w = 0; w < W; ++w) {
+    uint32_t m = row[w] & mask[w];
+    while (m) {
+      const int bit = __builtin_ctz(m);
+      m &= m - 1;
+      const int b = rank[w] + popc32(mask[w] & ((1u << bit) - 1u));
+      out[b >> 5] |= 1u << (b & 31);
+    }
+  }
+}
+
+#if defined(__x86_64__)
+// BMI2 version: one PEXT per word, appended to the output bit stream.
+__attribute__((target("bmi2"))) inline void compress_row_bmi2(const uint32_t *row, const uint32_t *mask,
+                                                              const int *rank, int W, uint32_t *out) {
+  for (int w = 0; w < W; ++w) {
+    const uint32_t mk = mask[w];
+    if (!mk) continue;
+    const uint64_t packed = _pext_u32(row[w], mk);
+    const int b = rank[w];
+    const int sh = b & 31;
+    const uint64_t v = packed << sh;
+    out[b >> 5] |= uint32_t(v);
+    if (v >> 32) out[(b >> 5) + 1] |= uint32_t(v >> 32);
+  }
+}
+inline bool have_bmi2() {
+  static const bool yes = [] {
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("bmi2") != 0;
+  }();
+  return yes;
+}
+#endif
+
 // The clique gate of selectWithinDistance (:203-268) on an inlier list of size > 7.  Returns true if the list stands.
 bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScratch &g) {
   const size_t minimal = 7;  // std::min(best_inlier_number_, 7) with best_inlier_number_ >= 8 always (:85, :203)
@@ -350,15 +393,13 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
   for (int a = 0; a < nv; ++a) {
     const uint32_t *row = c.S + size_t(g.filtered[size_t(a)]) * W;
     uint32_t *out = g.adj.data() + size_t(a) * words;
-    for (int w = 0; w < W; ++w) {
-      uint32_t m = row[w] & g.mask[size_t(w)];
-      while (m) {
-        const int bit = __builtin_ctz(m);
-        m &= m - 1;
-        const int b = g.rank[size_t(w)] + popc32(g.mask[size_t(w)] & ((1u << bit) - 1u));
-        out[b >> 5] |= 1u << (b & 31);
-      }
+#if defined(__x86_64__)
+    if (have_bmi2()) {
+      compress_row_bmi2(row, g.mask.data(), g.rank.data(), W, out);
+      continue;
     }
+#endif
+    compress_row_generic(row, g.mask.data(), g.rank.data(), W, out);
   }
   const Clock::time_point t1 = Clock::now();
   g.ms_setup += std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -449,10 +490,11 @@ void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_
   if (n_rounds) *n_rounds = g ? g->n_rounds : 0;
 }
 
-int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp, const float *cloud, int32_t height,
-                      int32_t width, const tod_match *matches, const int32_t *counts, int32_t k,
-                      const float *points3d, const float *spans, int32_t n_objects, tod_pose *poses,
-                      int32_t max_poses, int32_t *n_poses, int32_t *inlier_keypoints, int32_t max_inlier_total) {
+int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_offsets, const tod_keypoint *keypoints,
+                            const float *clouds, int32_t height, int32_t width, const tod_match *matches,
+                            const int32_t *counts, int32_t k, const float *points3d, const float *spans,
+                            int32_t n_objects, tod_pose *poses, int32_t *pose_frames, int32_t max_poses,
+                            int32_t *n_poses, int32_t *inlier_keypoints, int32_t max_inlier_total) {
   TOD_REQUIRE(g && n_poses, "null argument");
   *n_poses = 0;
   g->k2_ms = g->k3_ms = 0.f;
@@ -461,38 +503,49 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
   for (double &v : g->prof) v = 0.0;
   const Clock::time_point t_total = Clock::now();
   Clock::time_point t_phase = t_total;
-  TOD_REQUIRE(n_kp >= 0 && k >= 1 && n_objects >= 0 && max_poses >= 0, "bad sizes");
-  if (n_kp == 0) return TOD_OK;
+  TOD_REQUIRE(n_frames >= 0 && k >= 1 && n_objects >= 0 && max_poses >= 0, "bad sizes");
+  if (n_frames == 0) return TOD_OK;
+  TOD_REQUIRE(kp_offsets && kp_offsets[0] == 0, "kp_offsets must start at 0");
+  for (int f = 0; f < n_frames; ++f) TOD_REQUIRE(kp_offsets[f + 1] >= kp_offsets[f], "kp_offsets must not decrease");
+  const int32_t n_kp_total = kp_offsets[n_frames];
+  if (n_kp_total == 0) return TOD_OK;
   TOD_REQUIRE(keypoints && matches && counts && points3d && spans && (poses || max_poses == 0), "null input buffer");
   // "if (point_cloud.empty()) { TODO 2d-3d }" — no cloud, no poses (GuessGenerator.cpp:147-152)
-  if (!cloud || height <= 0 || width <= 0) return TOD_OK;
+  if (!clouds || height <= 0 || width <= 0) return TOD_OK;
   TOD_CUDA(cudaSetDevice(g->p.device));
   cudaStream_t st = g->stream;
   const float err = g->p.sensor_error;
   const bool inf_thr = !(g->p.ransac_threshold < 1e150);
   const double thr2 = inf_thr ? std::numeric_limits<double>::infinity() : g->p.ransac_threshold * g->p.ransac_threshold;
 
-  // ---- ClusterPerObject (adjacency_ransac.cpp:176-205) -------------------------------------------------------------
-  std::map<int, Cluster> by_object;
-  for (int32_t qi = 0; qi < n_kp; ++qi) {
-    const int cnt = counts[qi];
-    TOD_REQUIRE(cnt >= 0 && cnt <= k, "counts[%d] = %d outside [0, k=%d]", qi, cnt, k);
-    // point_cloud.at<Vec3f>(pt.y, pt.x): float -> int conversion truncates (quirk Q9)
-    const int y = int(keypoints[qi].y), x = int(keypoints[qi].x);
-    TOD_REQUIRE(y >= 0 && y < height && x >= 0 && x < width, "keypoint %d at (%g, %g) outside the %dx%d cloud", qi,
-                keypoints[qi].x, keypoints[qi].y, width, height);
-    const float *qp = cloud + (size_t(y) * width + x) * 3;
-    if (std::isnan(qp[0])) continue;  // x only, like cvIsNaN(query_point[0]) (:189)
-    for (int j = 0; j < cnt; ++j) {
-      const tod_match &m = matches[size_t(qi) * k + j];
-      TOD_REQUIRE(m.imgIdx >= 0 && m.imgIdx < n_objects, "match imgIdx %d outside [0, %d)", m.imgIdx, n_objects);
-      Cluster &c = by_object[m.imgIdx];
-      const float *tp = points3d + (size_t(qi) * k + j) * 3;
-      c.t.insert(c.t.end(), tp, tp + 3);
-      c.q.insert(c.q.end(), qp, qp + 3);
-      c.px.push_back(keypoints[qi].x);
-      c.px.push_back(keypoints[qi].y);
-      c.qidx.push_back(uint32_t(qi));
+  // ---- ClusterPerObject (adjacency_ransac.cpp:176-205), frame by frame: one cluster per (frame, object) ------------
+  std::map<int64_t, Cluster> by_object;  // key = frame * n_objects + object: frames, then objects, ascending
+  const size_t cloud_stride = size_t(height) * size_t(width) * 3;
+  for (int f = 0; f < n_frames; ++f) {
+    const float *cloud = clouds + size_t(f) * cloud_stride;
+    for (int32_t gi = kp_offsets[f]; gi < kp_offsets[f + 1]; ++gi) {
+      const int32_t qi = gi - kp_offsets[f];  // keypoint index inside its frame
+      const int cnt = counts[gi];
+      TOD_REQUIRE(cnt >= 0 && cnt <= k, "counts[%d] = %d outside [0, k=%d]", gi, cnt, k);
+      // point_cloud.at<Vec3f>(pt.y, pt.x): float -> int conversion truncates (quirk Q9)
+      const int y = int(keypoints[gi].y), x = int(keypoints[gi].x);
+      TOD_REQUIRE(y >= 0 && y < height && x >= 0 && x < width, "keypoint %d at (%g, %g) outside the %dx%d cloud", gi,
+                  keypoints[gi].x, keypoints[gi].y, width, height);
+      const float *qp = cloud + (size_t(y) * width + x) * 3;
+      if (std::isnan(qp[0])) continue;  // x only, like cvIsNaN(query_point[0]) (:189)
+      for (int j = 0; j < cnt; ++j) {
+        const tod_match &m = matches[size_t(gi) * k + j];
+        TOD_REQUIRE(m.imgIdx >= 0 && m.imgIdx < n_objects, "match imgIdx %d outside [0, %d)", m.imgIdx, n_objects);
+        Cluster &c = by_object[int64_t(f) * n_objects + m.imgIdx];
+        c.frame = f;
+        c.object = m.imgIdx;
+        const float *tp = points3d + (size_t(gi) * k + j) * 3;
+        c.t.insert(c.t.end(), tp, tp + 3);
+        c.q.insert(c.q.end(), qp, qp + 3);
+        c.px.push_back(keypoints[gi].x);
+        c.px.push_back(keypoints[gi].y);
+        c.qidx.push_back(uint32_t(qi));
+      }
     }
   }
   if (by_object.empty()) return TOD_OK;
@@ -505,7 +558,6 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
   int max_n = 0;
   for (auto &kv : by_object) {
     Cluster &c = kv.second;
-    c.object = kv.first;
     c.n = int(c.qidx.size());
     c.W = tod::adjacency_row_words(c.n);
     c.point_offset = offsets.back();
@@ -583,6 +635,7 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
 
   // ---- RANSAC rounds, all active objects in lock-step ------------------------------------------------------------------
   struct Found {
+    int frame;
     int object;
     unsigned round;
     tod_pose pose;
@@ -892,6 +945,7 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
         }
       }
       Found f;
+      f.frame = c->frame;
       f.object = c->object;
       f.round = c->round;
       std::memcpy(f.pose.R, Rt, sizeof(Rt));
@@ -906,7 +960,7 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
   }
 
   // emission order of the reference: objects ascending (std::map), rounds in order (GuessGenerator.cpp:170-235);
-  // `clusters` is already in ascending object order and every cluster appended its rounds in order
+  // `clusters` is already in ascending (frame, object) order and every cluster appended its rounds in order
   std::vector<Found> found;
   for (auto &v : found_by_cluster)
     for (auto &f : v) found.push_back(std::move(f));
@@ -924,6 +978,7 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
   int64_t n_inl = 0;
   for (size_t i = 0; i < found.size(); ++i) {
     poses[i] = found[i].pose;
+    if (pose_frames) pose_frames[i] = found[i].frame;
     if (inlier_keypoints) {
       if (n_inl + int64_t(found[i].kp.size()) > max_inlier_total)
         return fail(TOD_ERR_LIMIT, "inlier_keypoints capacity %d too small", max_inlier_total);
@@ -932,6 +987,16 @@ int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp,
   }
   *n_poses = int32_t(found.size());
   return TOD_OK;
+}
+
+int tod_guess_process(tod_guess *g, const tod_keypoint *keypoints, int32_t n_kp, const float *cloud, int32_t height,
+                      int32_t width, const tod_match *matches, const int32_t *counts, int32_t k,
+                      const float *points3d, const float *spans, int32_t n_objects, tod_pose *poses,
+                      int32_t max_poses, int32_t *n_poses, int32_t *inlier_keypoints, int32_t max_inlier_total) {
+  TOD_REQUIRE(n_kp >= 0, "bad sizes");
+  const int32_t off[2] = {0, n_kp};
+  return tod_guess_process_batch(g, 1, off, keypoints, cloud, height, width, matches, counts, k, points3d, spans,
+                                 n_objects, poses, nullptr, max_poses, n_poses, inlier_keypoints, max_inlier_total);
 }
 
 }  // extern "C"
