@@ -146,6 +146,27 @@ float tod_matcher_last_k1_ms(const tod_matcher *m);
 const char *tod_matcher_last_kernel(const tod_matcher *m);
 
 /* ================================================================================================================
+ * Trained-DB snapshot — what parameter_callback (DescriptorMatcher.cpp:60-129) reads from the object DB, as one flat
+ * mmap-able file (layout: tod_b200/csrc/snapshot.cpp).  Host-only entry points: no GPU needed.
+ * ============================================================================================================== */
+
+typedef struct tod_snapshot tod_snapshot;
+
+/* Write n_objects models: object_ids[o], descriptors[o] = rows[o] x 32 u8 (attachment "descriptors",
+ * training.cpp:157), points[o] = rows[o] x 3 f32 (attachment "points", training.cpp:158).  Spans are stored too. */
+int tod_snapshot_write(const char *path, int32_t n_objects, const char *const *object_ids,
+                       const uint8_t *const *descriptors, const float *const *points, const int32_t *rows);
+int tod_snapshot_open(const char *path, tod_snapshot **out);   /* mmap + validation */
+void tod_snapshot_close(tod_snapshot *s);
+int32_t tod_snapshot_num_objects(const tod_snapshot *s);
+int64_t tod_snapshot_num_descriptors(const tod_snapshot *s);
+/* Pointers into the mapping (valid until close); any output may be NULL. */
+int tod_snapshot_object(const tod_snapshot *s, int32_t index, const char **object_id, const uint8_t **descriptors,
+                        const float **points, int32_t *rows, float *span);
+/* parameter_callback from a snapshot: clear(), then add_object() for every model in file order; call train() next. */
+int tod_matcher_load_snapshot(tod_matcher *m, const char *path);
+
+/* ================================================================================================================
  * Geometry stages (adjacency_ransac.cpp, sac_model_registration_graph.h) — exposed for parity tests and reuse
  * ============================================================================================================== */
 

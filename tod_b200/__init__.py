@@ -2,7 +2,7 @@
 against the trained object DB + geometric guess generation, behind the reference's DescriptorMatcher /
 GuessGenerator cell surface.  All compute lives in libtod_b200.so (hand-written CUDA, C-ABI in include/tod_b200.h);
 this package is the Python binding.  There is no CPU fallback."""
-from . import capi  # noqa: F401
+from . import capi, dbio  # noqa: F401
 from .cells import DescriptorMatcher, GuessGenerator, fill_adjacency, score_hypotheses  # noqa: F401
 
-__all__ = ["capi", "DescriptorMatcher", "GuessGenerator", "fill_adjacency", "score_hypotheses"]
+__all__ = ["capi", "dbio", "DescriptorMatcher", "GuessGenerator", "fill_adjacency", "score_hypotheses"]

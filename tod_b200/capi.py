@@ -68,6 +68,14 @@ SIGNATURES = [
     ("tod_matcher_merge_device", ctypes.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P]),
     ("tod_matcher_last_k1_ms", _F, [_P]),
     ("tod_matcher_last_kernel", ctypes.c_char_p, [_P]),
+    ("tod_snapshot_write", ctypes.c_int, [ctypes.c_char_p, _I32, _P, _P, _P, _P]),
+    ("tod_snapshot_open", ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_P)]),
+    ("tod_snapshot_close", None, [_P]),
+    ("tod_snapshot_num_objects", _I32, [_P]),
+    ("tod_snapshot_num_descriptors", _I64, [_P]),
+    ("tod_snapshot_object", ctypes.c_int, [_P, _I32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_P),
+                                           ctypes.POINTER(_P), ctypes.POINTER(_I32), ctypes.POINTER(_F)]),
+    ("tod_matcher_load_snapshot", ctypes.c_int, [_P, ctypes.c_char_p]),
     ("tod_adjacency_row_words", _I32, [_I32]),
     ("tod_fill_adjacency", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _F, _P, _P, _P]),
     ("tod_score_hypotheses", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _I32, _P, _D, _P, _P, _P]),

@@ -62,6 +62,10 @@ class DescriptorMatcher:
     def clear(self):
         capi.check(self._lib.tod_matcher_clear(self._h))
 
+    def load_snapshot(self, path):
+        """parameter_callback from a flat DB snapshot (tod_b200.dbio.write_snapshot); call train() next."""
+        capi.check(self._lib.tod_matcher_load_snapshot(self._h, str(path).encode()))
+
     def train(self):
         capi.check(self._lib.tod_matcher_train(self._h))
 

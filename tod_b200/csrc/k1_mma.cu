@@ -713,11 +713,9 @@ cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map
                           cudaStream_t stream) {
   if (k < 1 || k > TOD_MAX_K) return cudaErrorInvalidValue;
   const uint32_t thr_init = radius ? min(radius + 1u, 511u) : 511u;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per device and per context, so not cached in a static: a process may hold handles on several GPUs
     cudaError_t e = cudaFuncSetAttribute(k1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMma);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   static const int debug_mode = [] {  // TOD_K1_DEBUG_MODE: profiling knob, never set in production
     const char *e = getenv("TOD_K1_DEBUG_MODE");
