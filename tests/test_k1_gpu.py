@@ -187,3 +187,38 @@ def test_sharded_db_merge_equals_unsharded(world, kernel):
     assert (pts.cpu().numpy() == e3).all()
     for h in handles:
         h.close()
+
+
+def test_maximum_db_size_and_limit():
+    """The packed key addresses 2^23 rows: a DB of exactly that size works (bit-exact on planted and random queries,
+    first / last rows included), one more row is refused with TOD_ERR_LIMIT."""
+    rng = np.random.default_rng(99)
+    n_obj, rows = 32, 262144                                   # 32 x 2^18 = 2^23 descriptors (268 MB packed)
+    base = rng.integers(0, 256, (rows, 32), dtype=np.uint8)
+    pts = rng.random((rows, 3)).astype(np.float32)
+    m = DescriptorMatcher(k=2, radius=0)
+    descs = []
+    for o in range(n_obj):
+        d = base.copy()
+        d[:, 0] ^= np.uint8(o)                                 # objects differ in a few bits of byte 0
+        d[:, 31] = rng.integers(0, 256, rows, dtype=np.uint8)
+        descs.append(d)
+        m.add_object("o%d" % o, d, pts)
+    assert m.num_descriptors == 1 << 23
+    with pytest.raises(capi.TodError) as e:
+        m.add_object("one_too_many", base[:1], pts[:1])
+    assert e.value.code == capi.TOD_ERR_LIMIT
+    m.train()
+    # queries: exact copies of chosen rows (first row of the DB, last row of the DB, random ones) + random clutter
+    picks = [(0, 0), (n_obj - 1, rows - 1)] + [(int(rng.integers(0, n_obj)), int(rng.integers(0, rows)))
+                                              for _ in range(30)]
+    q = np.stack([descs[o][r] for o, r in picks] + [rng.integers(0, 256, 32, dtype=np.uint8) for _ in range(32)])
+    out = m.process(q)
+    assert m.last_kernel == "mma"
+    em, ec = hk.knn_c(q, descs, 2, 0)
+    assert_matches_equal(out["matches"], out["counts"], em["trainIdx"], em["imgIdx"], em["distance"], ec)
+    for i, (o, r) in enumerate(picks):
+        assert out["matches"]["distance"][i, 0] == 0
+        # the same row of a lower-numbered object can tie at distance 0 only if byte 0 and 31 agree; the oracle decides
+        assert (int(out["matches"]["imgIdx"][i, 0]), int(out["matches"]["trainIdx"][i, 0])) <= (o, r)
+    m.close()
