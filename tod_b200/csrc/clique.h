@@ -46,6 +46,16 @@ class CliqueFinder {
 
   bool connected(int a, int b) const { return (bits_[size_t(a) * words_ + (b >> 5)] >> (b & 31)) & 1u; }
 
+  // The gate's question (sac_model_registration_graph.h:260-265): would find(minimal_size) return MORE than
+  // minimal_size vertices?  Same search, same answer, but it stops as soon as the answer is certain.
+  bool finds_more_than(unsigned minimal_size) {
+    decide_only_ = true;
+    decided_ = false;
+    const bool yes = find(minimal_size).size() > minimal_size;
+    decide_only_ = false;
+    return yes;
+  }
+
   // Returns the clique found: the first one reaching `minimal_size`, else the largest seen within the step budget.
   std::vector<int> find(unsigned minimal_size) {
     best_.clear();
@@ -166,6 +176,14 @@ class CliqueFinder {
       const unsigned c = colour_back();
       if (current_.size() + c > best_.size()) {
         current_.push_back(p);
+        // Decision-only mode: current_ is a clique of minimal_ + 1 vertices and the search is still alive (best_ <
+        // minimal_), so from here it can only descend — size + colour > best_ holds at every deeper level — to a leaf
+        // of at least this size, unless the 100000-step budget ran out first; the descent is at most |r| levels deep.
+        if (decide_only_ && current_.size() > minimal_ && steps_ + int(r.size()) + 1 <= 100000) {
+          best_ = current_;
+          decided_ = true;
+          return;
+        }
         std::vector<int> next;
         for (int v : r)
           if (connected(p, v)) next.push_back(v);
@@ -176,6 +194,7 @@ class CliqueFinder {
           ++steps_;
           if (steps_ > 100000) return;
           expand(next, level + 1);
+          if (decided_) return;
         } else if (current_.size() > best_.size()) {
           best_ = current_;
           if (best_.size() >= minimal_) return;
@@ -189,6 +208,7 @@ class CliqueFinder {
     }
   }
 
+  bool decide_only_ = false, decided_ = false;
   int n_;
   int words_;
   std::vector<uint32_t> set_mask_, used_;

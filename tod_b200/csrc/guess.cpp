@@ -412,7 +412,7 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
   }
   // the bounded clique search (:258-265)
   tod::CliqueFinder finder(nv, g.adj.data());
-  const bool ok = finder.find(unsigned(minimal)).size() > minimal;
+  const bool ok = finder.finds_more_than(unsigned(minimal));
   g.ms_search += ms_since(t2);
   return ok;
 }
