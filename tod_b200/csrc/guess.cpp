@@ -424,7 +424,7 @@ struct tod_guess {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DeviceBuffer d_off, d_mo, d_q, d_t, d_px, d_sp, d_P, d_S, d_desc, d_valid, d_finite, d_hyps, d_counts, d_R, d_T;
-  std::vector<uint32_t> h_P, h_S;
+  tod::PinnedBuffer h_P, h_S;  // host copies of the bit-matrices (read by the sampler and the gate)
   float k2_ms = 0, k3_ms = 0;
   int64_t n_hyp_total = 0;
   int32_t n_rounds = 0;
@@ -474,6 +474,8 @@ void tod_guess_destroy(tod_guess *g) {
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->stream) cudaStreamDestroy(g->stream);
+  g->h_P.release();
+  g->h_S.release();
   delete g->pool;
   delete g;
 }
@@ -620,15 +622,15 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
                                       g->d_t.as<float>(), g->d_px.as<float>(), g->d_sp.as<float>(), err,
                                       g->d_P.as<uint32_t>(), g->d_S.as<uint32_t>(), max_n, st));
   TOD_CUDA(cudaEventRecord(g->ev1, st));
-  g->h_P.resize(mat_words);
-  g->h_S.resize(mat_words);
-  TOD_CUDA(cudaMemcpyAsync(g->h_P.data(), g->d_P.ptr, mat_words * 4, cudaMemcpyDeviceToHost, st));
-  TOD_CUDA(cudaMemcpyAsync(g->h_S.data(), g->d_S.ptr, mat_words * 4, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(g->h_P.reserve(mat_words * 4));
+  TOD_CUDA(g->h_S.reserve(mat_words * 4));
+  TOD_CUDA(cudaMemcpyAsync(g->h_P.ptr, g->d_P.ptr, mat_words * 4, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaMemcpyAsync(g->h_S.ptr, g->d_S.ptr, mat_words * 4, cudaMemcpyDeviceToHost, st));
   TOD_CUDA(cudaStreamSynchronize(st));
   TOD_CUDA(cudaEventElapsedTime(&g->k2_ms, g->ev0, g->ev1));
   for (Cluster *c : clusters) {
-    c->P = g->h_P.data() + c->matrix_offset;
-    c->S = g->h_S.data() + c->matrix_offset;
+    c->P = g->h_P.as<uint32_t>() + c->matrix_offset;
+    c->S = g->h_S.as<uint32_t>() + c->matrix_offset;
   }
   // "InvalidateIndices({})" at the end of FillAdjacency is a no-op (quirk Q4): no pruning before the first round.
   g->prof[0] = ms_since(t_phase);  // ClusterPerObject + upload + K2 + bit-matrix download

@@ -57,6 +57,30 @@ struct DeviceBuffer {
   T *as() const { return static_cast<T *>(ptr); }
 };
 
+// Growable pinned host buffer (cudaHostAlloc'd, never shrinks): device -> host copies into it run at PCIe speed
+// instead of through the driver's pageable staging path.
+struct PinnedBuffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    size_t want = n + n / 4;
+    cudaError_t e = cudaHostAlloc(&ptr, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T *as() const { return static_cast<T *>(ptr); }
+};
+
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------------------------
 
 // Packed key of one candidate: distance (9 bits) << 23 | global DB row (23 bits).  min() over keys is exactly the
