@@ -8,8 +8,9 @@ A "step" = one batch of `--frames` synthetic frames (2000 query descriptors each
   value : frames/s with the queries already resident in HBM (K1 k-NN -> [NCCL all-gather of packed top-k keys when
           the DB is sharded] -> merge/radius/decode/3-D gather), timed with CUDA events, max over ranks;
   e2e   : the same metric through the reference-facing call with HOST buffers (pinned): H2D of the descriptors,
-          DescriptorMatcher.process, D2H of matches / counts / matches_3d, and GuessGenerator.process on the frame
-          (when --geometry is on), wall clock around synchronous calls.
+          DescriptorMatcher.process, D2H of matches / counts / matches_3d, wall clock around synchronous calls.
+          (The geometry half is measured by tools/bench_geometry.py and, together with the matcher on the C4 stream
+          configuration, by tools/bench_pipeline.py.)
 N > 1 shards the DB rows over the ranks (strong scaling: the 1M-descriptor DB is fixed).
 
 `--impl reference` times the reference's own CPU implementation of the path on the host cores: OpenCV's
