@@ -79,3 +79,12 @@ def test_no_gpu_means_loud_failure(lib):
     h = ctypes.c_void_p()
     assert lib.tod_matcher_create(ctypes.byref(p), ctypes.byref(h)) == capi.TOD_ERR_CUDA
     assert b"no CPU fallback" in lib.tod_last_error()
+
+
+def test_sass_shows_blackwell_native_instructions():
+    """The evidence B200_PROFILING.md asks for: tcgen05.mma -> UTCIMMA (int8), tcgen05.ld -> LDTM, TMA tensor loads ->
+    UTMALDG, 1-D bulk copies -> UBLKCP; and none of the legacy tensor paths (HMMA / IMMA via mma.sync)."""
+    sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG", "UBLKCP", "VIMNMX3", "REDUX"):
+        assert mnemonic in sass, mnemonic
+    assert " HMMA" not in sass and " IMMA" not in sass
