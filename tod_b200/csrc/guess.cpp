@@ -520,25 +520,48 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   const bool inf_thr = !(g->p.ransac_threshold < 1e150);
   const double thr2 = inf_thr ? std::numeric_limits<double>::infinity() : g->p.ransac_threshold * g->p.ransac_threshold;
 
-  // ---- ClusterPerObject (adjacency_ransac.cpp:176-205), frame by frame: one cluster per (frame, object) ------------
-  std::map<int64_t, Cluster> by_object;  // key = frame * n_objects + object: frames, then objects, ascending
+  // host threads: the per-frame and per-cluster work is independent (see HostPool); small inputs stay on the caller
+  if (!g->pool) {
+    int want = g->p.host_threads > 0 ? g->p.host_threads : int(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+    if (const char *e = getenv("TOD_HOST_THREADS")) want = std::max(1, atoi(e));
+    g->pool = new HostPool(want);
+  }
+  HostPool &pool = *g->pool;
+
+  // ---- ClusterPerObject (adjacency_ransac.cpp:176-205), frames in parallel: one cluster per (frame, object) --------
+  std::vector<std::map<int, Cluster> > per_frame(static_cast<size_t>(n_frames));  // per frame: object -> cluster
+  std::vector<std::string> frame_error(static_cast<size_t>(n_frames));
   const size_t cloud_stride = size_t(height) * size_t(width) * 3;
-  for (int f = 0; f < n_frames; ++f) {
+  pool.run(n_frames, [&](int f, int) {
     const float *cloud = clouds + size_t(f) * cloud_stride;
+    std::map<int, Cluster> &mine = per_frame[size_t(f)];
+    char buf[200];
     for (int32_t gi = kp_offsets[f]; gi < kp_offsets[f + 1]; ++gi) {
       const int32_t qi = gi - kp_offsets[f];  // keypoint index inside its frame
       const int cnt = counts[gi];
-      TOD_REQUIRE(cnt >= 0 && cnt <= k, "counts[%d] = %d outside [0, k=%d]", gi, cnt, k);
+      if (cnt < 0 || cnt > k) {
+        snprintf(buf, sizeof(buf), "counts[%d] = %d outside [0, k=%d]", gi, cnt, k);
+        frame_error[size_t(f)] = buf;
+        return;
+      }
       // point_cloud.at<Vec3f>(pt.y, pt.x): float -> int conversion truncates (quirk Q9)
       const int y = int(keypoints[gi].y), x = int(keypoints[gi].x);
-      TOD_REQUIRE(y >= 0 && y < height && x >= 0 && x < width, "keypoint %d at (%g, %g) outside the %dx%d cloud", gi,
-                  keypoints[gi].x, keypoints[gi].y, width, height);
+      if (!(y >= 0 && y < height && x >= 0 && x < width)) {
+        snprintf(buf, sizeof(buf), "keypoint %d at (%g, %g) outside the %dx%d cloud", gi, keypoints[gi].x,
+                 keypoints[gi].y, width, height);
+        frame_error[size_t(f)] = buf;
+        return;
+      }
       const float *qp = cloud + (size_t(y) * width + x) * 3;
       if (std::isnan(qp[0])) continue;  // x only, like cvIsNaN(query_point[0]) (:189)
       for (int j = 0; j < cnt; ++j) {
         const tod_match &m = matches[size_t(gi) * k + j];
-        TOD_REQUIRE(m.imgIdx >= 0 && m.imgIdx < n_objects, "match imgIdx %d outside [0, %d)", m.imgIdx, n_objects);
-        Cluster &c = by_object[int64_t(f) * n_objects + m.imgIdx];
+        if (m.imgIdx < 0 || m.imgIdx >= n_objects) {
+          snprintf(buf, sizeof(buf), "match imgIdx %d outside [0, %d)", m.imgIdx, n_objects);
+          frame_error[size_t(f)] = buf;
+          return;
+        }
+        Cluster &c = mine[m.imgIdx];
         c.frame = f;
         c.object = m.imgIdx;
         const float *tp = points3d + (size_t(gi) * k + j) * 3;
@@ -549,7 +572,12 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         c.qidx.push_back(uint32_t(qi));
       }
     }
-  }
+  });
+  for (const std::string &e : frame_error)
+    if (!e.empty()) return fail(TOD_ERR_INVALID, "%s", e.c_str());
+  std::vector<Cluster *> by_object;  // frames, then objects, ascending: the reference's std::map order per frame
+  for (auto &mp : per_frame)
+    for (auto &kv : mp) by_object.push_back(&kv.second);
   if (by_object.empty()) return TOD_OK;
 
   std::vector<Cluster *> clusters;
@@ -558,8 +586,8 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   std::vector<float> spans_c;
   int64_t vo = 0;
   int max_n = 0;
-  for (auto &kv : by_object) {
-    Cluster &c = kv.second;
+  for (Cluster *cp : by_object) {
+    Cluster &c = *cp;
     c.n = int(c.qidx.size());
     c.W = tod::adjacency_row_words(c.n);
     c.point_offset = offsets.back();
@@ -644,13 +672,6 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     std::vector<uint32_t> kp;
   };
   const int max_iter = int(g->p.n_ransac_iterations);
-  // host threads: the per-cluster work is independent (see HostPool); small frames stay on the calling thread
-  if (!g->pool) {
-    int want = g->p.host_threads > 0 ? g->p.host_threads : int(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
-    if (const char *e = getenv("TOD_HOST_THREADS")) want = std::max(1, atoi(e));
-    g->pool = new HostPool(want);
-  }
-  HostPool &pool = *g->pool;
   const int n_thr = pool.size();
   struct ThreadScratch {
     GateScratch gate;

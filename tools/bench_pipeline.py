@@ -18,8 +18,101 @@ sys.path.insert(0, ROOT)
 from tod_b200 import DescriptorMatcher, GuessGenerator, synth  # noqa: E402
 
 
+def run_distributed(n_frames):
+    """torchrun mode (one process per GPU): the DB is sharded over the ranks for K1 (NCCL all-gather of the packed keys,
+    merge on every rank), then the batch's frames are split over the ranks for the guess generator — frames are
+    independent — and the pose counts are gathered.  Throughput = frames / max-over-ranks wall time."""
+    import torch
+    import torch.distributed as dist
+    from tod_b200 import capi
+    world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n_kp, H, W, K, RADIUS, ITERS = 4096, 960, 1280, 5, 35, 2500
+    descs, points = synth.make_db(100, 10000, seed=synth.BASE_SEED + 2)
+    rng = np.random.default_rng(4)
+    vis_all = [sorted(int(x) for x in rng.choice(100, 4, replace=False)) for _ in range(n_frames)]
+    f0, f1 = rank * n_frames // world, (rank + 1) * n_frames // world      # this rank's frames for the geometry half
+    # every rank needs every frame's descriptors (queries are replicated) but only its own frames' clouds / keypoints
+    frames = [synth.make_frame(descs, points, vis_all[f], n_kp, height=H, width=W, seed=synth.BASE_SEED + 400 + f)
+              for f in range(n_frames)]
+    q_all = np.ascontiguousarray(np.concatenate([f["descriptors"] for f in frames]))
+    clouds = np.stack([frames[f]["cloud"] for f in range(f0, f1)])
+    kps = [frames[f]["keypoints_xy"] for f in range(f0, f1)]
+    planted = [frames[f]["poses"] for f in range(f0, f1)]
+    del frames
+    m = DescriptorMatcher(k=K, radius=RADIUS, device=local, shard_rank=rank, shard_count=world)
+    for i, (d, p) in enumerate(zip(descs, points)):
+        m.add_object("object_%03d" % i, d, p)
+    m.train()
+    spans = m.spans_by_index
+    gg = GuessGenerator(min_inliers=15, n_ransac_iterations=ITERS, sensor_error=0.01, seed=9, device=local,
+                        host_threads=max(1, min(16, (os.cpu_count() or 16) // world)))
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    nq = q_all.shape[0]
+    q_host = torch.from_numpy(q_all).pin_memory()
+    q_dev = torch.empty((nq, 32), dtype=torch.uint8, device=dev)
+    keys = torch.empty((nq, K), dtype=torch.int32, device=dev)
+    keys_all = torch.empty((world, nq, K), dtype=torch.int32, device=dev)
+    matches = torch.empty((nq, K, 4), dtype=torch.int32, device=dev)
+    counts = torch.empty((nq,), dtype=torch.int32, device=dev)
+    pts3d = torch.empty((nq, K, 3), dtype=torch.float32, device=dev)
+    lo, hi = f0 * n_kp, f1 * n_kp
+    m_host = torch.empty((hi - lo, K, 4), dtype=torch.int32).pin_memory()
+    c_host = torch.empty((hi - lo,), dtype=torch.int32).pin_memory()
+    p_host = torch.empty((hi - lo, K, 3), dtype=torch.float32).pin_memory()
+    times, res = [], None
+    for rep in range(4):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        q_dev.copy_(q_host, non_blocking=True)
+        m.knn_keys_device(q_dev.data_ptr(), nq, keys.data_ptr(), sptr)
+        dist.all_gather_into_tensor(keys_all.view(-1), keys.view(-1))
+        m.merge_device(keys_all.data_ptr(), world, nq, matches.data_ptr(), counts.data_ptr(), pts3d.data_ptr(), sptr)
+        m_host.copy_(matches[lo:hi], non_blocking=True)      # only this rank's frames come back to the host
+        c_host.copy_(counts[lo:hi], non_blocking=True)
+        p_host.copy_(pts3d[lo:hi], non_blocking=True)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        mm = m_host.numpy().view(capi.MATCH_DTYPE).reshape(hi - lo, K).copy()
+        mm["queryIdx"] = np.where(mm["queryIdx"] >= 0, mm["queryIdx"] - lo, mm["queryIdx"])
+        res = gg.process_batch(kps, clouds, mm, c_host.numpy(), p_host.numpy(), spans, max_poses=64 * (f1 - f0))
+        t2 = time.perf_counter()
+        t = torch.tensor([t2 - t0, t1 - t0, t2 - t1], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rep:
+            times.append(t.cpu().numpy())
+    want = got = 0
+    for pl, r in zip(planted, res):
+        for o, (R, T) in pl.items():
+            want += 1
+            got += any(int(p["object_index"]) == o and np.abs(p["R"].reshape(3, 3) - R).max() < 0.02 and
+                       np.abs(p["T"] - T).max() < 0.01 for p in r["pose_results"])
+    tot = torch.tensor([want, got, sum(len(r["pose_results"]) for r in res)], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    tm = np.median(np.array(times), axis=0)
+    d = {"config": "C4 on %d GPUs: %d frames x %d keypoints, %dx%d clouds, 1M-descriptor DB sharded by rows for K1, "
+                   "frames split over the ranks for the guess generator" % (world, n_frames, n_kp, W, H),
+         "n_gpus": world, "frames_per_s": n_frames / float(tm[0]), "matcher_ms_per_batch_max_rank": 1e3 * float(tm[1]),
+         "guess_ms_per_batch_max_rank": 1e3 * float(tm[2]), "planted_objects": int(tot[0]),
+         "planted_recovered": int(tot[1]), "poses_found": int(tot[2]), "host_cores": os.cpu_count()}
+    if rank == 0:
+        s = json.dumps(d, indent=1)
+        if len(sys.argv) > 1:
+            open(sys.argv[1], "w").write(s)
+        print(s)
+    dist.destroy_process_group()
+
+
 def main():
     n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_distributed(n_frames)
     n_kp, H, W, K, RADIUS, ITERS = 4096, 960, 1280, 5, 35, 2500
     descs, points = synth.make_db(100, 10000, seed=synth.BASE_SEED + 2)
     rng = np.random.default_rng(4)
@@ -35,11 +128,24 @@ def main():
     m.train()
     spans = m.spans_by_index
     gg = GuessGenerator(min_inliers=15, n_ransac_iterations=ITERS, sensor_error=0.01, seed=9)
+    # host buffers the way a capture pipeline would hold them: pinned (two sets, for the streaming mode below)
+    import torch
+    from tod_b200 import capi
+    nq_all = q_all.shape[0]
+    q_pin = torch.from_numpy(q_all).pin_memory()
+
+    def pinned_out():
+        mt = torch.empty((nq_all, K, 4), dtype=torch.int32).pin_memory()
+        ct = torch.empty((nq_all,), dtype=torch.int32).pin_memory()
+        pt = torch.empty((nq_all, K, 3), dtype=torch.float32).pin_memory()
+        return {"matches": mt.numpy().view(capi.MATCH_DTYPE).reshape(nq_all, K), "counts": ct.numpy(),
+                "matches_3d": pt.numpy(), "_keep": (mt, ct, pt)}
+    bufs = [pinned_out(), pinned_out()]
     t_match, t_guess = [], []
     res = out = None
     for rep in range(4):
         t0 = time.perf_counter()
-        out = m.process(q_all)
+        out = m.process(q_pin.numpy(), out=bufs[0])
         t1 = time.perf_counter()
         res = gg.process_batch([f["keypoints_xy"] for f in frames], clouds, out["matches"], out["counts"],
                                out["matches_3d"], spans, max_poses=64 * n_frames)
@@ -50,7 +156,7 @@ def main():
     st = gg.last_stats()
     # ---- streaming mode: the matcher works on batch i + 1 (GPU) while the guess generator finishes batch i (host) ----
     import threading
-    n_batches = 6
+    n_batches = 8
     t0 = time.perf_counter()
     prev = [None]
 
@@ -59,8 +165,7 @@ def main():
                                    o["matches_3d"], spans, max_poses=64 * n_frames)
     worker = None
     for b in range(n_batches):
-        o = m.process(q_all)                      # ctypes releases the GIL: runs beside the previous batch's guess
-        o = {k_: (v.copy() if isinstance(v, np.ndarray) else v) for k_, v in o.items()}
+        o = m.process(q_pin.numpy(), out=bufs[b & 1])   # ctypes releases the GIL: runs beside the previous batch's guess
         if worker is not None:
             worker.join()
         worker = threading.Thread(target=guess_job, args=(o,))
