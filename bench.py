@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=32, help="frames per step (batch)")
+    ap.add_argument("--frames", type=int, default=64, help="frames per step (batch)")
     ap.add_argument("--keypoints", type=int, default=2000)
     ap.add_argument("--objects", type=int, default=100)
     ap.add_argument("--rows", type=int, default=10000, help="descriptors per object")

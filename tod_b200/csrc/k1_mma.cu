@@ -4,8 +4,12 @@
 // (cv::BFMatcher(NORM_HAMMING) semantics, see oracle/hamming_knn.py) — same contract and same packed-key output as
 // k1_popc.cu, so the merge kernels are shared.
 //
-// Identity: with every descriptor bit b mapped to the int8 value (1 - 2b), a . b = 256 - 2 * Hamming(a, b); the int32
-// accumulation is exact, so distances are bit-identical to XOR+POPC.
+// Identity: query bits x are expanded to the int8 values 2x - 1 (+-1), database bits y to the int8 values y (0 / 1):
+//   a . b = |x & y| - |~x & y|   and   Hamming(x, y) = popcount(x) - a . b ;
+// the int32 accumulation is exact, so distances are bit-identical to XOR+POPC, and popcount(x) is a per-query
+// constant folded into the thresholds.  Why 0/1 and not +-1 on the database side: the kernel is power-capped, and
+// the multipliers burn measurably less on 0/1 operands — tools/mma_peak.cu sustains 4.59 POPS with a 0/1 B operand
+// against 3.95 POPS with +-1 x +-1 under the same 1 kW cap (profiles/int_peaks.json).
 //
 // Structure — a cluster of 2 CTAs (one per SM of a TPC) runs tcgen05.mma.cta_group::2 tiles of M = 256 queries
 // (128 per CTA) x N = 256 database rows (128 per CTA) x K = 256:
@@ -235,11 +239,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // Returns the new dot-product threshold.
 //   list + i * 4 * kBlockM (i < k), a shared::cta address : ascending packed keys
 //   n_valid : columns of the sub-group that are real db rows (the last tile of a chunk may be partial)
+//   popx    : popcount of this thread's query descriptor (distance = popx - dot)
 __device__ __noinline__ int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4,
                                              uint32_t p5, uint32_t p6, uint32_t p7, uint32_t p8, uint32_t p9,
                                              uint32_t p10, uint32_t p11, uint32_t p12, uint32_t p13, uint32_t p14,
                                              uint32_t p15, uint32_t list, int k, uint32_t thr_init, uint32_t grow,
-                                             int n_valid, int thr_dot, uint32_t *gthr) {
+                                             int n_valid, int thr_dot, uint32_t *gthr, int popx) {
   constexpr uint32_t kStride = 4u * kBlockM;  // bytes between consecutive slots of one list
   const uint32_t v[16] = {p0, p1, p2, p3, p4, p5, p6, p7, p8, p9, p10, p11, p12, p13, p14, p15};
   // Hit mask, 3 instructions per register: d = v - (thr + 1) per int16 half (VIADD.16x2, no carry between halves;
@@ -286,7 +291,7 @@ __device__ __noinline__ int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t 
     const uint32_t s2a = (b & 2) ? s4[2] : s4[0], s2b = (b & 2) ? s4[3] : s4[1];
     const uint32_t x = (b & 1) ? s2b : s2a;
     const int dot = (b & 16) ? (int(x) >> 16) : (int(x << 16) >> 16);
-    const uint32_t dist = uint32_t(256 - dot) >> 1;
+    const uint32_t dist = uint32_t(popx - dot);               // Hamming = popcount(query) - dot
     const uint32_t key = (dist << kKeyRowBits) | (grow + uint32_t(2 * (b & 15) + (b >> 4)));
     if (key < worst) {
       // sorted insert: the new key displaces the worst entry and sinks to its place
@@ -304,7 +309,7 @@ __device__ __noinline__ int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t 
   }
   if (inserted) {
     const uint32_t kth = min(thr_init, worst >> kKeyRowBits);  // strict bound of this list (511 while not full)
-    thr_dot = max(thr_dot, 256 - 2 * int(kth));
+    thr_dot = max(thr_dot, popx - int(kth));                  // distance < kth  <=>  dot > popx - kth
   }
   if (inserted && gthr) {
     const uint32_t kth = worst >> kKeyRowBits;   // 511 while the list is not full
@@ -322,7 +327,8 @@ __global__ void __launch_bounds__(kThreadsMma, 1)
 #endif
 k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, int nq,
               int shard_rows, uint32_t global_row_base, int rows_per_chunk, int n_chunks, uint32_t thr_init, int K,
-              uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, int debug_mode) {
+              uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, const uint32_t *__restrict__ popq,
+              int debug_mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *a_smem = smem;                                   // [kQT][2 k-halves][128 rows][128 B]   (own queries)
@@ -466,8 +472,9 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t my_list = ptx::smem_u32(lists + size_t(j * TOD_MAX_K) * kBlockM + row_in_tile);
     for (int i = 0; i < K; ++i) sts_u32(my_list + uint32_t(i) * 4u * kBlockM, kKeyEmpty);
-    int thr_dot = 256 - 2 * int(thr_init);                // distance < thr  <=>  dot > 256 - 2 thr
     const int qi = q_row0 + j * kBlockM + row_in_tile;
+    const int popx = qi < nq ? int(__ldg(popq + qi)) : 0;  // popcount of this thread's query: distance = popx - dot
+    int thr_dot = popx - int(thr_init);                   // distance < thr  <=>  dot > popx - thr
     uint32_t *const my_gthr = (qi < nq && !(debug_mode & 16)) ? gthr + qi : nullptr;
     uint32_t g_next = 511u;                               // shared bound, loaded one tile ahead of its use
     const uint32_t acc_empty_leader = mapa_u32(ptx::smem_u32(&acc_empty[j]), 0);
@@ -484,7 +491,7 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     auto slow32 = [&](const uint32_t (&v)[32], int o, uint32_t grow, int n_valid) {
       thr_dot = k1_mma_slow_scan(v[o + 0], v[o + 1], v[o + 2], v[o + 3], v[o + 4], v[o + 5], v[o + 6], v[o + 7],
                                  v[o + 8], v[o + 9], v[o + 10], v[o + 11], v[o + 12], v[o + 13], v[o + 14], v[o + 15],
-                                 my_list, K, thr_init, grow, n_valid, thr_dot, my_gthr);
+                                 my_list, K, thr_init, grow, n_valid, thr_dot, my_gthr, popx);
     };
 
     for (int t = 0; t < n_tiles; ++t) {
@@ -505,7 +512,7 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       tmem_ld64_pack16(taddr + 128u, vc);
       tmem_ld64_pack16(taddr + 192u, vd);
       // shared bound of this query: use the value loaded during the previous tile, start the next load now
-      thr_dot = max(thr_dot, 255 - 2 * int(g_next));
+      thr_dot = max(thr_dot, popx - int(g_next) - 1);    // distance <= g  <=>  dot > popx - g - 1
       if (my_gthr) g_next = *reinterpret_cast<volatile uint32_t *>(my_gthr);
       tmem_wait_ld();
       tc_fence_before();
@@ -580,20 +587,33 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   }
 }
 
-// bits -> +-1 int8:  out[row][8 * byte + b] = (in[row][byte] >> b) & 1 ? -1 : +1
-__global__ void __launch_bounds__(256) expand_pm1_kernel(const uint8_t *__restrict__ in, uint2 *__restrict__ out,
-                                                         size_t n_bytes) {
+// database bits -> 0/1 int8:  out[row][8 * byte + b] = (in[row][byte] >> b) & 1
+__global__ void __launch_bounds__(256) expand_db01_kernel(const uint8_t *__restrict__ in, uint2 *__restrict__ out,
+                                                          size_t n_bytes) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_bytes) return;
   const uint32_t x = in[i];
   const uint32_t lo = ((x & 0xFu) * 0x00204081u) & 0x01010101u;
   const uint32_t hi = ((x >> 4) * 0x00204081u) & 0x01010101u;
-  out[i] = make_uint2(lo * 0xFEu + 0x01010101u, hi * 0xFEu + 0x01010101u);
+  out[i] = make_uint2(lo, hi);
 }
 
-__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *__restrict__ p, uint32_t v, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+// query bits -> +-1 int8:  out[row][8 * byte + b] = (in[row][byte] >> b) & 1 ? +1 : -1.  A warp is one descriptor
+// (32 bytes): it also writes the descriptor's popcount and resets the query's shared bound to "none" (511).
+__global__ void __launch_bounds__(256) expand_query_kernel(const uint8_t *__restrict__ in, uint2 *__restrict__ out,
+                                                           size_t n_bytes, uint32_t *__restrict__ popq,
+                                                           uint32_t *__restrict__ gthr) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint32_t x = i < n_bytes ? in[i] : 0u;
+  const uint32_t pop = __reduce_add_sync(0xffffffffu, unsigned(__popc(x)));
+  if (i >= n_bytes) return;
+  const uint32_t lo = (((x & 0xFu) * 0x00204081u) & 0x01010101u) ^ 0x01010101u;   // 1 where the bit is 0
+  const uint32_t hi = (((x >> 4) * 0x00204081u) & 0x01010101u) ^ 0x01010101u;
+  out[i] = make_uint2(lo * 0xFEu + 0x01010101u, hi * 0xFEu + 0x01010101u);        // bit 0 -> 0xFF, bit 1 -> 0x01
+  if ((threadIdx.x & 31) == 0) {
+    popq[i >> 5] = pop;
+    gthr[i >> 5] = 511u;
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -648,19 +668,23 @@ K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count) {
   return p;
 }
 
-cudaError_t launch_expand_pm1(const void *d_bits, void *d_int8, int64_t rows, cudaStream_t stream) {
+cudaError_t launch_expand_db(const void *d_bits, void *d_int8, int64_t rows, cudaStream_t stream) {
   const size_t n_bytes = size_t(rows) * 32;
   if (n_bytes == 0) return cudaSuccess;
   const unsigned blocks = unsigned((n_bytes + 255) / 256);
-  expand_pm1_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint8_t *>(d_bits), static_cast<uint2 *>(d_int8),
-                                                n_bytes);
+  expand_db01_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint8_t *>(d_bits), static_cast<uint2 *>(d_int8),
+                                                 n_bytes);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_fill_u32(uint32_t *d_p, uint32_t v, int n, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
-  fill_u32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_p, v, n);
+cudaError_t launch_expand_queries(const void *d_bits, void *d_int8, int64_t rows, uint32_t *d_popq, uint32_t *d_gthr,
+                                  cudaStream_t stream) {
+  const size_t n_bytes = size_t(rows) * 32;
+  if (n_bytes == 0) return cudaSuccess;
+  const unsigned blocks = unsigned((n_bytes + 255) / 256);
+  expand_query_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint8_t *>(d_bits), static_cast<uint2 *>(d_int8),
+                                                  n_bytes, d_popq, d_gthr);
   count_launch();
   return cudaGetLastError();
 }
@@ -697,7 +721,7 @@ size_t tensor_map_bytes() { return sizeof(CUtensorMap); }
 
 cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
-                          cudaStream_t stream) {
+                          const uint32_t *d_popq, cudaStream_t stream) {
   if (k < 1 || k > TOD_MAX_K) return cudaErrorInvalidValue;
   const uint32_t thr_init = radius ? min(radius + 1u, 511u) : 511u;
   {  // per device and per context, so not cached in a static: a process may hold handles on several GPUs
@@ -712,7 +736,7 @@ cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map
   k1_mma_kernel<<<grid, kThreadsMma, kSmemMma, stream>>>(*static_cast<const CUtensorMap *>(map_q),
                                                          *static_cast<const CUtensorMap *>(map_db), nq, int(shard_rows),
                                                          global_row_base, plan.rows_per_chunk, plan.n_chunks, thr_init, k, d_partial,
-                                                         d_gthr, debug_mode);
+                                                         d_gthr, d_popq, debug_mode);
   count_launch();
   return cudaGetLastError();
 }

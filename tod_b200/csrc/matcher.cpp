@@ -29,8 +29,8 @@ struct tod_matcher {
   bool ev_valid = false;
   int64_t shard_begin = 0, shard_rows = 0;
   DeviceBuffer d_db, d_pts, d_offsets, d_query, d_partial, d_matches, d_counts, d_pts3d;
-  // tensor-core formulation: +-1 int8 copies (256 B / descriptor) and their TMA tensor maps
-  DeviceBuffer d_db8, d_q8, d_gthr;
+  // tensor-core formulation: int8 copies (db 0/1, queries +-1; 256 B / descriptor) and their TMA tensor maps
+  DeviceBuffer d_db8, d_q8, d_gthr, d_popq;
   alignas(64) unsigned char map_db[128];
   alignas(64) unsigned char map_q[128];
   bool have_db8 = false;
@@ -65,11 +65,13 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
       m->map_q_rows = nq;
     }
     TOD_CUDA(m->d_gthr.reserve(size_t(nq) * sizeof(uint32_t)));
-    TOD_CUDA(tod::launch_expand_pm1(d_query, m->d_q8.ptr, nq, st));
-    TOD_CUDA(tod::launch_fill_u32(m->d_gthr.as<uint32_t>(), 511u, nq, st));
+    TOD_CUDA(m->d_popq.reserve(size_t(nq) * sizeof(uint32_t)));
+    TOD_CUDA(tod::launch_expand_queries(d_query, m->d_q8.ptr, nq, m->d_popq.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
+                                        st));
     TOD_CUDA(cudaEventRecord(m->ev0, st));
     TOD_CUDA(tod::launch_k1_mma(plan, m->map_q, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
-                                m->p.radius, m->d_partial.as<uint32_t>(), m->d_gthr.as<uint32_t>(), st));
+                                m->p.radius, m->d_partial.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
+                                m->d_popq.as<uint32_t>(), st));
     TOD_CUDA(cudaEventRecord(m->ev1, st));
     m->ev_valid = true;
     m->last_kernel = "mma";
@@ -172,7 +174,7 @@ void tod_matcher_destroy(tod_matcher *m) {
   if (!m) return;
   cudaSetDevice(m->p.device);
   for (DeviceBuffer *b : {&m->d_db, &m->d_pts, &m->d_offsets, &m->d_query, &m->d_partial, &m->d_matches,
-                          &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8, &m->d_gthr})
+                          &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8, &m->d_gthr, &m->d_popq})
     b->release();
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -241,7 +243,7 @@ int tod_matcher_train(tod_matcher *m) {
     static_assert(sizeof(m->map_db) >= 128, "CUtensorMap is 128 bytes");
     if (tod::tensor_map_bytes() > sizeof(m->map_db)) return fail(TOD_ERR_CUDA, "unexpected CUtensorMap size");
     TOD_CUDA(m->d_db8.reserve(std::max<size_t>(size_t(m->shard_rows) * 256, 1024)));
-    TOD_CUDA(tod::launch_expand_pm1(m->d_db.ptr, m->d_db8.ptr, m->shard_rows, m->stream));
+    TOD_CUDA(tod::launch_expand_db(m->d_db.ptr, m->d_db8.ptr, m->shard_rows, m->stream));
     if (!tod::make_desc_tensor_map(m->map_db, m->d_db8.ptr, m->shard_rows, tod::k1_mma_db_box_rows()))
       return fail(TOD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the database");
     m->have_db8 = true;

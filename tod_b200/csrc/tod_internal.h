@@ -105,19 +105,22 @@ cudaError_t launch_k1_popc(const K1Plan &plan, const void *d_query, int nq, cons
                            uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial,
                            cudaStream_t stream);
 
-// K1 (tcgen05 int8 formulation, k1_mma.cu).  The database / queries are expanded to +-1 int8 (256 B per descriptor)
-// and described by TMA tensor maps (opaque CUtensorMap blobs of tensor_map_bytes() bytes, host memory).
+// K1 (tcgen05 int8 formulation, k1_mma.cu).  The database is expanded to 0/1 int8 and the queries to +-1 int8 (256 B
+// per descriptor), both described by TMA tensor maps (opaque CUtensorMap blobs of tensor_map_bytes() bytes, host
+// memory).  launch_expand_queries also writes the queries' popcounts and resets their shared bounds to 511.
 K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count);
-cudaError_t launch_expand_pm1(const void *d_bits, void *d_int8, int64_t rows, cudaStream_t stream);
+cudaError_t launch_expand_db(const void *d_bits, void *d_int8, int64_t rows, cudaStream_t stream);
+cudaError_t launch_expand_queries(const void *d_bits, void *d_int8, int64_t rows, uint32_t *d_popq, uint32_t *d_gthr,
+                                  cudaStream_t stream);
 bool make_desc_tensor_map(void *map_out, const void *d_int8, int64_t rows, int box_rows);
 int k1_mma_query_box_rows();
 int k1_mma_db_box_rows();
 size_t tensor_map_bytes();
-// d_gthr: nq u32 shared per-query bounds, must hold 511 (no bound) before the launch (launch_fill_u32).
+// d_gthr: nq u32 shared per-query bounds, must hold 511 (no bound) before the launch; d_popq: nq query popcounts
+// (both written by launch_expand_queries).
 cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
-                          cudaStream_t stream);
-cudaError_t launch_fill_u32(uint32_t *d_p, uint32_t v, int n, cudaStream_t stream);
+                          const uint32_t *d_popq, cudaStream_t stream);
 
 // Reduce n_src x nq x k key lists to nq x k keys (ascending).
 cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t *d_out,

@@ -21,8 +21,9 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
   return d;
 }
 
+// pattern: 0 = A and B random +-1 (the K1 encoding), 1 = A +-1, B random {0,1}, 2 = A and B {0,1}, 3 = all zero
 template <int N>
-__global__ void __launch_bounds__(128, 1) peak_kernel(int tiles, long long *cycles) {
+__global__ void __launch_bounds__(128, 1) peak_kernel(int tiles, long long *cycles, int pattern) {
   extern __shared__ uint8_t raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   uint8_t *a = smem;                 // 128 rows x 256 B  (2 k-halves of 128 B)
@@ -34,7 +35,12 @@ __global__ void __launch_bounds__(128, 1) peak_kernel(int tiles, long long *cycl
     uint32_t w = 0;
     for (int j = 0; j < 4; ++j) {
       x = x * 1664525u + 1013904223u;
-      w |= ((x >> 16) & 1 ? 0x01u : 0xFFu) << (8 * j);
+      const bool bit = (x >> 16) & 1;
+      const bool is_b = i >= 32768 / 4;
+      uint32_t v = bit ? 0x01u : 0xFFu;
+      if ((pattern == 1 && is_b) || pattern == 2) v = bit ? 0x01u : 0x00u;
+      if (pattern == 3) v = 0u;
+      w |= v << (8 * j);
     }
     reinterpret_cast<uint32_t *>(smem)[i] = w;
   }
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(128, 1) peak_kernel(int tiles, long long *cycl
 }
 
 template <int N>
-int run(int sms, int tiles, int reps) {
+int run(int sms, int tiles, int reps, int pattern = 0) {
   long long *d_c;
   CK(cudaMalloc(&d_c, sizeof(long long) * sms));
   const int smem = 32768 + N * 256 + 1024;
@@ -103,12 +109,12 @@ int run(int sms, int tiles, int reps) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  peak_kernel<N><<<sms, 128, smem>>>(tiles, d_c);
+  peak_kernel<N><<<sms, 128, smem>>>(tiles, d_c, pattern);
   CK(cudaDeviceSynchronize());
   float best = 1e30f, sum = 0.f;
   for (int r = 0; r < reps; ++r) {
     CK(cudaEventRecord(e0));
-    peak_kernel<N><<<sms, 128, smem>>>(tiles, d_c);
+    peak_kernel<N><<<sms, 128, smem>>>(tiles, d_c, pattern);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;
@@ -122,9 +128,9 @@ int run(int sms, int tiles, int reps) {
   for (int i = 0; i < sms; ++i) cyc += double(h[i]);
   cyc /= sms;
   const double macs = double(sms) * tiles * 128.0 * N * 256.0;
-  printf("{\"shape\": \"M128 N%d K256 tile, cta_group::1\", \"sms\": %d, \"tiles_per_cta\": %d, \"best_ms\": %.4f, \"mean_ms\": %.4f, "
+  printf("{\"pattern\": %d, \"shape\": \"M128 N%d K256 tile, cta_group::1\", \"sms\": %d, \"tiles_per_cta\": %d, \"best_ms\": %.4f, \"mean_ms\": %.4f, "
          "\"tops_best\": %.1f, \"tops_mean\": %.1f, \"gcmp_best\": %.1f, \"gcmp_mean\": %.1f, \"mac_per_clk_per_sm\": %.1f}\n",
-         N, sms, tiles, best, sum / reps, 2.0 * macs / (best * 1e-3) / 1e12, 2.0 * macs / (sum / reps * 1e-3) / 1e12,
+         pattern, N, sms, tiles, best, sum / reps, 2.0 * macs / (best * 1e-3) / 1e12, 2.0 * macs / (sum / reps * 1e-3) / 1e12,
          macs / 256.0 / (best * 1e-3) / 1e9, macs / 256.0 / (sum / reps * 1e-3) / 1e9, 128.0 * N * 256.0 * tiles / cyc);
   cudaFree(d_c);
   free(h);
@@ -139,5 +145,9 @@ int main(int argc, char **argv) {
   if (run<128>(sms, tiles, 5)) return 1;
   // a long run (seconds): the sustained figure under the power cap
   if (run<256>(sms, tiles * 20, 3)) return 1;
+  // operand-value patterns (power under the cap depends on what the multipliers see)
+  if (argc > 2)
+    for (int pattern = 1; pattern <= 3; ++pattern)
+      if (run<256>(sms, tiles * 20, 3, pattern)) return 1;
   return 0;
 }
