@@ -229,10 +229,11 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// Slow path of the epilogue: one copy, out of line, COMPACT (it runs from a cold instruction cache: the first
-// version, a 32-way unrolled scan with a divergent insert per column, cost ~2900 cycles per call, almost all of it
-// instruction fetch — profiles/r1_k1_stats.md) and fed from REGISTERS: the accumulator stage has already been handed
-// back to the tensor core when it runs.  Called warp-uniformly for one 32-column sub-group in which some lane saw a
+// Slow path of the epilogue, COMPACT and fed from REGISTERS: the accumulator stage has already been handed back to the
+// tensor core when it runs.  History (profiles/r1_k1_stats_*.jsonl): the first version, a 32-way unrolled scan with a
+// divergent insert per column that re-read TMEM, cost ~2900 cycles per call; as one out-of-line copy of this routine
+// ~1200; inlined at its 8 call sites (TOD_K1_INLINE_SLOW, default) another 7 % faster on small shards.
+// Runs warp-uniformly for one 32-column sub-group in which some lane saw a
 // candidate.  p0..p15 hold the sub-group's dot products as packed int16 pairs (register r = columns 2r, 2r + 1).
 // Builds each lane's hit mask branch-free; every lane then walks its own hit columns (usually none or one) and inserts
 // the candidates into its sorted top-k list in shared memory.
@@ -240,7 +241,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 //   list + i * 4 * kBlockM (i < k), a shared::cta address : ascending packed keys
 //   n_valid : columns of the sub-group that are real db rows (the last tile of a chunk may be partial)
 //   popx    : popcount of this thread's query descriptor (distance = popx - dot)
-__device__ __noinline__ int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4,
+#ifndef TOD_K1_INLINE_SLOW
+#define TOD_K1_INLINE_SLOW 1  // 1 (default): inlined at its 8 call sites — +7% on small shards vs one out-of-line copy
+#endif
+#if TOD_K1_INLINE_SLOW
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4,
                                              uint32_t p5, uint32_t p6, uint32_t p7, uint32_t p8, uint32_t p9,
                                              uint32_t p10, uint32_t p11, uint32_t p12, uint32_t p13, uint32_t p14,
                                              uint32_t p15, uint32_t list, int k, uint32_t thr_init, uint32_t grow,
