@@ -198,6 +198,24 @@ int tod_score_hypotheses(int32_t device, int32_t n, const float *query_pts, cons
  * tod_score_hypotheses call on this thread; < 0 if unknown. */
 float tod_last_stage_ms(void);
 
+/* Host-only pieces of the guess generator (no GPU needed), exposed so that they can be pinned against the reference's
+ * known-answer tests and compiled sources on a CPU-only machine:
+ *   tod_clique_find  the bounded MaxCliqueDyn search of the clique gate (maximum_clique.cpp:286-369 as restated in
+ *                    tod_b200/csrc/clique.h) on a graph given as an edge list (edges added in the given order, like
+ *                    Graph::AddEdgeSorted).  Returns the clique size (-1 on bad input), the vertices in out_vertices
+ *                    (capacity n_vertices, may be NULL); *finds_more (may be NULL) = the decision-only variant the
+ *                    gate actually runs: would the search return MORE than minimal_size vertices?
+ *   tod_rigid_fit    the m-point Kabsch fit of the refinement loop (estimateRigidTransformationSVD,
+ *                    sac_model_registration_graph.h:304-347): R (9, row-major) and T (3) map query -> training. */
+int32_t tod_clique_find(int32_t n_vertices, const int32_t *edges, int32_t n_edges, uint32_t minimal_size,
+                        int32_t *out_vertices, int32_t *finds_more);
+int tod_rigid_fit(const float *query_pts, const float *train_pts, const uint32_t *indices, int32_t m, float *R, float *T);
+/*   tod_sample_triples  getSamples (sac_model_registration_graph.h:141-168): n_hyp sample triples from the sample
+ *                    graph (n x tod_adjacency_row_words(n) bit-matrix) restricted to the valid mask, consuming the
+ *                    stream *rng_state (tod_rng_seed / tod_rng_next).  Returns the number of triples produced. */
+int32_t tod_sample_triples(int32_t n, const uint32_t *sample_bits, const uint32_t *valid_bits, uint64_t *rng_state,
+                           int32_t n_hyp, uint32_t *triples);
+
 /* ================================================================================================================
  * GuessGenerator  (GuessGenerator.cpp)
  * ============================================================================================================== */

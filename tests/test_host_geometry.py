@@ -1,0 +1,98 @@
+"""CPU: the host-side pieces of the product's guess generator (tod_b200/csrc/clique.h, host_geometry.h) through their
+host-only C-ABI entry points, against the reference's known-answer tests (test/test_maximum_clique.cpp:7-53) and the
+reference's own compiled sources (oracle/_ref)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import geometry as og
+from oracle import ref
+from tod_b200 import capi, synth
+from test_oracle_geometry import KAT1_EDGES
+
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libtod_ref.so not built")
+
+
+def clique_find(n, edges, minimal=0xFFFFFFFF):
+    lib = capi.load()
+    e = np.ascontiguousarray(edges, np.int32).reshape(-1, 2)
+    out = np.zeros(max(n, 1), np.int32)
+    more = ctypes.c_int32(-1)
+    k = lib.tod_clique_find(n, capi._ptr(e), e.shape[0], minimal, capi._ptr(out), ctypes.byref(more))
+    assert k >= 0
+    return [int(x) for x in out[:k]], bool(more.value)
+
+
+def test_reference_kats_on_the_product_clique_finder():
+    got, _ = clique_find(10, KAT1_EDGES)                        # test_maximum_clique.cpp:7-38
+    assert len(got) == 4
+    full = [(i, j) for i in range(10) for j in range(i + 1, 10) if (i, j) != (0, 1)]
+    got, _ = clique_find(10, full)                              # :40-53 (K10 minus one edge)
+    assert len(got) == 9
+    for clique, edges in ((clique_find(10, KAT1_EDGES)[0], KAT1_EDGES), (got, full)):
+        es = set(map(tuple, edges)) | set((b, a) for a, b in edges)
+        assert all((a, b) in es for a in clique for b in clique if a != b)      # it IS a clique
+
+
+@needs_ref
+def test_product_clique_finder_equals_compiled_reference():
+    """Gate mode (minimal size 7, sac_model_registration_graph.h:259): identical vertex lists, and the decision-only
+    variant the gate runs answers exactly `len(reference result) > 7` — sparse, dense and near-complete graphs."""
+    rng = np.random.default_rng(1)
+    for trial in range(250):
+        n = int(rng.integers(5, 60))
+        p = rng.choice([0.15, 0.4, 0.7, 0.9, 0.97])
+        edges = [(i, j) for i in range(n) for j in range(i + 1, n) if rng.random() < p]
+        exp = ref.find_clique(n, edges, 7, sorted_insert=True)
+        got, more = clique_find(n, edges, 7)
+        assert got == exp, trial
+        assert more == (len(exp) > 7), trial
+
+
+@needs_ref
+def test_product_rigid_fit_equals_reference():
+    lib = capi.load()
+    for n, seed in ((3, 1), (10, 2), (200, 3)):
+        q, t, px, _, _ = synth.make_cluster(n, 1.0, seed=seed)
+        ar = ref.RefAdjacencyRansac()
+        for i in range(n):
+            ar.add_points(t[i], q[i], i)
+        idx = np.arange(n, dtype=np.uint32)
+        eR, eT = ar.kabsch(idx)
+        R, T = np.zeros(9, np.float32), np.zeros(3, np.float32)
+        capi.check(lib.tod_rigid_fit(capi._ptr(q), capi._ptr(t), capi._ptr(idx), n, capi._ptr(R), capi._ptr(T)))
+        assert np.abs(R.reshape(3, 3) - eR).max() < 1e-5 and np.abs(T - eT).max() < 1e-5
+        oR, oT = og.kabsch(q, t, list(range(n)))
+        assert np.abs(R.reshape(3, 3) - oR).max() < 1e-5 and np.abs(T - oT).max() < 1e-5
+
+
+@needs_ref
+@pytest.mark.parametrize("n,frac,seed", [(60, 0.8, 1), (300, 0.4, 2), (700, 0.15, 3)])
+def test_product_sampler_equals_reference_sampler(n, frac, seed):
+    """The library's getSamples on bit-rows draws the same triples, in the same (s3, s2, s1) order, as the reference's
+    drawIndexSampleHelper on sorted neighbour lists when both consume the same stream (libc rand() in the reference is
+    redirected to tod_rng_* by the harness), also after part of the cluster has been invalidated."""
+    lib = capi.load()
+    q, t, px, _, _ = synth.make_cluster(n, frac, seed=seed)
+    ar = ref.RefAdjacencyRansac()
+    for i in range(n):
+        ar.add_points(t[i], q[i], i)
+    ar.fill_adjacency(px, 0.25, 0.01)
+    S = og.pack_bits(ar.dense("sample"))
+    W = capi.adjacency_row_words(n)
+    assert S.shape == (n, W)
+    for invalidate in (False, True):
+        if invalidate:
+            ar.invalidate_query_indices(np.arange(0, n, 7, dtype=np.uint32))
+        valid = np.zeros(W * 32, bool)
+        valid[ar.valid()] = True
+        V = np.packbits(valid, bitorder="little").view("<u4")
+        state0 = int(lib.tod_rng_seed(1234, 5, 1 if invalidate else 0))
+        exp = ar.get_samples(state0, 400)
+        st = ctypes.c_uint64(state0)
+        out = np.zeros((400, 3), np.uint32)
+        k = lib.tod_sample_triples(n, capi._ptr(np.ascontiguousarray(S)), capi._ptr(V), ctypes.byref(st), 400,
+                                   capi._ptr(out))
+        assert k == len(exp)
+        assert (out[:k] == exp).all()

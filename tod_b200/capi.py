@@ -80,6 +80,9 @@ SIGNATURES = [
     ("tod_fill_adjacency", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _F, _P, _P, _P]),
     ("tod_score_hypotheses", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _I32, _P, _D, _P, _P, _P]),
     ("tod_last_stage_ms", _F, []),
+    ("tod_clique_find", _I32, [_I32, _P, _I32, _U32, _P, ctypes.POINTER(_I32)]),
+    ("tod_rigid_fit", ctypes.c_int, [_P, _P, _P, _I32, _P, _P]),
+    ("tod_sample_triples", _I32, [_I32, _P, _P, ctypes.POINTER(_U64), _I32, _P]),
     ("tod_guess_default_params", None, [ctypes.POINTER(GuessParams)]),
     ("tod_guess_create", ctypes.c_int, [ctypes.POINTER(GuessParams), ctypes.POINTER(_P)]),
     ("tod_guess_destroy", None, [_P]),

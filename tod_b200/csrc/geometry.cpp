@@ -5,6 +5,8 @@
 #include <cstring>
 #include <vector>
 
+#include "clique.h"
+#include "host_geometry.h"
 #include "tod_internal.h"
 
 using tod::DeviceBuffer;
@@ -57,6 +59,37 @@ int check_device(int device) {
 extern "C" {
 
 float tod_last_stage_ms(void) { return g_last_stage_ms; }
+
+// ---- host-only pieces of the guess generator, exposed so that they can be checked without a GPU -------------------
+int32_t tod_clique_find(int32_t n_vertices, const int32_t *edges, int32_t n_edges, uint32_t minimal_size,
+                        int32_t *out_vertices, int32_t *finds_more) {
+  if (n_vertices < 0 || n_edges < 0 || (n_edges > 0 && !edges)) {
+    tod::set_error("bad graph");
+    return -1;
+  }
+  for (int32_t e = 0; e < n_edges * 2; ++e)
+    if (edges[e] < 0 || edges[e] >= n_vertices) {
+      tod::set_error("edge endpoint %d out of range", edges[e]);
+      return -1;
+    }
+  tod::CliqueFinder finder(n_vertices);
+  for (int32_t e = 0; e < n_edges; ++e) finder.add_edge(edges[2 * e], edges[2 * e + 1]);
+  const std::vector<int> best = finder.find(minimal_size);
+  if (out_vertices)
+    for (size_t i = 0; i < best.size(); ++i) out_vertices[i] = best[i];
+  if (finds_more) {
+    tod::CliqueFinder again(n_vertices);
+    for (int32_t e = 0; e < n_edges; ++e) again.add_edge(edges[2 * e], edges[2 * e + 1]);
+    *finds_more = again.finds_more_than(minimal_size) ? 1 : 0;
+  }
+  return int32_t(best.size());
+}
+
+int tod_rigid_fit(const float *query_pts, const float *train_pts, const uint32_t *indices, int32_t m, float *R, float *T) {
+  TOD_REQUIRE(query_pts && train_pts && indices && R && T && m >= 1, "bad argument");
+  tod::rigid_fit(query_pts, train_pts, indices, m, R, T);
+  return TOD_OK;
+}
 
 int32_t tod_adjacency_row_words(int32_t n) { return n <= 0 ? 0 : tod::adjacency_row_words(n); }
 

@@ -435,6 +435,28 @@ struct tod_guess {
 
 extern "C" {
 
+// Host-only: getSamples (sac_model_registration_graph.h:141-168) as this library runs it — n_hyp triples drawn from the
+// sample graph given as an n x row_words(n) bit-matrix and a valid mask, consuming the stream *rng_state.  Returns the
+// number of triples produced (the draw stops when the valid set holds no triangle).  For CPU tests against the reference.
+int32_t tod_sample_triples(int32_t n, const uint32_t *sample_bits, const uint32_t *valid_bits, uint64_t *rng_state,
+                           int32_t n_hyp, uint32_t *triples) {
+  if (n < 0 || n_hyp < 0 || !sample_bits || !valid_bits || !rng_state || (n_hyp > 0 && !triples)) {
+    tod::set_error("bad argument");
+    return -1;
+  }
+  Cluster c;
+  c.n = n;
+  c.W = tod::adjacency_row_words(n);
+  c.S = sample_bits;
+  c.valid.assign(valid_bits, valid_bits + c.W);
+  c.n_valid = mask_count(c.valid.data(), c.W);
+  SamplerScratch sc;
+  int32_t made = 0;
+  for (; made < n_hyp; ++made)
+    if (!get_samples(c, sc, *rng_state, triples + size_t(made) * 3)) break;
+  return made;
+}
+
 void tod_guess_default_params(tod_guess_params *p) {
   if (!p) return;
   std::memset(p, 0, sizeof(*p));
