@@ -66,7 +66,8 @@ def build(force=False, verbose=False):
                 if verbose and log:
                     sys.stderr.write(log)
     if todo or not os.path.exists(LIB):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-Xlinker", "--exclude-libs,ALL"]
+        link_extra = os.environ.get("TOD_B200_LINK_FLAGS", "").split() if VARIANT else []
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-Xlinker", "--exclude-libs,ALL"] + link_extra
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
