@@ -88,3 +88,18 @@ def test_sass_shows_blackwell_native_instructions():
     for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG", "UBLKCP", "VIMNMX3", "REDUX"):
         assert mnemonic in sass, mnemonic
     assert " HMMA" not in sass and " IMMA" not in sass
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under tod_b200/ (Python or C++/CUDA) may import, include or open it."""
+    pkg = os.path.join(ROOT, "tod_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        if os.path.basename(d).startswith("build"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                txt = open(os.path.join(d, f), errors="replace").read()
+                if re.search(r"^\s*(import|from)\s+oracle\b|#\s*include.*oracle|(open|CDLL|dlopen)\(.*oracle", txt, re.M):
+                    bad.append(os.path.join(d, f))  # (comments may cite oracle/ files as documentation)
+    assert not bad, bad

@@ -480,9 +480,13 @@ int tod_guess_create(const tod_guess_params *p, tod_guess **out) {
   TOD_CUDA(cudaSetDevice(p->device));
   tod_guess *g = new tod_guess();
   g->p = *p;
-  TOD_CUDA(cudaStreamCreate(&g->stream));
-  TOD_CUDA(cudaEventCreate(&g->ev0));
-  TOD_CUDA(cudaEventCreate(&g->ev1));
+  cudaError_t ce = cudaStreamCreate(&g->stream);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev1);
+  if (ce != cudaSuccess) {
+    tod_guess_destroy(g);
+    return fail(TOD_ERR_CUDA, "creating the guess generator's stream/events failed: %s", cudaGetErrorString(ce));
+  }
   *out = g;
   return TOD_OK;
 }

@@ -162,10 +162,14 @@ int tod_matcher_create(const tod_matcher_params *p, tod_matcher **out) {
   if (major != 10) return fail(TOD_ERR_CUDA, "device %d is sm_%dx; this library is built for sm_100a only", p->device, major);
   tod_matcher *m = new tod_matcher();
   m->p = *p;
-  TOD_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, p->device));
-  TOD_CUDA(cudaStreamCreate(&m->stream));
-  TOD_CUDA(cudaEventCreate(&m->ev0));
-  TOD_CUDA(cudaEventCreate(&m->ev1));
+  cudaError_t ce = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, p->device);
+  if (ce == cudaSuccess) ce = cudaStreamCreate(&m->stream);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev1);
+  if (ce != cudaSuccess) {
+    tod_matcher_destroy(m);
+    return fail(TOD_ERR_CUDA, "creating the matcher's stream/events failed: %s", cudaGetErrorString(ce));
+  }
   *out = m;
   return TOD_OK;
 }
