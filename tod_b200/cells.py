@@ -292,3 +292,29 @@ class GuessGenerator:
                             "replay_gate": prof[3], "refine_invalidate": prof[4], "total": prof[7]},
                 "gate_calls": int(prof[5]), "gate_proved_empty": int(prof[6]), "gate_core_rejects": int(prof[11]),
                 "gate_thread_ms": {"setup": prof[8], "proof": prof[9], "search": prof[10]}}
+
+
+# ---- the `.ork` pipeline parameters, as TodDetector forwards them (python/object_recognition_tod/detector.py:34-62) ----
+def ork_parameters(parameters):
+    """`parameters` = the `pipelineN.parameters` subtree of a detection `.ork` file (conf/detection.ork:21-46) as a
+    dict.  Returns (MatcherParams, guess_kwargs): the `search` subtree goes to the matcher as a JSON string, exactly
+    like TodDetector.configure does (detector.py:57-60 json-dumps it into `search_json_params`), and
+    n_ransac_iterations / min_inliers / sensor_error go to the guess generator (detector.py:37-39).  Host-only."""
+    lib = capi.load()
+    p = capi.MatcherParams()
+    lib.tod_matcher_default_params(ctypes.byref(p))
+    capi.check(lib.tod_matcher_params_from_json(json.dumps(parameters["search"]).encode(), ctypes.byref(p)))
+    guess = {}
+    for key, cast in (("n_ransac_iterations", int), ("min_inliers", int), ("sensor_error", float)):
+        if key in parameters:
+            guess[key] = cast(parameters[key])
+    return p, guess
+
+
+def detector_from_ork(parameters, device=0, seed=0):
+    """(DescriptorMatcher, GuessGenerator) configured from a detection `.ork` `parameters` subtree; add the models
+    (add_object / load_snapshot) and train() before processing frames."""
+    _, guess = ork_parameters(parameters)
+    m = DescriptorMatcher(search_json_params=json.dumps(parameters["search"]), device=device)
+    g = GuessGenerator(device=device, seed=seed, **guess)
+    return m, g
