@@ -22,29 +22,35 @@ namespace tod {
 
 class CliqueFinder {
  public:
+  // adjacency is kept as n rows of 64-bit words
   explicit CliqueFinder(int n_vertices)
-      : n_(n_vertices), words_((n_vertices + 31) / 32), bits_(size_t(n_vertices) * size_t((n_vertices + 31) / 32), 0u),
+      : n_(n_vertices), words_((n_vertices + 63) / 64), bits_(size_t(n_vertices) * size_t((n_vertices + 63) / 64), 0ull),
         degree_(size_t(n_vertices), 0u) {}
 
-  // from a dense symmetric n x ceil(n/32) bit-matrix (no self-loops)
+  // from a dense symmetric n x ceil(n/32) bit-matrix of 32-bit words (no self-loops)
   CliqueFinder(int n_vertices, const uint32_t *adjacency) : CliqueFinder(n_vertices) {
-    std::copy(adjacency, adjacency + bits_.size(), bits_.begin());
+    const int w32 = (n_ + 31) / 32;
     for (int v = 0; v < n_; ++v) {
+      const uint32_t *src = adjacency + size_t(v) * w32;
+      uint64_t *dst = bits_.data() + size_t(v) * words_;
       unsigned d = 0;
-      for (int w = 0; w < words_; ++w) d += unsigned(__builtin_popcount(bits_[size_t(v) * words_ + w]));
+      for (int w = 0; w < w32; ++w) {
+        dst[w >> 1] |= uint64_t(src[w]) << (32 * (w & 1));
+        d += unsigned(__builtin_popcount(src[w]));
+      }
       degree_[size_t(v)] = d;
     }
   }
 
   void add_edge(int a, int b) {
     if (a == b || connected(a, b)) return;
-    bits_[size_t(a) * words_ + (b >> 5)] |= 1u << (b & 31);
-    bits_[size_t(b) * words_ + (a >> 5)] |= 1u << (a & 31);
+    bits_[size_t(a) * words_ + (b >> 6)] |= 1ull << (b & 63);
+    bits_[size_t(b) * words_ + (a >> 6)] |= 1ull << (a & 63);
     ++degree_[size_t(a)];
     ++degree_[size_t(b)];
   }
 
-  bool connected(int a, int b) const { return (bits_[size_t(a) * words_ + (b >> 5)] >> (b & 31)) & 1u; }
+  bool connected(int a, int b) const { return (bits_[size_t(a) * words_ + (b >> 6)] >> (b & 63)) & 1ull; }
 
   // The gate's question (sac_model_registration_graph.h:260-265): would find(minimal_size) return MORE than
   // minimal_size vertices?  Same search, same answer, but it stops as soon as the answer is certain.
@@ -88,13 +94,13 @@ class CliqueFinder {
   // degree inside r = popcount(row & mask of r) — the same numbers the reference gets from pairwise tests.
   void sort_by_degree(std::vector<int> &r) {
     const size_t m = r.size();
-    set_mask_.assign(size_t(words_), 0u);
-    for (int v : r) set_mask_[size_t(v) >> 5] |= 1u << (v & 31);
+    set_mask_.assign(size_t(words_), 0ull);
+    for (int v : r) set_mask_[size_t(v) >> 6] |= 1ull << (v & 63);
     pairs_.resize(m);
     for (size_t i = 0; i < m; ++i) {
-      const uint32_t *row = bits_.data() + size_t(r[i]) * words_;
+      const uint64_t *row = bits_.data() + size_t(r[i]) * words_;
       unsigned d = 0;
-      for (int w = 0; w < words_; ++w) d += unsigned(__builtin_popcount(row[w] & set_mask_[size_t(w)]));
+      for (int w = 0; w < words_; ++w) d += unsigned(__builtin_popcountll(row[w] & set_mask_[size_t(w)]));
       pairs_[i] = std::make_pair(d, r[i]);
     }
     std::sort(pairs_.begin(), pairs_.end());
@@ -112,7 +118,7 @@ class CliqueFinder {
     if (classes_.size() < 2) classes_.resize(2);
     classes_[0].clear();
     classes_[1].clear();
-    set_mask_.assign(size_t(words_), 0u);            // vertices already pushed into a class
+    set_mask_.assign(size_t(words_), 0ull);          // vertices already pushed into a class
     if (class_of_.size() < size_t(n_)) class_of_.resize(size_t(n_));
     if (used_.size() < r.size() + 3) used_.resize(r.size() + 3, 0u);
     if (count_.size() < r.size() + 3) count_.resize(r.size() + 3, 0u);
@@ -120,7 +126,7 @@ class CliqueFinder {
     snapshot_.assign(r.begin(), r.end());
     size_t first_empty = 1;  // smallest k >= 1 whose class has no member yet, or n_classes when there is none
     for (int p : snapshot_) {
-      const uint32_t *row = bits_.data() + size_t(p) * words_;
+      const uint64_t *row = bits_.data() + size_t(p) * words_;
       if (++stamp_ == 0u) {  // wrapped: start over with clean stamps
         std::fill(used_.begin(), used_.end(), 0u);
         stamp_ = 1u;
@@ -129,9 +135,9 @@ class CliqueFinder {
       if (!dense_) {
         // walk p's already-coloured NEIGHBOURS and stamp their classes; first unstamped class wins
         for (int w = 0; w < words_; ++w) {
-          uint32_t m = row[w] & set_mask_[size_t(w)];
+          uint64_t m = row[w] & set_mask_[size_t(w)];
           while (m) {
-            const int v = w * 32 + __builtin_ctz(m);
+            const int v = w * 64 + __builtin_ctzll(m);
             m &= m - 1;
             used_[size_t(class_of_[size_t(v)])] = stamp_;
           }
@@ -146,9 +152,9 @@ class CliqueFinder {
         // class is free of neighbours of p exactly when all its members are non-neighbours; empty classes are free too
         touched_.clear();
         for (int w = 0; w < words_; ++w) {
-          uint32_t m = ~row[w] & set_mask_[size_t(w)];
+          uint64_t m = ~row[w] & set_mask_[size_t(w)];
           while (m) {
-            const int v = w * 32 + __builtin_ctz(m);
+            const int v = w * 64 + __builtin_ctzll(m);
             m &= m - 1;
             const size_t c = size_t(class_of_[size_t(v)]);
             if (used_[c] != stamp_) {
@@ -174,7 +180,7 @@ class CliqueFinder {
       } else {
         classes_[k].push_back(p);
         class_of_[size_t(p)] = int(k);
-        set_mask_[size_t(p) >> 5] |= 1u << (p & 31);
+        set_mask_[size_t(p) >> 6] |= 1ull << (p & 63);
       }
       while (first_empty < n_classes && !classes_[first_empty].empty()) ++first_empty;
     }
@@ -245,7 +251,8 @@ class CliqueFinder {
   bool decide_only_ = false, decided_ = false;
   int n_;
   int words_;
-  std::vector<uint32_t> set_mask_, used_, count_;
+  std::vector<uint64_t> set_mask_;
+  std::vector<uint32_t> used_, count_;
   std::vector<int> touched_;
   bool dense_ = false;  // more than half of all vertex pairs are edges: colour_sort walks non-neighbours
   std::vector<int> class_of_;
@@ -253,7 +260,7 @@ class CliqueFinder {
   std::vector<std::pair<unsigned, int> > pairs_;
   std::vector<std::vector<int> > classes_;
   std::vector<int> snapshot_;
-  std::vector<uint32_t> bits_;
+  std::vector<uint64_t> bits_;
   std::vector<unsigned> degree_;
   std::vector<unsigned> colour_;
   long colour_size_ = 0;
