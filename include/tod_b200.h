@@ -215,6 +215,12 @@ int tod_rigid_fit(const float *query_pts, const float *train_pts, const uint32_t
  *                    stream *rng_state (tod_rng_seed / tod_rng_next).  Returns the number of triples produced. */
 int32_t tod_sample_triples(int32_t n, const uint32_t *sample_bits, const uint32_t *valid_bits, uint64_t *rng_state,
                            int32_t n_hyp, uint32_t *triples);
+/*   tod_select_inliers  selectWithinDistance (sac_model_registration_graph.h:171-269) with the reference's never-set
+ *                    threshold: candidates from the physical bit-rows of the triple, then the clique gate on the
+ *                    sample graph exactly as tod_guess_process runs it.  Returns the inlier count (sorted list in
+ *                    `inliers`, capacity n + 3); 0 = the gate cleared the list; -1 on bad input. */
+int32_t tod_select_inliers(int32_t n, const uint32_t *physical_bits, const uint32_t *sample_bits,
+                           const uint32_t *valid_bits, const uint32_t *triple, uint32_t *inliers);
 
 /* ================================================================================================================
  * GuessGenerator  (GuessGenerator.cpp)

@@ -96,3 +96,36 @@ def test_product_sampler_equals_reference_sampler(n, frac, seed):
                                    capi._ptr(out))
         assert k == len(exp)
         assert (out[:k] == exp).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("n,frac,seed", [(80, 0.9, 4), (300, 0.5, 5), (600, 0.2, 6), (900, 0.1, 7)])
+def test_product_select_within_distance_equals_reference(n, frac, seed):
+    """selectWithinDistance with the never-set threshold (quirk Q3): candidate list + clique gate.  The product's host
+    code (7-core test, no-8-clique proofs, decision-only bounded search) must return exactly the reference's inlier
+    list for every sampled triple — outlier-heavy clusters make most gates fail, inlier-rich ones make them pass."""
+    lib = capi.load()
+    q, t, px, _, _ = synth.make_cluster(n, frac, seed=seed)
+    ar = ref.RefAdjacencyRansac()
+    for i in range(n):
+        ar.add_points(t[i], q[i], i)
+    ar.fill_adjacency(px, 0.25, 0.01)
+    P = np.ascontiguousarray(og.pack_bits(ar.dense("physical")))
+    S = np.ascontiguousarray(og.pack_bits(ar.dense("sample")))
+    W = capi.adjacency_row_words(n)
+    valid = np.zeros(W * 32, bool)
+    valid[ar.valid()] = True
+    V = np.packbits(valid, bitorder="little").view("<u4")
+    triples = ar.get_samples(int(lib.tod_rng_seed(99, seed, 0)), 150)
+    assert len(triples) > 20
+    out = np.zeros(n + 3, np.uint32)
+    passed = failed = 0
+    for tr in triples:
+        exp, _, _ = ar.select(tr)
+        tri = np.ascontiguousarray(tr, np.uint32)
+        k = lib.tod_select_inliers(n, capi._ptr(P), capi._ptr(S), capi._ptr(V), capi._ptr(tri), capi._ptr(out))
+        assert k >= 0
+        assert [int(x) for x in out[:k]] == exp
+        passed += k > 7
+        failed += k == 0
+    assert passed + failed > 0

@@ -83,6 +83,7 @@ SIGNATURES = [
     ("tod_clique_find", _I32, [_I32, _P, _I32, _U32, _P, ctypes.POINTER(_I32)]),
     ("tod_rigid_fit", ctypes.c_int, [_P, _P, _P, _I32, _P, _P]),
     ("tod_sample_triples", _I32, [_I32, _P, _P, ctypes.POINTER(_U64), _I32, _P]),
+    ("tod_select_inliers", _I32, [_I32, _P, _P, _P, _P, _P]),
     ("tod_guess_default_params", None, [ctypes.POINTER(GuessParams)]),
     ("tod_guess_create", ctypes.c_int, [ctypes.POINTER(GuessParams), ctypes.POINTER(_P)]),
     ("tod_guess_destroy", None, [_P]),

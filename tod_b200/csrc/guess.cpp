@@ -417,6 +417,38 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
   return ok;
 }
 
+// Per-round state of a cluster that the clique gate reads: sample-degrees inside the round's valid set (:209-213) and
+// the 7-core of the valid sample graph (peel vertices with fewer than 7 live neighbours until a fixed point).
+void prepare_round(Cluster &c) {
+  c.sdeg.assign(size_t(c.n), 0);
+  for (int v = 0; v < c.n; ++v) {
+    const uint32_t *row = c.S + size_t(v) * c.W;
+    int d = 0;
+    for (int w = 0; w < c.W; ++w) d += popc32(row[w] & c.valid[size_t(w)]);
+    c.sdeg[size_t(v)] = uint16_t(std::min(d, 65535));
+  }
+  c.core7 = c.valid;
+  std::vector<uint32_t> &core = c.core7;
+  bool changed = true;
+  while (changed) {
+    changed = false;
+    for (int w0 = 0; w0 < c.W; ++w0) {
+      uint32_t m = core[size_t(w0)];
+      while (m) {
+        const int v = w0 * 32 + __builtin_ctz(m);
+        m &= m - 1;
+        const uint32_t *row = c.S + size_t(v) * c.W;
+        int d = 0;
+        for (int w = 0; w < c.W; ++w) d += popc32(row[w] & core[size_t(w)]);
+        if (d < 7) {
+          core[size_t(v) >> 5] &= ~(1u << (v & 31));
+          changed = true;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 struct tod_guess {
@@ -455,6 +487,37 @@ int32_t tod_sample_triples(int32_t n, const uint32_t *sample_bits, const uint32_
   for (; made < n_hyp; ++made)
     if (!get_samples(c, sc, *rng_state, triples + size_t(made) * 3)) break;
   return made;
+}
+
+// Host-only: selectWithinDistance (sac_model_registration_graph.h:171-269) with the reference's never-set threshold, as
+// this library evaluates it — candidate list from the physical bit-rows, then the clique gate on the sample graph
+// (degree filter, 7-core test, no-8-clique proofs, bounded search).  Returns the number of inliers written to
+// `inliers` (capacity n + 3): the sorted list when the gate passes or at most 7 candidates exist, 0 when it fails.
+int32_t tod_select_inliers(int32_t n, const uint32_t *physical_bits, const uint32_t *sample_bits,
+                           const uint32_t *valid_bits, const uint32_t *triple, uint32_t *inliers) {
+  if (n < 3 || !physical_bits || !sample_bits || !valid_bits || !triple || !inliers || triple[0] >= uint32_t(n) ||
+      triple[1] >= uint32_t(n) || triple[2] >= uint32_t(n)) {
+    tod::set_error("bad argument");
+    return -1;
+  }
+  Cluster c;
+  c.n = n;
+  c.W = tod::adjacency_row_words(n);
+  c.P = physical_bits;
+  c.S = sample_bits;
+  c.valid.assign(valid_bits, valid_bits + c.W);
+  c.n_valid = mask_count(c.valid.data(), c.W);
+  c.finite.assign(size_t(c.W), 0xFFFFFFFFu);
+  prepare_round(c);
+  std::vector<uint32_t> list;
+  hypothesis_inliers(c, triple, true, std::numeric_limits<double>::infinity(), nullptr, nullptr, list);
+  GateScratch gs;
+  if (list.size() > 7) {  // :204-205 returns shorter lists as they are (candidates ascending, then the samples)
+    if (!clique_gate(c, list, gs)) list.clear();
+    std::sort(list.begin(), list.end());  // :267
+  }
+  for (size_t i = 0; i < list.size(); ++i) inliers[i] = list[i];
+  return int32_t(list.size());
 }
 
 void tod_guess_default_params(tod_guess_params *p) {
@@ -734,37 +797,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     if (active_idx.empty()) break;
     ++g->n_rounds;
     t_phase = Clock::now();
-    pool.run(int(active_idx.size()), [&](int ai, int) {  // sample-degrees inside this round's valid set
-      Cluster *c = clusters[size_t(active_idx[size_t(ai)])];
-      c->sdeg.assign(size_t(c->n), 0);
-      for (int v = 0; v < c->n; ++v) {
-        const uint32_t *row = c->S + size_t(v) * c->W;
-        int d = 0;
-        for (int w = 0; w < c->W; ++w) d += popc32(row[w] & c->valid[size_t(w)]);
-        c->sdeg[size_t(v)] = uint16_t(std::min(d, 65535));
-      }
-      // 7-core of the valid sample graph (peel vertices with fewer than 7 live neighbours until a fixed point)
-      c->core7 = c->valid;
-      std::vector<uint32_t> &core = c->core7;
-      bool changed = true;
-      while (changed) {
-        changed = false;
-        for (int w0 = 0; w0 < c->W; ++w0) {
-          uint32_t m = core[size_t(w0)];
-          while (m) {
-            const int v = w0 * 32 + __builtin_ctz(m);
-            m &= m - 1;
-            const uint32_t *row = c->S + size_t(v) * c->W;
-            int d = 0;
-            for (int w = 0; w < c->W; ++w) d += popc32(row[w] & core[size_t(w)]);
-            if (d < 7) {
-              core[size_t(v) >> 5] &= ~(1u << (v & 31));
-              changed = true;
-            }
-          }
-        }
-      }
-    });
+    pool.run(int(active_idx.size()), [&](int ai, int) { prepare_round(*clusters[size_t(active_idx[size_t(ai)])]); });
     g->prof[4] += ms_since(t_phase);
     TOD_CUDA(cudaMemcpyAsync(g->d_valid.ptr, all_valid.data(), all_valid.size() * 4, cudaMemcpyHostToDevice, st));
 
