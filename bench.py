@@ -47,7 +47,13 @@ def parse_args():
     ap.add_argument("--radius", type=int, default=0)
     ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "mma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-queries", type=int, default=250)
+    ap.add_argument("--cpu-sample-queries", type=int, default=0,
+                    help="keypoints per CPU-baseline repetition (0 = all keypoints of a frame)")
+    ap.add_argument("--no-lsh", action="store_true", help="skip the FlannBasedMatcher+LSH leg of the CPU baseline")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the C4 (matcher + guess generator) leg")
+    ap.add_argument("--pipeline-frames", type=int, default=64)
+    ap.add_argument("--c5-objects", type=int, default=100, help="objects in the C5 RANSAC-stress leg (0 = skip)")
+    ap.add_argument("--no-share-bounds", action="store_true", help="N > 1: keep K1's bounds local to each GPU")
     return ap.parse_args()
 
 
@@ -145,7 +151,8 @@ def load_measured_peaks():
 
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference_knn(descs, queries, k, threads=None):
-    """The reference's matcher on the host: cv2.BFMatcher(NORM_HAMMING) if importable, else the oracle C port."""
+    """The reference's exact matcher on the host: cv2.BFMatcher(NORM_HAMMING) if importable, else the oracle C port.
+    Returns (seconds, kind, cores, what, (trainIdx, imgIdx, distance) arrays)."""
     try:
         import cv2
         if threads:
@@ -156,13 +163,51 @@ def cpu_reference_knn(descs, queries, k, threads=None):
         res = m.knnMatch(np.ascontiguousarray(queries), k)
         dt = time.perf_counter() - t0
         assert len(res) == queries.shape[0]
-        return dt, "reference", cv2.getNumThreads(), "cv2 %s BFMatcher(NORM_HAMMING).knnMatch" % cv2.__version__
+        trn = np.array([[x.trainIdx for x in r] + [-1] * (k - len(r)) for r in res], np.int32).reshape(-1, k)
+        img = np.array([[x.imgIdx for x in r] + [-1] * (k - len(r)) for r in res], np.int32).reshape(-1, k)
+        dist = np.array([[x.distance for x in r] + [0] * (k - len(r)) for r in res], np.float32).reshape(-1, k)
+        return dt, "reference", cv2.getNumThreads(), "cv2 %s BFMatcher(NORM_HAMMING).knnMatch" % cv2.__version__, \
+            (trn, img, dist)
     except ImportError:
         from oracle import hamming_knn as hk
         t0 = time.perf_counter()
-        hk.knn_c(queries, descs, k)
+        em, ec = hk.knn_c(queries, descs, k)
         dt = time.perf_counter() - t0
-        return dt, "port", os.cpu_count(), "oracle/hamming_knn.c (OpenMP)"
+        return dt, "port", os.cpu_count(), "oracle/hamming_knn.c (OpenMP)", (em["trainIdx"], em["imgIdx"],
+                                                                              em["distance"])
+
+
+def lsh_reference(descs, queries, exact, radius=35):
+    """The matcher the reference actually ships (DescriptorMatcher.cpp:175-181 with conf/detection.ork:32-39):
+    cv::FlannBasedMatcher + LshIndexParams(10 tables, key 16, multi-probe 1), knnMatch(5) + radius cut, on the host —
+    timed on one frame, with its recall of the exact within-radius matches `exact` = (trainIdx, imgIdx, distance)."""
+    try:
+        import cv2
+    except ImportError:
+        return {"unavailable": "cv2 not importable"}
+    fl = cv2.FlannBasedMatcher(dict(algorithm=6, table_number=10, key_size=16, multi_probe_level=1), dict())
+    fl.add([np.ascontiguousarray(d) for d in descs])
+    t0 = time.perf_counter()
+    fl.train()
+    t_train = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    res = fl.knnMatch(np.ascontiguousarray(queries), 5)
+    t_knn = time.perf_counter() - t0
+    got = set()
+    for qi, r in enumerate(res):
+        for x in r[:5]:
+            if x.distance > radius:          # DescriptorMatcher.cpp:212-220
+                break
+            got.add((qi, x.imgIdx, x.trainIdx))
+    trn, img, dist = exact
+    want = set((qi, int(img[qi, j]), int(trn[qi, j])) for qi in range(trn.shape[0]) for j in range(trn.shape[1])
+               if trn[qi, j] >= 0 and dist[qi, j] <= radius)
+    return {"what": "cv2 FlannBasedMatcher LSH(table_number 10, key_size 16, multi_probe_level 1), knnMatch(5) + "
+                    "radius %d (conf/detection.ork:32-39)" % radius,
+            "frames_per_s": 1.0 / t_knn, "knn_ms_per_frame": 1e3 * t_knn, "train_ms_once": 1e3 * t_train,
+            "cores": 1, "sample": "one whole frame (%d keypoints)" % queries.shape[0],
+            "recall_of_exact_within_radius": (len(got & want) / float(len(want))) if want else None,
+            "exact_within_radius": len(want), "lsh_within_radius": len(got)}
 
 
 def run_reference(args):
@@ -170,16 +215,19 @@ def run_reference(args):
     if rank != 0:
         return 0
     descs, points, queries = workload(args)
-    nsamp = min(args.cpu_sample_queries, args.keypoints)
+    nsamp = args.keypoints if args.cpu_sample_queries <= 0 else min(args.cpu_sample_queries, args.keypoints)
     times = []
     info = None
+    exact = None
     for s in range(args.warmup + args.steps):
         f = s % args.frames
         q = queries[f * args.keypoints: f * args.keypoints + nsamp]
-        dt, kind, cores, what = cpu_reference_knn(descs, q, args.k)
+        dt, kind, cores, what, ex = cpu_reference_knn(descs, q, args.k)
         info = (kind, cores, what)
         if s >= args.warmup:
             times.append(dt)
+        if f == 0:
+            exact = ex
     total = float(sum(times))
     frames = args.steps * nsamp / float(args.keypoints)
     value = frames / total
@@ -192,15 +240,189 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": info[1], "kind": info[0], "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gcmp_per_s": value * args.keypoints * args.objects * args.rows / 1e9}
+    if not args.no_lsh and nsamp == args.keypoints:
+        # second leg, reported beside the headline: the matcher the reference ships (LSH), with its recall
+        k5 = cpu_reference_knn(descs, queries[:args.keypoints], 5)[4] if args.k != 5 else exact
+        line["reference_lsh"] = lsh_reference(descs, queries[:args.keypoints], k5)
     print(json.dumps(line))
     return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def parity_sample(args, m_np, c_np, p_np, descs, points, queries):
+    """Bit-exact check of the result of the TIMED configuration (the last end-to-end step) on a fixed sample of its
+    queries — first and last query tile, plus queries spread over every frame — against cv::BFMatcher(NORM_HAMMING)
+    (DescriptorMatcher.cpp:211-220 semantics) and the matches_3d gather (:232-244)."""
+    from oracle import hamming_knn as hk
+    nqt, k = queries.shape[0], args.k
+    rng = np.random.default_rng(12345)
+    idx = set(range(0, min(128, nqt))) | set(range(max(0, nqt - 128), nqt))
+    per_frame = max(1, 320 // max(1, args.frames))
+    for f in range(args.frames):
+        lo = f * args.keypoints
+        idx |= set(int(x) for x in lo + rng.choice(args.keypoints, min(per_frame, args.keypoints), replace=False))
+    idx = np.array(sorted(idx), np.int64)
+    _, kind, _, what, (trn, img, dist) = cpu_reference_knn(descs, queries[idx], k)
+    cnt = (trn >= 0).sum(axis=1).astype(np.int32)
+    if args.radius > 0:
+        keep = np.cumprod((dist <= args.radius) & (trn >= 0), axis=1).astype(bool)
+        cnt = keep.sum(axis=1).astype(np.int32)
+    mask = np.arange(k)[None, :] < cnt[:, None]
+    got_m, got_c, got_p = m_np[idx], c_np[idx], p_np[idx]
+    bad = (got_c != cnt)
+    for f, exp in (("trainIdx", trn), ("imgIdx", img), ("distance", dist)):
+        bad |= ((got_m[f] != exp) & mask).any(axis=1)
+    bad |= ((got_m["queryIdx"] != idx[:, None]) & mask).any(axis=1)
+    em = np.zeros((idx.shape[0], k), got_m.dtype)
+    em["trainIdx"], em["imgIdx"] = np.where(mask, trn, 0), np.where(mask, img, 0)
+    e3 = hk.gather_points3d(em, cnt, points)
+    bad |= ((got_p != e3) & mask[:, :, None]).any(axis=(1, 2))
+    return {"checked": int(idx.shape[0]), "mismatches": int(bad.sum()), "against": what, "kind": kind,
+            "fields": "counts, trainIdx, imgIdx, distance, queryIdx, matches_3d",
+            "where": "result of the last timed end-to-end step (merged result when sharded): first and last 128 "
+                     "queries + %d per frame" % per_frame}
+
+
+def hbm_roofline(kernel, alg_bytes, ms, hbm_peak, hbm_src, extra=None):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    r = {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+         "peak_source": hbm_src, "kernel_ms": ms, "algorithmic_bytes": alg_bytes, "traffic": None}
+    if extra:
+        r.update(extra)
+    return r
+
+
+def pipeline_leg(args, descs, points, m, hbm_peak, hbm_src):
+    """BASELINE config C4 through the reference-facing calls with HOST buffers: a batch of 64 synthetic 1280x960
+    RGB-D frames x 4096 keypoints, DescriptorMatcher.process (k = 5, radius 35 as in conf/detection.ork) then the
+    batched GuessGenerator.process — the whole north_star path.  Returns the `e2e_pipeline` and `stages` objects."""
+    import torch
+    from tod_b200 import DescriptorMatcher, GuessGenerator, capi, synth
+    n_frames, n_kp, H, W, K, RADIUS, ITERS = args.pipeline_frames, 4096, 960, 1280, 5, 35, 2500
+    rng = np.random.default_rng(4)
+    frames = []
+    for f in range(n_frames):
+        vis = sorted(int(x) for x in rng.choice(len(descs), min(4, len(descs)), replace=False))
+        frames.append(synth.make_frame(descs, points, vis, n_kp, height=H, width=W, seed=synth.BASE_SEED + 400 + f))
+    q_all = np.ascontiguousarray(np.concatenate([f["descriptors"] for f in frames]))
+    clouds = np.stack([f["cloud"] for f in frames])
+    kps = [f["keypoints_xy"] for f in frames]
+    m5 = DescriptorMatcher(search_json_params='{"type": "LSH", "radius": %d, "ratio": 0.8, "n_tables": 10, '
+                                              '"key_size": 16, "multi_probe_level": 1}' % RADIUS)
+    assert m5.k == K
+    for i, (d, p) in enumerate(zip(descs, points)):
+        m5.add_object("object_%03d" % i, d, p)
+    m5.train()
+    nq = q_all.shape[0]
+    m5.reserve(nq)
+    spans = m5.spans_by_index
+    gg = GuessGenerator(min_inliers=15, n_ransac_iterations=ITERS, sensor_error=0.01, seed=9)
+    q_pin = torch.from_numpy(q_all).pin_memory()
+    mt = torch.empty((nq, K, 4), dtype=torch.int32).pin_memory()
+    ct = torch.empty((nq,), dtype=torch.int32).pin_memory()
+    pt = torch.empty((nq, K, 3), dtype=torch.float32).pin_memory()
+    out = {"matches": mt.numpy().view(capi.MATCH_DTYPE).reshape(nq, K), "counts": ct.numpy(), "matches_3d": pt.numpy()}
+    t_m, t_g, k1, stats, res = [], [], [], None, None
+    for rep in range(4):
+        t0 = time.perf_counter()
+        o = m5.process(q_pin.numpy(), out=out)
+        t1 = time.perf_counter()
+        res = gg.process_batch(kps, clouds, o["matches"], o["counts"], o["matches_3d"], spans, max_poses=64 * n_frames)
+        t2 = time.perf_counter()
+        if rep:
+            t_m.append(t1 - t0)
+            t_g.append(t2 - t1)
+            k1.append(m5.last_k1_ms)
+            stats = gg.last_stats()
+    want = got = 0
+    for f, r in zip(frames, res):
+        for o_, (R, T) in f["poses"].items():
+            want += 1
+            got += any(int(p["object_index"]) == o_ and np.abs(p["R"].reshape(3, 3) - R).max() < 0.02 and
+                       np.abs(p["T"] - T).max() < 0.01 for p in r["pose_results"])
+    tm, tg = float(np.median(t_m)), float(np.median(t_g))
+    k1_ms = float(np.median(k1))
+    e2e = {"value": n_frames / (tm + tg), "unit": UNIT,
+           "workload": "C4: %d frames x %d keypoints, %dx%d clouds, %d-descriptor DB, k=%d radius=%d, "
+                       "n_ransac_iterations=%d, min_inliers=15" % (n_frames, n_kp, W, H, sum(d.shape[0] for d in descs),
+                                                                   K, RADIUS, ITERS),
+           "scope": "DescriptorMatcher.process + GuessGenerator.process(batch) through the C-ABI, pinned host buffers, "
+                    "sequential (no overlap between the two cells)",
+           "matcher_ms_per_batch": 1e3 * tm, "guess_ms_per_batch": 1e3 * tg,
+           "h2d_bytes_per_step": int(nq * 32), "d2h_bytes_per_step": int(nq * K * 16 + nq * 4 + nq * K * 12),
+           "poses_found": int(sum(len(r["pose_results"]) for r in res)), "planted_objects": want,
+           "planted_recovered": got, "matches_per_frame": float(out["counts"].sum()) / n_frames}
+    stages = {"k1": {"kernel_ms": k1_ms, "gcmp_per_s": nq * float(m5.num_descriptors) / (k1_ms * 1e-3) / 1e9},
+              "k2": hbm_roofline("k2_adjacency_kernel", stats["k2_bytes"], stats["k2_ms"], hbm_peak, hbm_src,
+                                 {"clusters": stats["n_clusters"], "correspondences": stats["n_correspondences"]}),
+              "k3": hbm_roofline("k3_score_kernel", stats["k3_bytes"], stats["k3_ms"], hbm_peak, hbm_src,
+                                 {"hypotheses": stats["n_hypotheses"], "rounds": stats["n_rounds"]}),
+              "guess_host_ms": stats["host_ms"], "gate_calls": stats["gate_calls"]}
+    # the reference's CPU pipeline on a bounded sample of the same batch: exact matcher on one whole frame (all host
+    # cores) + the reference's own geometry code (oracle/_ref, single-threaded like the reference) on that frame
+    cpu = None
+    try:
+        dt, kind, cores, what, _ = cpu_reference_knn(descs, frames[0]["descriptors"], K)
+        cpu = {"matcher": {"kind": kind, "what": what, "cores": cores, "ms_per_frame": 1e3 * dt,
+                           "sample": "frame 0 (all %d keypoints)" % n_kp}}
+        from oracle import ref
+        if ref.available():
+            t0 = time.perf_counter()
+            exp = ref.process(frames[0]["keypoints_xy"], frames[0]["cloud"], out["matches"][:n_kp],
+                              out["counts"][:n_kp], out["matches_3d"][:n_kp], spans, 15, ITERS, 0.01, seed=9)
+            dg = time.perf_counter() - t0
+            cpu["geometry"] = {"kind": "reference", "what": "src/common compiled unmodified (oracle/_ref)", "cores": 1,
+                               "sample": "frame 0", "ms_per_frame": 1e3 * dg, "poses": len(exp)}
+            cpu["value"] = 1.0 / (dt + dg)
+            cpu["unit"] = UNIT
+            # parity of the pipeline on the frame the CPU reference just processed
+            mine = res[0]
+            same = len(mine["pose_results"]) == len(exp)
+            if same:
+                for p, inl, (eo, eR, eT, einl) in zip(mine["pose_results"], mine["inliers"], exp):
+                    same = same and int(p["object_index"]) == eo and list(inl) == list(einl) and \
+                        float(np.abs(p["R"].reshape(3, 3) - eR).max()) < 1e-4 and float(np.abs(p["T"] - eT).max()) < 1e-4
+            e2e["parity"] = {"checked": "frame 0: poses, inlier keypoint sets, R/T within 1e-4 vs oracle/_ref",
+                             "poses": len(exp), "mismatches": 0 if same else 1}
+    except Exception as e:                                      # the checker is optional on a box without cv2 / _ref
+        cpu = {"unavailable": str(e)[:200]}
+    e2e["cpu_baseline"] = cpu
+    m5.close()
+    gg.close()
+    return e2e, stages
+
+
+def c5_leg(args, hbm_peak, hbm_src):
+    """BASELINE config C5 (RANSAC stress): 100 objects x 2000 correspondences, 90 % outlier matches injected at the
+    GuessGenerator boundary, 4096 iterations per object."""
+    from tod_b200 import GuessGenerator, synth
+    n_obj, n_per, iters = args.c5_objects, 2000, 4096
+    g = synth.make_guess_inputs(n_obj, n_per, 0.1, seed=synth.BASE_SEED + 5, k=1, height=960, width=1280)
+    gg = GuessGenerator(min_inliers=15, n_ransac_iterations=iters, sensor_error=0.01, seed=11)
+    wall, res = [], None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res = gg.process(g["keypoints_xy"], g["cloud"], g["matches"], g["counts"], g["points3d"], g["spans"],
+                         max_poses=32 * n_obj)
+        wall.append(time.perf_counter() - t0)
+    st = gg.last_stats()
+    out = {"workload": "C5: %d objects x %d correspondences, 90%% outliers, %d iterations/object" % (n_obj, n_per, iters),
+           "wall_ms": 1e3 * float(np.median(wall[1:])), "poses": int(len(res["pose_results"])),
+           "objects_recovered": int(len(set(int(p["object_index"]) for p in res["pose_results"]))),
+           "k2": hbm_roofline("k2_adjacency_kernel", st["k2_bytes"], st["k2_ms"], hbm_peak, hbm_src,
+                              {"clusters": st["n_clusters"], "correspondences": st["n_correspondences"]}),
+           "k3": hbm_roofline("k3_score_kernel", st["k3_bytes"], st["k3_ms"], hbm_peak, hbm_src,
+                              {"hypotheses": st["n_hypotheses"], "rounds": st["n_rounds"]}),
+           "guess_host_ms": st["host_ms"], "gate_calls": st["gate_calls"]}
+    gg.close()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from tod_b200 import DescriptorMatcher, capi
+    from tod_b200 import DescriptorMatcher, capi, comm_unique_id
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,35 +432,39 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)   # plumbing only: id broadcast, barriers, max over ranks
     lib = capi.load()
 
     descs, points, queries = workload(args)
     kernel = {"auto": capi.TOD_KERNEL_AUTO, "popc": capi.TOD_KERNEL_POPC, "mma": capi.TOD_KERNEL_MMA}[args.kernel]
     m = DescriptorMatcher(k=args.k, radius=args.radius, device=local_rank, shard_rank=rank, shard_count=world,
-                          kernel=kernel)
+                          kernel=kernel, share_bounds=not args.no_share_bounds)
     for i, (d, p) in enumerate(zip(descs, points)):
         m.add_object("object_%03d" % i, d, p)
     m.train()
-
     k = args.k
     nqt = queries.shape[0]
+    m.reserve(nqt)
+    if world > 1:
+        # the exchange lives INSIDE the library: an NCCL communicator owned by the matcher handle (unique id created by
+        # rank 0's library, handed over by the host-side plumbing)
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        m.set_comm(box[0])
+
     stream = torch.cuda.Stream(device=dev)     # explicit, non-legacy: K1 / NCCL / merge are all ordered on it
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     q_dev = torch.from_numpy(queries).to(dev)
-    keys = torch.empty((nqt, k), dtype=torch.int32, device=dev)
-    keys_all = torch.empty((world, nqt, k), dtype=torch.int32, device=dev) if world > 1 else keys
     matches = torch.empty((nqt, k, 4), dtype=torch.int32, device=dev)
     counts = torch.empty((nqt,), dtype=torch.int32, device=dev)
     pts3d = torch.empty((nqt, k, 3), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
-        m.knn_keys_device(q_dev.data_ptr(), nqt, keys.data_ptr(), sptr)
-        if world > 1:
-            dist.all_gather_into_tensor(keys_all.view(-1), keys.view(-1))
-        m.merge_device(keys_all.data_ptr(), world, nqt, matches.data_ptr(), counts.data_ptr(), pts3d.data_ptr(), sptr)
+        # DescriptorMatcher.process on device buffers, one C-ABI call: K1 -> [top-k reduction -> ncclAllGather of the
+        # packed keys] -> merge / radius cut / decode / matches_3d gather
+        m.process_device(q_dev.data_ptr(), nqt, matches.data_ptr(), counts.data_ptr(), pts3d.data_ptr(), sptr)
 
     def barrier():
         if world > 1:
@@ -290,13 +516,11 @@ def run_ours(args):
     out = {"matches": m_np, "counts": c_host.numpy(), "matches_3d": p_host.numpy()}
 
     if world > 1:
-        # sharded path: the public API is the device-stage calls, the host<->device copies are the caller's — and a
-        # streaming caller overlaps them with compute: two buffer sets, copy-in / compute / copy-out streams chained by
-        # events.  Every step still moves its own inputs from pinned host memory and its own results back.
+        # sharded: a streaming caller overlaps its copies with the compute — two buffer sets, copy-in / compute /
+        # copy-out streams chained by events around tod_matcher_knn_device.  Every step still moves its own inputs from
+        # pinned host memory and its own results back.
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         qd = [torch.empty_like(q_dev) for _ in range(2)]
-        ky = [torch.empty_like(keys) for _ in range(2)]
-        ka = [torch.empty_like(keys_all) for _ in range(2)]
         mt = [torch.empty_like(matches) for _ in range(2)]
         ct = [torch.empty_like(counts) for _ in range(2)]
         pt = [torch.empty_like(pts3d) for _ in range(2)]
@@ -313,9 +537,7 @@ def run_ours(args):
                     ev_in[b].record(s_in)
                 stream.wait_event(ev_in[b])
                 stream.wait_event(ev_out[b])                 # the copy-out that last read mt[b] ... has finished
-                m.knn_keys_device(qd[b].data_ptr(), nqt, ky[b].data_ptr(), sptr)
-                dist.all_gather_into_tensor(ka[b].view(-1), ky[b].view(-1))
-                m.merge_device(ka[b].data_ptr(), world, nqt, mt[b].data_ptr(), ct[b].data_ptr(), pt[b].data_ptr(), sptr)
+                m.process_device(qd[b].data_ptr(), nqt, mt[b].data_ptr(), ct[b].data_ptr(), pt[b].data_ptr(), sptr)
                 ev_done[b].record(stream)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_done[b])
@@ -342,17 +564,26 @@ def run_ours(args):
     e2e_value = frames_total / e2e_s
     h2d = nqt * 32
     d2h = nqt * k * 16 + nqt * 4 + nqt * k * 12
+    comm_mode = m.comm_mode
 
-    # ---- sanity: the timed path produced real matches (planted queries are found) ----
-    res = m_np
-    if not os.environ.get("TOD_K1_DEBUG_MODE"):
-        assert (c_host.numpy() == k).all() or args.radius > 0
-        assert (res["distance"][:, 0] <= res["distance"][:, -1]).all()
+    # ---- the sharded reference-facing call itself (tod_matcher_knn, host buffers) must agree with the streamed result
+    if world > 1:
+        ref_m, ref_c, ref_p = m_np.copy(), c_host.numpy().copy(), p_host.numpy().copy()
+        m.process(q_host.numpy(), out=out)
+        assert (m_np == ref_m).all() and (c_host.numpy() == ref_c).all() and (p_host.numpy() == ref_p).all()
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
+
+    # ---- parity of exactly what was timed: bit-exact against the exact-Hamming reference on a fixed sample ----
+    parity = parity_sample(args, m_np, c_host.numpy(), p_host.numpy(), descs, points, queries)
+    if parity["mismatches"] != 0:
+        print(json.dumps({"error": "parity check failed", "parity": parity}), file=sys.stderr)
+        raise SystemExit(3)
+    assert (c_host.numpy() == k).all() or args.radius > 0
 
     # ---- roofline of the dominant kernel (K1) ----
     shard_rows = m.shard_rows
@@ -394,14 +625,15 @@ def run_ours(args):
         except Exception:
             pass
 
-    cpu = None
+    cpu = lsh = None
     if world == 1 and not args.no_cpu_baseline:
-        nsamp = min(args.cpu_sample_queries, args.keypoints)
+        # the exact matcher north_star names, ALL keypoints of a frame per repetition, on the box's host cores
+        nsamp = args.keypoints if args.cpu_sample_queries <= 0 else min(args.cpu_sample_queries, args.keypoints)
         times, info = [], None
         t_start = time.perf_counter()
-        while len(times) < 7 and (time.perf_counter() - t_start) < 15.0:
+        while len(times) < 8 and (time.perf_counter() - t_start) < 20.0:
             f = len(times) % args.frames
-            dt, kind, cores, what = cpu_reference_knn(descs, queries[f * args.keypoints:][:nsamp], args.k)
+            dt, kind, cores, what, _ = cpu_reference_knn(descs, queries[f * args.keypoints:][:nsamp], args.k)
             times.append(dt)
             info = (kind, cores, what)
         timed = times[1:] if len(times) > 1 else times      # first repetition warms the thread pool / page cache
@@ -409,6 +641,9 @@ def run_ours(args):
         cpu = {"value": cpu_value, "unit": UNIT, "cores": info[1], "kind": info[0],
                "sample": "%d x (%d of the %d keypoints of a frame vs the full %d-descriptor DB); %s" % (
                    len(timed), nsamp, args.keypoints, args.objects * args.rows, info[2])}
+        if not args.no_lsh:
+            k5 = cpu_reference_knn(descs, queries[:args.keypoints], 5)[4]
+            lsh = lsh_reference(descs, queries[:args.keypoints], k5)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -416,13 +651,29 @@ def run_ours(args):
             "config": config_dict(args, world),
             "gcmp_per_s": value * args.keypoints * args.objects * args.rows / 1e9,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "scope": ("DescriptorMatcher.process through the C-ABI with pinned host buffers" if world == 1 else
-                              "device-stage C-ABI calls + NCCL all-gather, pinned host buffers, copies of step i+1 / "
-                              "i-1 overlapped with the compute of step i (two buffer sets)")},
+                    "scope": ("DescriptorMatcher.process through the C-ABI (tod_matcher_knn) with pinned host buffers"
+                              if world == 1 else
+                              "tod_matcher_knn_device per step (K1 + in-library ncclAllGather + merge), pinned host "
+                              "buffers, copies of step i+1 / i-1 overlapped with the compute of step i")},
+            "parity": parity,
+            "collective": (None if world == 1 else
+                           {"where": "inside libtod_b200.so (ncclAllGather of packed top-k keys on the handle's "
+                                     "stream); no torch.distributed collective in the timed region",
+                            "comm_mode": comm_mode,
+                            "peer_shared_bounds": comm_mode == 2}),
             "gpu_launches": int(launches), "wall_s_timed_region": wall, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "cpu_baseline_lsh": lsh}
+    m.close()
+    if world == 1 and not args.no_pipeline:
+        torch.cuda.synchronize()
+        e2e_pipe, stages = pipeline_leg(args, descs, points, m, hbm_peak, hbm_src)
+        line["e2e_pipeline"] = e2e_pipe
+        line["stages"] = stages
+        if args.c5_objects > 0:
+            line["stages_c5"] = c5_leg(args, hbm_peak, hbm_src)
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

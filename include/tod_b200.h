@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TOD_B200_ABI_VERSION 1
+#define TOD_B200_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------------------------------------------- */
 enum {
@@ -86,15 +86,30 @@ typedef struct tod_matcher_params {
   int32_t shard_rank;   /* this handle holds rows [rank*ceil(N/count), ...) of the concatenated DB */
   int32_t shard_count;  /* 1 = whole DB on this GPU */
   int32_t kernel;       /* TOD_KERNEL_* : which K1 formulation to run */
-  int32_t reserved;
+  /* --- the two TODO blocks of DescriptorMatcher.cpp:223-229, implemented as opt-in extensions (default off: the
+   *     reference's `ratio_` is an unsigned int, so the .ork value 0.8 truncates to 0 and its block is empty) --- */
+  int32_t ratio_enabled;      /* 1: Lowe's ratio test on the two nearest neighbours, BEFORE the radius cut: a query
+                                 keeps at most its best match, and only if distance0 < ratio * distance1 (float
+                                 arithmetic, the OpenCV knnMatch(k=2) idiom); needs k >= 2.  A query with a single
+                                 neighbour in the whole DB keeps it. */
+  float ratio;                /* search_json_params.ratio as a real number (conf/detection.ork:39: 0.8) */
+  int32_t remove_duplicates;  /* 1: "remove matches that match the same (common descriptors)" (:229): when several
+                                 keypoints of one frame match the same DB descriptor, only the match with the
+                                 smallest (distance, queryIdx) survives; lists are compacted, order kept. */
+  int32_t frame_keypoints;    /* scope of remove_duplicates in a batched call: queries [f*n, (f+1)*n) are frame f;
+                                 0 = the whole call is one frame */
+  int32_t share_bounds;       /* sharded handles with a communicator: 1 (default) = K1's per-query pruning bounds are
+                                 pushed to the peer GPUs over NVLink while the kernel runs (results unchanged) */
 } tod_matcher_params;
 
-void tod_matcher_default_params(tod_matcher_params *p); /* k=5, radius=0, exact, device 0, 1 shard, auto */
+void tod_matcher_default_params(tod_matcher_params *p); /* k=5, radius=0, exact, device 0, 1 shard, auto, no ratio
+                                                           test, no duplicate removal, share_bounds=1 */
 
 /* configure(): parses the reference's "search_json_params" string — fields type, radius, ratio, n_tables, key_size,
  * multi_probe_level (DescriptorMatcher.cpp:159-181) — into *p (k stays 5, as hard-coded in the reference).
  * type "LSH" is accepted and mapped to the exact search; unknown types fail with TOD_ERR_INVALID instead of the
- * reference's bare `throw;` -> std::terminate (:182-186). */
+ * reference's bare `throw;` -> std::terminate (:182-186).  `ratio` is stored as a real number but only applied when
+ * the (non-reference) keys "ratio_enabled": true / "remove_duplicates": true are present. */
 int tod_matcher_params_from_json(const char *search_json_params, tod_matcher_params *p);
 
 int tod_matcher_create(const tod_matcher_params *p, tod_matcher **out);
@@ -121,9 +136,33 @@ int32_t tod_matcher_k(const tod_matcher *m);
 /* process() (DescriptorMatcher.cpp:195-252) with HOST buffers: knnMatch(k) -> radius cut -> matches_3d gather.
  *   descriptors: nq x 32 u8.   matches: nq x k (row q holds counts[q] valid entries, sorted by
  *   (distance, imgIdx, trainIdx) exactly like cv::BFMatcher(NORM_HAMMING).knnMatch).  counts: nq.
- *   points3d: nq x k x 3 f32 (matches_3d), may be NULL.  Only valid with shard_count == 1. */
+ *   points3d: nq x k x 3 f32 (matches_3d), may be NULL.
+ * With shard_count > 1 the handle needs a communicator (tod_matcher_set_comm); every rank calls with the same
+ * descriptors and every rank receives the same, complete result: K1 on the shard -> top-k reduction -> ncclAllGather
+ * of the packed keys -> merge, all on the handle's stream. */
 int tod_matcher_knn(tod_matcher *m, const uint8_t *descriptors, int32_t nq, tod_match *matches, int32_t *counts,
                     float *points3d);
+/* The same call with DEVICE buffers on the handle's device (descriptors already in HBM, results stay in HBM),
+ * enqueued on `stream` (a cudaStream_t; NULL = the handle's own stream) without synchronising it.  d_points3d may be
+ * NULL.  Works for shard_count == 1 and, with a communicator, for sharded handles. */
+int tod_matcher_knn_device(tod_matcher *m, const void *d_descriptors, int32_t nq, tod_match *d_matches,
+                           int32_t *d_counts, float *d_points3d, void *stream);
+/* Pre-size every per-call device buffer for up to max_nq queries, so that no cudaMalloc / cudaFree (an implicit device
+ * synchronisation) can happen inside a streamed step.  Call after tod_matcher_train. */
+int tod_matcher_reserve(tod_matcher *m, int32_t max_nq);
+
+/* ---- communicator of a sharded matcher (one process per GPU) ----------------------------------------------------
+ * tod_comm_unique_id: rank 0 creates a 128-byte NCCL unique id (ncclGetUniqueId) and hands it to the other ranks by
+ * any host-side means (MPI, torch.distributed broadcast, a file).  tod_matcher_set_comm: collective over all
+ * shard_count ranks — ncclCommInitRank on the handle's device with rank = shard_rank, world = shard_count; when
+ * share_bounds is set it also exchanges CUDA IPC handles of the per-query bound buffers so that K1 can push its
+ * pruning bounds straight into the peers' HBM over NVLink (falls back silently to local bounds if peer mapping is
+ * not possible).  libnccl.so.2 is loaded with dlopen at this point; the library has no link-time NCCL dependency. */
+#define TOD_COMM_ID_BYTES 128
+int tod_comm_unique_id(void *id_out);
+int tod_matcher_set_comm(tod_matcher *m, const void *unique_id);
+/* 0 = no communicator, 1 = NCCL only, 2 = NCCL + peer-shared bounds */
+int32_t tod_matcher_comm_mode(const tod_matcher *m);
 
 /* Sharding of the concatenated DB over `shard_count` GPUs (host-only, no device needed): rank r holds the contiguous
  * global rows [*begin, *begin + *rows), ceil(total/shard_count) rows each except the last ranks.  tod_matcher_train
@@ -275,6 +314,16 @@ int32_t tod_rng_next(uint64_t *state);
 
 /* Device time (ms) spent in K2 / K3 kernels and number of K3 hypotheses scored during the last process call. */
 void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_t *n_hypotheses, int32_t *n_rounds);
+/* Shape of the clique gate's work in the last process call (24 counters): [0..7] gates that reached the induced
+ * sub-graph stage by sub-graph size (buckets <= 16, 32, 64, 128, 256, 512, 1024, more), [8..15] the same by the size
+ * of the sub-graph's 7-core, [16] settled because the core has fewer than 8 vertices, [17] settled by the colouring
+ * bound, [18] bounded searches run, [19] of those, passes, [20] search steps summed; the rest reserved. */
+void tod_guess_last_gate_stats(const tod_guess *g, int64_t *out24);
+/* Algorithmic bytes (SURVEY.md §8d units) moved by the K2 launch (32 n in + two n x W bit-matrices out, summed over
+ * the clusters) and by all K3 launches ((3 rows + 2 masks) x W x 4 + 140 per hypothesis) of the last process call,
+ * with the number of (frame, object) clusters and correspondences: bench.py divides them by k2_ms / k3_ms. */
+void tod_guess_last_traffic(const tod_guess *g, double *k2_bytes, double *k3_bytes, int64_t *n_clusters,
+                            int64_t *n_correspondences);
 /* Host wall-clock profile (ms) of the last process call: [0] ClusterPerObject + upload + K2 + bit-matrix download,
  * [1] sampler, [2] K3 launches incl. copies and sync, [3] replay + inlier lists + clique gate, [4] refinement +
  * invalidation, [5] clique-gate evaluations (a count), [6] of those, settled by the exact no-8-clique proof without

@@ -36,16 +36,26 @@ def test_library_is_sm100a_only():
 
 
 def test_host_only_entry_points(lib):
-    assert lib.tod_abi_version() == 1
+    assert lib.tod_abi_version() == 2
     assert isinstance(lib.tod_last_error(), bytes)
     p = capi.MatcherParams()
     lib.tod_matcher_default_params(ctypes.byref(p))
     assert (p.k, p.radius, p.shard_count) == (5, 0, 1)
+    assert (p.ratio_enabled, p.remove_duplicates, p.frame_keypoints, p.share_bounds) == (0, 0, 0, 1)
+    assert ctypes.sizeof(capi.MatcherParams) == 48
     # conf/detection.ork `search:` subtree as ORK core would serialise it
     js = b'{"type": "LSH", "module": "ecto_opencv.features2d", "key_size": 16, "multi_probe_level": 1, ' \
          b'"n_tables": 10, "radius": 35, "ratio": 0.8}'
     assert lib.tod_matcher_params_from_json(js, ctypes.byref(p)) == capi.TOD_OK
     assert (p.radius, p.search_type, p.k) == (35, capi.TOD_SEARCH_LSH, 5)
+    # the reference's ratio_ is an unsigned int and its block is empty (DescriptorMatcher.cpp:170-171, 223-227): the
+    # value is remembered as a real number but the test stays off unless this library's own key asks for it
+    assert abs(p.ratio - 0.8) < 1e-6 and p.ratio_enabled == 0 and p.remove_duplicates == 0
+    js2 = b'{"type": "LSH", "radius": 35, "ratio": 0.7, "ratio_enabled": true, "remove_duplicates": true}'
+    q = capi.MatcherParams()
+    lib.tod_matcher_default_params(ctypes.byref(q))
+    assert lib.tod_matcher_params_from_json(js2, ctypes.byref(q)) == capi.TOD_OK
+    assert abs(q.ratio - 0.7) < 1e-6 and q.ratio_enabled == 1 and q.remove_duplicates == 1
     # unknown type: the reference does a bare `throw;` (DescriptorMatcher.cpp:182-186); here a status code
     assert lib.tod_matcher_params_from_json(b'{"type": "KDTREE", "radius": 1, "ratio": 0}', ctypes.byref(p)) \
         == capi.TOD_ERR_INVALID
@@ -56,6 +66,26 @@ def test_host_only_entry_points(lib):
     assert (g.min_inliers, g.n_ransac_iterations) == (15, 1000) and abs(g.sensor_error - 0.01) < 1e-9
     assert lib.tod_adjacency_row_words(1) == 4 and lib.tod_adjacency_row_words(129) == 8
     assert lib.tod_adjacency_row_words(0) == 0
+
+
+def test_comm_unique_id_is_host_only(lib):
+    """NCCL is bound with dlopen at first use; creating a unique id needs no GPU.  Two ids differ."""
+    capi.preload_nccl()            # a process that also imports torch must map torch's NCCL first (see capi.py)
+    a = ctypes.create_string_buffer(capi.TOD_COMM_ID_BYTES)
+    b = ctypes.create_string_buffer(capi.TOD_COMM_ID_BYTES)
+    rc = lib.tod_comm_unique_id(a)
+    if rc != capi.TOD_OK:
+        pytest.skip("NCCL cannot create an id here: %s" % lib.tod_last_error().decode())
+    assert lib.tod_comm_unique_id(b) == capi.TOD_OK
+    assert a.raw != b.raw
+    out = subprocess.run(["readelf", "-d", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libnccl" not in out                                # no link-time NCCL dependency
+
+
+def test_production_library_has_no_debug_knobs():
+    """The K1 ablation knobs (TOD_K1_DEBUG_MODE / TOD_K1_CHUNKS) exist only in the instrumented TOD_K1_STATS build."""
+    blob = open(capi.LIB_PATH, "rb").read()
+    assert b"TOD_K1_DEBUG_MODE" not in blob and b"TOD_K1_CHUNKS" not in blob
 
 
 def test_rng_stream_matches_oracle_restatement(lib):

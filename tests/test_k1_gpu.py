@@ -98,26 +98,188 @@ def test_radius_cut_like_detection_ork(kernel):
 
 @both_kernels
 def test_config_c3_full_size_2k_by_1m(kernel):
-    """north_star size: 2k keypoints x 1M descriptors (100 objects x 10k), k=2 — bit-exact against the C oracle on a
-    query subset, plus size-independent properties on all queries."""
+    """north_star size: 2k keypoints x 1M descriptors (100 objects x 10k), k=2 — bit-exact against the C oracle on ALL
+    2000 queries (matches, counts, matches_3d), plus size-independent properties."""
     descs, points = synth.make_db(100, 10000, seed=synth.BASE_SEED + 2)
     q, src_obj, src_row = synth.make_queries(descs, 2000, seed=synth.BASE_SEED + 102)
-    out = run_matcher(q, descs, points, 2, 0, kernel)
+    out = check_against_oracle(q, descs, points, 2, 0, kernel)
     m, c = out["matches"], out["counts"]
     assert (c == 2).all()
     assert (m["distance"][:, 0] <= m["distance"][:, 1]).all()            # sortedness
     true = src_obj >= 0                                                  # planted rows are found as the best match
     assert (m["imgIdx"][true, 0] == src_obj[true]).mean() > 0.999
     assert (m["trainIdx"][true, 0] == src_row[true]).mean() > 0.999
-    sub = np.arange(0, 2000, 8)
-    em, ec = hk.knn_c(q[sub], descs, 2, 0)
-    for f in ("trainIdx", "imgIdx", "distance"):
-        assert (m[f][sub] == em[f]).all()
     # idempotence: distances recomputed from the returned indices
     db, off = hk.concat_objects(descs)
     g = off[m["imgIdx"]] + m["trainIdx"]
     d = np.bitwise_count(q.view(np.uint64)[:, None, :] ^ db.view(np.uint64)[g]).sum(axis=2)
     assert (d == m["distance"]).all()
+
+
+def test_timed_bench_shape_128k_queries_by_1m():
+    """The exact plan bench.py times: one call with 64 frames x 2000 = 128 000 queries against the 1M-descriptor DB
+    (500 query tiles x db chunks), host-buffer call and device-buffer call.  Bit-exact against the C oracle on a
+    sample that covers the first and last query tiles and every frame; sortedness / distance recomputation on all."""
+    import torch
+    descs, points = synth.make_db(100, 10000, seed=synth.BASE_SEED + 2)
+    q = np.ascontiguousarray(np.concatenate(
+        [synth.make_queries(descs, 2000, seed=synth.BASE_SEED + 102 + f)[0] for f in range(64)]))
+    nq, k = q.shape[0], 2
+    m = DescriptorMatcher(k=k, radius=0)
+    for i, (d, p) in enumerate(zip(descs, points)):
+        m.add_object("obj%d" % i, d, p)
+    m.train()
+    m.reserve(nq)
+    out = m.process(q)
+    assert m.last_kernel == "mma"
+    mm, c = out["matches"], out["counts"]
+    assert (c == k).all() and (mm["distance"][:, 0] <= mm["distance"][:, 1]).all()
+    rng = np.random.default_rng(7)
+    idx = np.unique(np.concatenate([np.arange(256), np.arange(nq - 256, nq), rng.choice(nq, 768, replace=False),
+                                    np.arange(64) * 2000, np.arange(64) * 2000 + 1999]))
+    em, ec = hk.knn_c(q[idx], descs, k, 0)
+    assert (c[idx] == ec).all()
+    for f in ("trainIdx", "imgIdx", "distance"):
+        assert (mm[f][idx] == em[f]).all(), f
+    assert (mm["queryIdx"][idx] == idx[:, None]).all()
+    assert (out["matches_3d"][idx] == hk.gather_points3d(em, ec, points)).all()
+    db, off = hk.concat_objects(descs)                                   # every distance recomputed from its indices
+    for lo in range(0, nq, 16000):
+        g = off[mm["imgIdx"][lo:lo + 16000]] + mm["trainIdx"][lo:lo + 16000]
+        d = np.bitwise_count(q[lo:lo + 16000].view(np.uint64)[:, None, :] ^ db.view(np.uint64)[g]).sum(axis=2)
+        assert (d == mm["distance"][lo:lo + 16000]).all()
+    # the device-buffer entry point (what bench.py's `value` times) returns the same bytes
+    dev = torch.device("cuda", 0)
+    qd = torch.from_numpy(q).to(dev)
+    md = torch.empty((nq, k, 4), dtype=torch.int32, device=dev)
+    cd = torch.empty((nq,), dtype=torch.int32, device=dev)
+    pd = torch.empty((nq, k, 3), dtype=torch.float32, device=dev)
+    st = torch.cuda.Stream()
+    qd.record_stream(st)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        m.process_device(qd.data_ptr(), nq, md.data_ptr(), cd.data_ptr(), pd.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    assert (md.cpu().numpy().view(capi.MATCH_DTYPE).reshape(nq, k) == mm).all()
+    assert (cd.cpu().numpy() == c).all() and (pd.cpu().numpy() == out["matches_3d"]).all()
+    m.close()
+
+
+# ---- the two TODO blocks of DescriptorMatcher.cpp:223-229 as opt-in extensions ----------------------------------
+def lowe_ratio_numpy(em, ec, ratio, radius):
+    """numpy restatement: on the k-NN lists (distances pinned to cv2 by the oracle), BEFORE the radius cut, keep the
+    best match only, and only if distance0 < ratio * distance1 in float32 (a lone neighbour is kept)."""
+    nq, k = em.shape
+    out = np.zeros_like(em)
+    out["queryIdx"] = out["trainIdx"] = out["imgIdx"] = -1
+    cnt = np.zeros(nq, np.int32)
+    for i in range(nq):
+        if ec[i] == 0:
+            continue
+        d0 = np.float32(em["distance"][i, 0])
+        ok = True if ec[i] < 2 else bool(d0 < np.float32(ratio) * np.float32(em["distance"][i, 1]))
+        if ok and (radius == 0 or d0 <= radius):
+            out[i, 0] = em[i, 0]
+            cnt[i] = 1
+    return out, cnt
+
+
+def dedupe_numpy(em, ec, offsets, frame_kp):
+    """Inside each frame a DB descriptor keeps only the match with the smallest (distance, queryIdx); lists compacted."""
+    nq, k = em.shape
+    best = {}
+    for i in range(nq):
+        f = i // frame_kp if frame_kp else 0
+        for j in range(int(ec[i])):
+            key = (f, int(offsets[em["imgIdx"][i, j]] + em["trainIdx"][i, j]))
+            val = (int(em["distance"][i, j]), i)
+            if key not in best or val < best[key]:
+                best[key] = val
+    out = np.zeros_like(em)
+    out["queryIdx"] = out["trainIdx"] = out["imgIdx"] = -1
+    cnt = np.zeros(nq, np.int32)
+    for i in range(nq):
+        f = i // frame_kp if frame_kp else 0
+        for j in range(int(ec[i])):
+            key = (f, int(offsets[em["imgIdx"][i, j]] + em["trainIdx"][i, j]))
+            if best[key] == (int(em["distance"][i, j]), i):
+                out[i, cnt[i]] = em[i, j]
+                cnt[i] += 1
+    return out, cnt
+
+
+def oracle_lists(q, descs, k):
+    em, ec = hk.knn_c(q, descs, k, 0)
+    full = np.zeros(em.shape, capi.MATCH_DTYPE)
+    for f in ("trainIdx", "imgIdx", "distance"):
+        full[f] = em[f]
+    full["queryIdx"] = np.arange(q.shape[0])[:, None]
+    return full, ec
+
+
+@both_kernels
+@pytest.mark.parametrize("ratio,radius", [(0.8, 0), (0.6, 35), (0.95, 55)])
+def test_ratio_test_extension(kernel, ratio, radius):
+    descs, points = synth.make_db(5, 1500, seed=71)
+    q, _, _ = synth.make_queries(descs, 600, seed=72, flip_p=0.12)
+    q[:40] = descs[2][:40]                                      # exact duplicates: distance0 == 0
+    descs[3][:40] = descs[2][:40]                               # ... present twice in the DB: 0 < ratio * 0 fails
+    m = DescriptorMatcher(k=5, radius=radius, kernel=KERNELS[kernel], ratio=ratio)
+    for i, (d, p) in enumerate(zip(descs, points)):
+        m.add_object("o%d" % i, d, p)
+    m.train()
+    out = m.process(q)
+    m.close()
+    full, ec = oracle_lists(q, descs, 5)
+    exp, cnt = lowe_ratio_numpy(full, ec, ratio, radius)
+    assert (out["counts"] == cnt).all()
+    assert (out["counts"][:40] == 0).all()
+    keep = cnt == 1
+    for f in ("queryIdx", "trainIdx", "imgIdx", "distance"):
+        assert (out["matches"][f][keep, 0] == exp[f][keep, 0]).all(), f
+    assert 0 < keep.sum() < q.shape[0]
+    # default (reference-faithful): the same .ork string leaves the lists untouched — the reference's block is empty
+    m2 = DescriptorMatcher(search_json_params='{"type": "LSH", "radius": %d, "ratio": %g}' % (radius, ratio),
+                           kernel=KERNELS[kernel])
+    for i, (d, p) in enumerate(zip(descs, points)):
+        m2.add_object("o%d" % i, d, p)
+    m2.train()
+    plain = m2.process(q)
+    m2.close()
+    em, ec2 = hk.knn_c(q, descs, 5, radius)
+    assert_matches_equal(plain["matches"], plain["counts"], em["trainIdx"], em["imgIdx"], em["distance"], ec2)
+
+
+@pytest.mark.parametrize("frame_kp", [0, 100])
+def test_duplicate_match_removal_extension(frame_kp):
+    descs, points = synth.make_db(4, 800, seed=81)
+    rng = np.random.default_rng(82)
+    base, _, _ = synth.make_queries(descs, 100, seed=83)
+    q = np.concatenate([base, base, base])                       # every true match is claimed three times
+    flips = np.packbits(rng.random((300, 256)) < 0.01, axis=1)
+    q = np.ascontiguousarray(q ^ flips)
+    m = DescriptorMatcher(k=5, radius=35, remove_duplicates=True, frame_keypoints=frame_kp)
+    for i, (d, p) in enumerate(zip(descs, points)):
+        m.add_object("o%d" % i, d, p)
+    m.train()
+    out = m.process(q)
+    m.close()
+    em, ec = hk.knn_c(q, descs, 5, 35)
+    full = np.zeros(em.shape, capi.MATCH_DTYPE)
+    for f in ("trainIdx", "imgIdx", "distance"):
+        full[f] = em[f]
+    full["queryIdx"] = np.arange(q.shape[0])[:, None]
+    _, off = hk.concat_objects(descs)
+    exp, cnt = dedupe_numpy(full, ec, off, frame_kp)
+    assert (out["counts"] == cnt).all()
+    mask = np.arange(5)[None, :] < cnt[:, None]
+    for f in ("queryIdx", "trainIdx", "imgIdx", "distance"):
+        assert (out["matches"][f][mask] == exp[f][mask]).all(), f
+    e3 = hk.gather_points3d(exp, cnt, points)
+    assert (out["matches_3d"][mask] == e3[mask]).all()
+    assert cnt.sum() < ec.sum()                                   # something was removed
+    if frame_kp:                                                  # frames are independent: each keeps its own winner
+        assert cnt[:100].sum() > 0 and cnt[100:200].sum() > 0 and cnt[200:].sum() > 0
 
 
 def test_empty_and_error_paths():

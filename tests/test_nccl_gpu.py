@@ -1,0 +1,104 @@
+"""GPU, >= 2 devices: the sharded matcher with the exchange INSIDE the library — one process per GPU, each handle holds
+one row range of the DB and an NCCL communicator (tod_matcher_set_comm); tod_matcher_knn / tod_matcher_knn_device then
+run K1 -> top-k reduction -> ncclAllGather -> merge on the handle's stream and every rank must return the complete,
+bit-exact result (oracle = exact Hamming k-NN over the whole DB), step after step with changing queries (the
+peer-shared bound buffers alternate by step parity), with and without peer sharing.
+
+Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_nccl_gpu.py -m gpu`."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _workload():
+    from tod_b200 import synth
+    rng = np.random.default_rng(17)
+    descs, points = synth.make_db(7, [9000, 1200, 30000, 41, 15000, 7777, 22000], seed=301)
+    descs[1][:, :] = 0
+    descs[1][:, 9] = rng.integers(0, 4, descs[1].shape[0])            # tie-heavy object straddling a shard boundary
+    steps = []
+    for s, nq in enumerate([700, 2000, 333, 2000, 1, 4096]):          # ragged, changing sizes step after step
+        q, _, _ = synth.make_queries(descs, nq, seed=400 + s)
+        if s == 2:
+            q[:60] = 0
+        steps.append(q)
+    return descs, points, steps
+
+
+def _rank_main(rank, world, uid, k, radius, share, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    from oracle import hamming_knn as hk
+    from tod_b200 import DescriptorMatcher, capi
+    torch.cuda.set_device(rank)
+    descs, points, steps = _workload()
+    m = DescriptorMatcher(k=k, radius=radius, device=rank, shard_rank=rank, shard_count=world, share_bounds=share)
+    for i, (d, p) in enumerate(zip(descs, points)):
+        m.add_object("o%d" % i, d, p)
+    m.train()
+    m.reserve(4096)
+    # a sharded handle without a communicator must refuse the whole-call entry point
+    try:
+        m.process(steps[0])
+        raise AssertionError("expected TOD_ERR_STATE")
+    except capi.TodError as e:
+        assert e.code == capi.TOD_ERR_STATE
+    m.set_comm(uid)
+    mode = m.comm_mode
+    assert mode in (1, 2) and (share or mode == 1)
+    dev = torch.device("cuda", rank)
+    ok = True
+    for rep in range(2):                                                # twice through: parity flips every step
+        for q in steps:
+            out = m.process(q)                                         # host buffers: H2D + K1 + all-gather + merge + D2H
+            em, ec = hk.knn_c(q, descs, k, radius)
+            same = (out["counts"] == ec).all()
+            mask = np.arange(k)[None, :] < ec[:, None]
+            for f in ("trainIdx", "imgIdx", "distance"):
+                same = same and (out["matches"][f][mask] == em[f][mask]).all()
+            e3 = hk.gather_points3d(em, ec, points)
+            same = same and (out["matches_3d"][mask] == e3[mask]).all()
+            # device buffers, user stream
+            nq = q.shape[0]
+            qd = torch.from_numpy(q).to(dev)
+            md = torch.empty((nq, k, 4), dtype=torch.int32, device=dev)
+            cd = torch.empty((nq,), dtype=torch.int32, device=dev)
+            pd = torch.empty((nq, k, 3), dtype=torch.float32, device=dev)
+            torch.cuda.synchronize()
+            m.process_device(qd.data_ptr(), nq, md.data_ptr(), cd.data_ptr(), pd.data_ptr())
+            torch.cuda.synchronize()
+            same = same and (md.cpu().numpy().view(capi.MATCH_DTYPE).reshape(nq, k) == out["matches"]).all()
+            same = same and (cd.cpu().numpy() == out["counts"]).all()
+            ok = ok and bool(same)
+    np.save(os.path.join(out_dir, "ok_%d.npy" % rank), np.array([int(ok), mode, m.shard_rows]))
+    m.close()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("k,radius,share", [(2, 0, True), (5, 35, True), (5, 0, False)])
+def test_sharded_matcher_with_in_library_nccl(tmp_path, k, radius, share):
+    import torch.multiprocessing as mp
+    from tod_b200 import comm_unique_id
+    world = min(_n_gpus(), 4)
+    uid = comm_unique_id()
+    mp.spawn(_rank_main, args=(world, uid, k, radius, share, str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(os.path.join(str(tmp_path), "ok_%d.npy" % r)) for r in range(world)]
+    assert all(int(r[0]) == 1 for r in res), res
+    assert len(set(int(r[1]) for r in res)) == 1                        # every rank agrees on the communicator mode
+    descs, _, _ = _workload()
+    assert sum(int(r[2]) for r in res) == sum(d.shape[0] for d in descs)

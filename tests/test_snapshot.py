@@ -50,6 +50,38 @@ def test_snapshot_rejects_garbage(tmp_path):
         dbio.write_snapshot(good, ["a"], descs, points)
 
 
+def test_snapshot_rejects_corrupted_header_offsets(tmp_path):
+    """Header offsets that would wrap a u64 sum, point outside the file, or are misaligned must be refused — never
+    dereferenced (the validation works by subtraction against the file size)."""
+    lib = capi.load()
+    descs, points = synth.make_db(1, 40, seed=2)
+    good = os.path.join(str(tmp_path), "good.todb")
+    dbio.write_snapshot(good, ["a"], descs, points)
+    raw = bytearray(open(good, "rb").read())
+    size = len(raw)
+    # header: magic[8] version u32 n_objects u32 total_rows u64 off_table off_desc off_pts off_ids file_bytes (u64 each)
+    OFF = {"total_rows": 16, "off_table": 24, "off_desc": 32, "off_pts": 40, "off_ids": 48}
+    cases = [("off_table", 2 ** 64 - 24), ("off_table", size + 8), ("off_table", 65), ("off_table", 2 ** 63),
+             ("off_desc", 2 ** 64 - 32), ("off_desc", size + 64), ("off_pts", 2 ** 64 - 16), ("off_pts", 0),
+             ("off_ids", 2 ** 64 - 1), ("off_ids", size + 1), ("total_rows", 2 ** 59), ("total_rows", 2 ** 64 - 1),
+             ("total_rows", 41)]
+    path = os.path.join(str(tmp_path), "bad.todb")
+    for field, value in cases:
+        bad = bytearray(raw)
+        bad[OFF[field]:OFF[field] + 8] = int(value).to_bytes(8, "little")
+        open(path, "wb").write(bad)
+        h = ctypes.c_void_p()
+        assert lib.tod_snapshot_open(path.encode(), ctypes.byref(h)) == capi.TOD_ERR_PARSE, (field, value)
+    bad = bytearray(raw)
+    bad[12:16] = (2 ** 32 - 1).to_bytes(4, "little")                                         # n_objects
+    open(path, "wb").write(bad)
+    h = ctypes.c_void_p()
+    assert lib.tod_snapshot_open(path.encode(), ctypes.byref(h)) == capi.TOD_ERR_PARSE
+    h = ctypes.c_void_p()
+    assert lib.tod_snapshot_open(good.encode(), ctypes.byref(h)) == capi.TOD_OK               # the original still opens
+    lib.tod_snapshot_close(h)
+
+
 def test_import_cv_filestorage(tmp_path):
     cv2 = pytest.importorskip("cv2")
     descs, points = synth.make_db(1, 222, seed=9)

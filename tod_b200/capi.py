@@ -13,6 +13,7 @@ TOD_OK, TOD_ERR_INVALID, TOD_ERR_STATE, TOD_ERR_CUDA, TOD_ERR_LIMIT, TOD_ERR_PAR
 TOD_SEARCH_EXACT, TOD_SEARCH_LSH = 0, 1
 TOD_KERNEL_AUTO, TOD_KERNEL_POPC, TOD_KERNEL_MMA = 0, 1, 2
 TOD_MAX_K = 8
+TOD_COMM_ID_BYTES = 128
 
 MATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
@@ -24,7 +25,9 @@ assert MATCH_DTYPE.itemsize == 16 and KEYPOINT_DTYPE.itemsize == 28 and POSE_DTY
 class MatcherParams(ctypes.Structure):
     _fields_ = [("k", ctypes.c_int32), ("radius", ctypes.c_uint32), ("search_type", ctypes.c_int32),
                 ("device", ctypes.c_int32), ("shard_rank", ctypes.c_int32), ("shard_count", ctypes.c_int32),
-                ("kernel", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("kernel", ctypes.c_int32), ("ratio_enabled", ctypes.c_int32), ("ratio", ctypes.c_float),
+                ("remove_duplicates", ctypes.c_int32), ("frame_keypoints", ctypes.c_int32),
+                ("share_bounds", ctypes.c_int32)]
 
 
 class GuessParams(ctypes.Structure):
@@ -62,6 +65,11 @@ SIGNATURES = [
     ("tod_matcher_span", _F, [_P, _I32]),
     ("tod_matcher_k", _I32, [_P]),
     ("tod_matcher_knn", ctypes.c_int, [_P, _P, _I32, _P, _P, _P]),
+    ("tod_matcher_knn_device", ctypes.c_int, [_P, _P, _I32, _P, _P, _P, _P]),
+    ("tod_matcher_reserve", ctypes.c_int, [_P, _I32]),
+    ("tod_comm_unique_id", ctypes.c_int, [_P]),
+    ("tod_matcher_set_comm", ctypes.c_int, [_P, _P]),
+    ("tod_matcher_comm_mode", _I32, [_P]),
     ("tod_shard_range", ctypes.c_int, [_I64, _I32, _I32, ctypes.POINTER(_I64), ctypes.POINTER(_I64)]),
     ("tod_pack_key", _U32, [_U32, _U32]),
     ("tod_matcher_knn_keys_device", ctypes.c_int, [_P, _P, _I32, _P, _P]),
@@ -93,6 +101,9 @@ SIGNATURES = [
                                                ctypes.POINTER(_I32), _P, _I32]),
     ("tod_rng_seed", _U64, [_U64, _U32, _U32]),
     ("tod_rng_next", _I32, [ctypes.POINTER(_U64)]),
+    ("tod_guess_last_gate_stats", None, [_P, ctypes.POINTER(_I64)]),
+    ("tod_guess_last_traffic", None, [_P, ctypes.POINTER(_D), ctypes.POINTER(_D), ctypes.POINTER(_I64),
+                                      ctypes.POINTER(_I64)]),
     ("tod_guess_last_profile", None, [_P, ctypes.POINTER(_D)]),
     ("tod_guess_last_stats", None, [_P, ctypes.POINTER(_F), ctypes.POINTER(_F), ctypes.POINTER(_I64),
                                     ctypes.POINTER(_I32)]),
@@ -115,6 +126,31 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+_nccl_preloaded = False
+
+
+def preload_nccl():
+    """libtod_b200.so binds NCCL with dlopen("libnccl.so.2") at first use, which returns the copy already mapped in
+    the process if there is one.  A Python process that will ALSO import torch must end up with torch's bundled NCCL
+    (torch needs symbols of its own, newer version), so map that copy first when it exists — found through the
+    `nvidia.nccl` wheel, without importing torch.  No-op when the wheel is absent (the system library is used)."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            for d in spec.submodule_search_locations:
+                path = os.path.join(d, "lib", "libnccl.so.2")
+                if os.path.exists(path):
+                    ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+                    return
+    except Exception:
+        pass
 
 
 def check(rc):

@@ -17,7 +17,8 @@ class DescriptorMatcher:
     """
 
     def __init__(self, search_json_params=None, k=None, radius=None, device=0, shard_rank=0, shard_count=1,
-                 kernel=capi.TOD_KERNEL_AUTO):
+                 kernel=capi.TOD_KERNEL_AUTO, ratio=None, remove_duplicates=None, frame_keypoints=0,
+                 share_bounds=True):
         lib = capi.load()
         p = capi.MatcherParams()
         lib.tod_matcher_default_params(ctypes.byref(p))
@@ -30,6 +31,12 @@ class DescriptorMatcher:
         if radius is not None:
             p.radius = int(radius)
         p.device, p.shard_rank, p.shard_count, p.kernel = int(device), int(shard_rank), int(shard_count), int(kernel)
+        if ratio is not None:        # opt-in extension (the reference's ratio block is an empty TODO)
+            p.ratio_enabled, p.ratio = (1, float(ratio)) if ratio else (0, 0.0)
+        if remove_duplicates is not None:
+            p.remove_duplicates = 1 if remove_duplicates else 0
+        p.frame_keypoints = int(frame_keypoints)
+        p.share_bounds = 1 if share_bounds else 0
         self.params = p
         self._h = ctypes.c_void_p()
         capi.check(lib.tod_matcher_create(ctypes.byref(p), ctypes.byref(self._h)))
@@ -111,6 +118,27 @@ class DescriptorMatcher:
             p3 = np.empty((nq, k, 3), np.float32)
         capi.check(self._lib.tod_matcher_knn(self._h, capi._ptr(q), nq, capi._ptr(m), capi._ptr(c), capi._ptr(p3)))
         return {"matches": m, "counts": c, "matches_3d": p3, "object_ids": self.object_ids, "spans": self.spans}
+
+    def reserve(self, max_nq):
+        """Pre-size every per-call device buffer (no cudaMalloc / cudaFree inside a streamed step afterwards)."""
+        capi.check(self._lib.tod_matcher_reserve(self._h, int(max_nq)))
+
+    def set_comm(self, unique_id):
+        """Collective over the shard_count ranks: NCCL communicator (+ peer-shared K1 bounds over NVLink)."""
+        capi.preload_nccl()
+        buf = ctypes.create_string_buffer(bytes(unique_id), capi.TOD_COMM_ID_BYTES)
+        capi.check(self._lib.tod_matcher_set_comm(self._h, buf))
+
+    @property
+    def comm_mode(self):
+        return int(self._lib.tod_matcher_comm_mode(self._h))
+
+    def process_device(self, d_query_ptr, nq, d_matches_ptr, d_counts_ptr, d_points3d_ptr, stream=None):
+        """DescriptorMatcher.process on device buffers (tod_matcher_knn_device), enqueued on `stream`."""
+        capi.check(self._lib.tod_matcher_knn_device(self._h, ctypes.c_void_p(d_query_ptr), int(nq),
+                                                    ctypes.c_void_p(d_matches_ptr), ctypes.c_void_p(d_counts_ptr),
+                                                    ctypes.c_void_p(d_points3d_ptr) if d_points3d_ptr else None,
+                                                    ctypes.c_void_p(stream) if stream else None))
 
     def knn_keys_device(self, d_query_ptr, nq, d_keys_ptr, stream=None):
         capi.check(self._lib.tod_matcher_knn_keys_device(self._h, ctypes.c_void_p(d_query_ptr), int(nq),
@@ -217,7 +245,7 @@ class GuessGenerator:
         sp = np.ascontiguousarray(spans_by_index, np.float32)
         poses = np.zeros(max_poses, capi.POSE_DTYPE)
         n_poses = ctypes.c_int32(0)
-        cap = max(1, kp.shape[0] * 2)
+        cap = max(1, kp.shape[0] * max(1, min(k, sp.shape[0])))   # a keypoint can be an inlier of one pose per object
         inl = np.zeros(cap, np.int32)
         capi.check(self._lib.tod_guess_process(self._h, capi._ptr(kp), kp.shape[0], capi._ptr(cloud), H, W,
                                                capi._ptr(m), capi._ptr(c), k, capi._ptr(p3), capi._ptr(sp),
@@ -261,7 +289,7 @@ class GuessGenerator:
         poses = np.zeros(max_poses, capi.POSE_DTYPE)
         frames = np.zeros(max_poses, np.int32)
         n_poses = ctypes.c_int32(0)
-        cap = max(1, kp.shape[0] * 2)
+        cap = max(1, kp.shape[0] * max(1, min(k, sp.shape[0])))
         inl = np.zeros(cap, np.int32)
         capi.check(self._lib.tod_guess_process_batch(self._h, F, capi._ptr(off), capi._ptr(kp), capi._ptr(clouds), H, W,
                                                      capi._ptr(m), capi._ptr(c), k, capi._ptr(p3), capi._ptr(sp),
@@ -287,7 +315,18 @@ class GuessGenerator:
         self._lib.tod_guess_last_stats(self._h, ctypes.byref(k2), ctypes.byref(k3), ctypes.byref(nh), ctypes.byref(nr))
         prof = (ctypes.c_double * 12)()
         self._lib.tod_guess_last_profile(self._h, prof)
-        return {"k2_ms": k2.value, "k3_ms": k3.value, "n_hypotheses": nh.value, "n_rounds": nr.value,
+        b2, b3 = ctypes.c_double(), ctypes.c_double()
+        ncl, ncor = ctypes.c_int64(), ctypes.c_int64()
+        self._lib.tod_guess_last_traffic(self._h, ctypes.byref(b2), ctypes.byref(b3), ctypes.byref(ncl),
+                                         ctypes.byref(ncor))
+        gh = (ctypes.c_int64 * 24)()
+        self._lib.tod_guess_last_gate_stats(self._h, gh)
+        gh = [int(x) for x in gh]
+        return {"gate_shape": {"by_graph_size": gh[0:8], "by_core_size": gh[8:16], "core_too_small": gh[16],
+                               "colour_bound": gh[17], "searches": gh[18], "search_passes": gh[19],
+                               "search_steps": gh[20]},
+                "k2_ms": k2.value, "k3_ms": k3.value, "k2_bytes": b2.value, "k3_bytes": b3.value,
+                "n_clusters": ncl.value, "n_correspondences": ncor.value, "n_hypotheses": nh.value, "n_rounds": nr.value,
                 "host_ms": {"cluster_k2": prof[0], "sampler": prof[1], "k3_launch_sync": prof[2],
                             "replay_gate": prof[3], "refine_invalidate": prof[4], "total": prof[7]},
                 "gate_calls": int(prof[5]), "gate_proved_empty": int(prof[6]), "gate_core_rejects": int(prof[11]),
@@ -318,3 +357,11 @@ def detector_from_ork(parameters, device=0, seed=0):
     m = DescriptorMatcher(search_json_params=json.dumps(parameters["search"]), device=device)
     g = GuessGenerator(device=device, seed=seed, **guess)
     return m, g
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it and hands it to the other ranks by any host-side means)."""
+    capi.preload_nccl()
+    buf = ctypes.create_string_buffer(capi.TOD_COMM_ID_BYTES)
+    capi.check(capi.load().tod_comm_unique_id(buf))
+    return buf.raw

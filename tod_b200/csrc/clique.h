@@ -50,6 +50,8 @@ class CliqueFinder {
     ++degree_[size_t(b)];
   }
 
+  int steps() const { return steps_; }  // search steps of the last find()
+
   bool connected(int a, int b) const { return (bits_[size_t(a) * words_ + (b >> 6)] >> (b & 63)) & 1ull; }
 
   // The gate's question (sac_model_registration_graph.h:260-265): would find(minimal_size) return MORE than

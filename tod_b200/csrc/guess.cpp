@@ -231,7 +231,18 @@ struct GateScratch {
   long calls = 0, proved_empty = 0;  // gate evaluations / those settled by the no-8-clique proof
   long core_rejects = 0;             // settled even earlier: fewer than 8 candidates inside the round's 7-core
   double ms_setup = 0, ms_proof = 0, ms_search = 0;
+  // shape of the gate's work (tod_guess_last_gate_stats): [0..7] gates by induced-graph size, [8..15] by the size of
+  // its 7-core (buckets <=16, 32, 64, 128, 256, 512, 1024, more), [16] core smaller than 8, [17] settled by the
+  // colouring bound, [18] bounded searches run, [19] of those, passes, [20] search steps summed
+  long hist[24] = {0};
+  int last_core = 0;
 };
+
+inline int size_bucket(int n) {
+  int b = 0;
+  for (int lim = 16; b < 7 && n > lim; lim <<= 1) ++b;
+  return b;
+}
 
 // Exact early "no": true iff the induced graph provably has NO clique of `size` vertices, so the bounded search of the
 // reference (whatever its order, early stop and step budget) cannot return one and the gate fails
@@ -257,6 +268,7 @@ bool proves_no_clique(GateScratch &g, int nv, int words, int size) {
       }
     }
   }
+  g.last_core = n_alive;
   if (n_alive < size) return true;
   // greedy colouring of the core with independent sets built on bit masks
   g.uncoloured = g.alive;
@@ -406,14 +418,20 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
   const bool none = proves_no_clique(g, nv, words, int(minimal) + 1);
   const Clock::time_point t2 = Clock::now();
   g.ms_proof += std::chrono::duration<double, std::milli>(t2 - t1).count();
+  ++g.hist[size_bucket(nv)];
+  ++g.hist[8 + size_bucket(g.last_core)];
   if (none) {
     ++g.proved_empty;
+    ++g.hist[g.last_core < int(minimal) + 1 ? 16 : 17];
     return false;
   }
   // the bounded clique search (:258-265)
   tod::CliqueFinder finder(nv, g.adj.data());
   const bool ok = finder.finds_more_than(unsigned(minimal));
   g.ms_search += ms_since(t2);
+  ++g.hist[18];
+  g.hist[19] += ok ? 1 : 0;
+  g.hist[20] += finder.steps();
   return ok;
 }
 
@@ -458,10 +476,13 @@ struct tod_guess {
   DeviceBuffer d_off, d_mo, d_q, d_t, d_px, d_sp, d_P, d_S, d_desc, d_valid, d_finite, d_hyps, d_counts, d_R, d_T;
   tod::PinnedBuffer h_P, h_S;  // host copies of the bit-matrices (read by the sampler and the gate)
   float k2_ms = 0, k3_ms = 0;
+  double k2_bytes = 0, k3_bytes = 0;  // algorithmic bytes of the last call's K2 / K3 launches (SURVEY.md §8d units)
+  int64_t n_clusters = 0, n_correspondences = 0;
   int64_t n_hyp_total = 0;
   int32_t n_rounds = 0;
   // host wall-clock profile of the last process call (ms): see tod_guess_last_profile
   double prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t gate_hist[24] = {0};
   HostPool *pool = nullptr;
 };
 
@@ -574,6 +595,19 @@ void tod_guess_last_profile(const tod_guess *g, double *ms12) {
   for (int i = 0; i < 12; ++i) ms12[i] = g ? g->prof[i] : 0.0;
 }
 
+void tod_guess_last_gate_stats(const tod_guess *g, int64_t *out24) {
+  if (!out24) return;
+  for (int i = 0; i < 24; ++i) out24[i] = g ? g->gate_hist[i] : 0;
+}
+
+void tod_guess_last_traffic(const tod_guess *g, double *k2_bytes, double *k3_bytes, int64_t *n_clusters,
+                            int64_t *n_correspondences) {
+  if (k2_bytes) *k2_bytes = g ? g->k2_bytes : 0.0;
+  if (k3_bytes) *k3_bytes = g ? g->k3_bytes : 0.0;
+  if (n_clusters) *n_clusters = g ? g->n_clusters : 0;
+  if (n_correspondences) *n_correspondences = g ? g->n_correspondences : 0;
+}
+
 void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_t *n_hyp, int32_t *n_rounds) {
   if (k2_ms) *k2_ms = g ? g->k2_ms : 0.f;
   if (k3_ms) *k3_ms = g ? g->k3_ms : 0.f;
@@ -589,9 +623,12 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   TOD_REQUIRE(g && n_poses, "null argument");
   *n_poses = 0;
   g->k2_ms = g->k3_ms = 0.f;
+  g->k2_bytes = g->k3_bytes = 0.0;
+  g->n_clusters = g->n_correspondences = 0;
   g->n_hyp_total = 0;
   g->n_rounds = 0;
   for (double &v : g->prof) v = 0.0;
+  for (int64_t &v : g->gate_hist) v = 0;
   const Clock::time_point t_total = Clock::now();
   Clock::time_point t_phase = t_total;
   TOD_REQUIRE(n_frames >= 0 && k >= 1 && n_objects >= 0 && max_poses >= 0, "bad sizes");
@@ -701,6 +738,9 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   const int nc = int(clusters.size());
   const int64_t N = offsets.back();
   const size_t mat_words = size_t(mo.back());
+  g->n_clusters = nc;
+  g->n_correspondences = N;
+  g->k2_bytes = 32.0 * double(N) + 2.0 * 4.0 * double(mat_words);  // 32 n in + two n x W bit-matrices out
 
   // ---- FillAdjacency for every cluster: K2 --------------------------------------------------------------------------
   std::vector<float> all_q(size_t(N) * 3), all_t(size_t(N) * 3), all_px(size_t(N) * 2);
@@ -862,6 +902,10 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         TOD_CUDA(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
         g->k3_ms += ms;
         g->n_hyp_total += H;
+        for (int ci : active_idx) {  // per hypothesis: 3 physical rows + valid + finite masks, samples, triple, result
+          const Cluster *c = clusters[size_t(ci)];
+          g->k3_bytes += double(c->hyps.size() / 3) * (5.0 * 4.0 * double(c->W) + 72.0 + 16.0 + 52.0);
+        }
       }
       g->prof[2] += ms_since(t_phase);
 
@@ -1115,6 +1159,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     g->prof[8] += sc.gate.ms_setup;
     g->prof[9] += sc.gate.ms_proof;
     g->prof[10] += sc.gate.ms_search;
+    for (int i = 0; i < 24; ++i) g->gate_hist[i] += sc.gate.hist[i];
   }
   g->prof[7] = ms_since(t_total);
   if (int64_t(found.size()) > max_poses)

@@ -30,6 +30,9 @@ struct Value {
   }
 };
 
+// true / non-zero number
+inline bool truthy(const Value &v) { return (v.type == Value::Bool && v.b) || (v.type == Value::Number && v.num != 0); }
+
 class Parser {
  public:
   explicit Parser(const std::string &s) : s_(s) {}

@@ -57,11 +57,21 @@ __global__ void __launch_bounds__(128)
 finalize_matches_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, uint32_t radius,
                         const uint32_t *__restrict__ obj_offsets, int n_objects, const float *__restrict__ points,
                         tod_match *__restrict__ matches, int32_t *__restrict__ counts,
-                        float *__restrict__ points3d) {
+                        float *__restrict__ points3d, int ratio_enabled, float ratio, uint32_t *__restrict__ rows_out) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   uint32_t best[K];
   reduce_query<K>(keys, n_src, nq, q, best);
+  if (ratio_enabled && K >= 2) {
+    // the ratio-test TODO of DescriptorMatcher.cpp:223-227 as Lowe's test on the two nearest neighbours (before the
+    // radius cut): keep the best match only, and only if distance0 < ratio * distance1
+    if (best[0] != kKeyEmpty && best[K >= 2 ? 1 : 0] != kKeyEmpty) {
+      const float d0 = float(best[0] >> kKeyRowBits), d1 = float(best[K >= 2 ? 1 : 0] >> kKeyRowBits);
+      if (!(d0 < __fmul_rn(ratio, d1))) best[0] = kKeyEmpty;
+    }
+#pragma unroll
+    for (int i = 1; i < K; ++i) best[i] = kKeyEmpty;
+  }
   int n = 0;
 #pragma unroll
   for (int i = 0; i < K; ++i) {
@@ -92,6 +102,7 @@ finalize_matches_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, ui
       m.queryIdx = -1; m.trainIdx = -1; m.imgIdx = -1; m.distance = 0.f;
     }
     matches[size_t(q) * K + i] = m;
+    if (rows_out) rows_out[size_t(q) * K + i] = keep ? (key & kKeyRowMask) : 0xFFFFFFFFu;
     if (points3d) {
       float *o = points3d + (size_t(q) * K + i) * 3;
       o[0] = px; o[1] = py; o[2] = pz;
@@ -100,7 +111,95 @@ finalize_matches_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, ui
   counts[q] = n;
 }
 
+// ---- duplicate-match removal (the TODO at DescriptorMatcher.cpp:229) ------------------------------------------------
+// A DB descriptor matched by several keypoints of one frame keeps only the match with the smallest (distance, queryIdx).
+// Open-addressing hash table keyed by (frame, global row): pass 1 records the winner per key with atomicMin, pass 2
+// drops the losers and compacts every query's list in place (order kept).
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+dedupe_insert_kernel(const tod_match *__restrict__ matches, const int32_t *__restrict__ counts,
+                     const uint32_t *__restrict__ rows, int nq, int k, int frame_kp,
+                     unsigned long long *__restrict__ hkeys, unsigned long long *__restrict__ hvals, uint64_t mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq * k) return;
+  const int q = i / k, j = i - q * k;
+  if (j >= counts[q]) return;
+  const uint64_t frame = frame_kp > 0 ? uint64_t(q / frame_kp) : 0ull;
+  const unsigned long long key = ((frame << 32) | uint64_t(rows[i])) + 1ull;
+  const unsigned long long val = (uint64_t(uint32_t(matches[i].distance)) << 32) | uint64_t(uint32_t(q));
+  uint64_t h = mix64(key) & mask;
+  for (;;) {
+    const unsigned long long old = atomicCAS(hkeys + h, 0ull, key);
+    if (old == 0ull || old == key) {
+      atomicMin(hvals + h, val);
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+dedupe_filter_kernel(tod_match *__restrict__ matches, int32_t *__restrict__ counts, float *__restrict__ points3d,
+                     const uint32_t *__restrict__ rows, int nq, int k, int frame_kp,
+                     const unsigned long long *__restrict__ hkeys, const unsigned long long *__restrict__ hvals,
+                     uint64_t mask) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int n = counts[q];
+  const uint64_t frame = frame_kp > 0 ? uint64_t(q / frame_kp) : 0ull;
+  int out = 0;
+  for (int j = 0; j < n; ++j) {
+    const size_t i = size_t(q) * k + j;
+    const tod_match m = matches[i];
+    const unsigned long long key = ((frame << 32) | uint64_t(rows[i])) + 1ull;
+    const unsigned long long val = (uint64_t(uint32_t(m.distance)) << 32) | uint64_t(uint32_t(q));
+    uint64_t h = mix64(key) & mask;
+    while (hkeys[h] != key) h = (h + 1) & mask;
+    if (hvals[h] != val) continue;  // another keypoint of this frame owns the descriptor
+    if (out != j) {
+      matches[size_t(q) * k + out] = m;
+      if (points3d)
+        for (int d = 0; d < 3; ++d) points3d[(size_t(q) * k + out) * 3 + d] = points3d[i * 3 + d];
+    }
+    ++out;
+  }
+  for (int j = out; j < n; ++j) {
+    tod_match e;
+    e.queryIdx = -1; e.trainIdx = -1; e.imgIdx = -1; e.distance = 0.f;
+    matches[size_t(q) * k + j] = e;
+    if (points3d)
+      for (int d = 0; d < 3; ++d) points3d[(size_t(q) * k + j) * 3 + d] = 0.f;
+  }
+  counts[q] = out;
+}
+
 }  // namespace
+
+cudaError_t launch_remove_duplicates(tod_match *d_matches, int32_t *d_counts, float *d_points3d,
+                                     const uint32_t *d_rows, int nq, int k, int frame_keypoints, void *d_hkeys,
+                                     void *d_hvals, size_t table_slots, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(d_hkeys, 0, table_slots * 8, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_hvals, 0xFF, table_slots * 8, stream);
+  if (e != cudaSuccess) return e;
+  const int n = nq * k;
+  dedupe_insert_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_matches, d_counts, d_rows, nq, k, frame_keypoints,
+                                                            static_cast<unsigned long long *>(d_hkeys),
+                                                            static_cast<unsigned long long *>(d_hvals),
+                                                            uint64_t(table_slots - 1));
+  dedupe_filter_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(d_matches, d_counts, d_points3d, d_rows, nq, k,
+                                                             frame_keypoints,
+                                                             static_cast<const unsigned long long *>(d_hkeys),
+                                                             static_cast<const unsigned long long *>(d_hvals),
+                                                             uint64_t(table_slots - 1));
+  count_launch(2);
+  return cudaGetLastError();
+}
 
 #define TOD_DISPATCH_K(k, CALL)       \
   switch (k) {                        \
@@ -127,12 +226,12 @@ cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k,
 cudaError_t launch_finalize_matches(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t radius,
                                     const uint32_t *d_obj_offsets, int n_objects, const float *d_points,
                                     tod_match *d_matches, int32_t *d_counts, float *d_points3d,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, int ratio_enabled, float ratio, uint32_t *d_rows_out) {
   if (nq <= 0) return cudaSuccess;
   const int blocks = (nq + 127) / 128;
   TOD_DISPATCH_K(k, (finalize_matches_kernel<K><<<blocks, 128, 0, stream>>>(
                         d_keys, n_src, nq, radius, d_obj_offsets, n_objects, d_points, d_matches, d_counts,
-                        d_points3d)));
+                        d_points3d, ratio_enabled, ratio, d_rows_out)));
   count_launch();
   return cudaGetLastError();
 }

@@ -182,6 +182,17 @@ k3_score_kernel(const K3Cluster *__restrict__ clusters, const float *__restrict_
       ct[d] *= third;
       cq[d] *= third;
     }
+    // Reference-faithful mode (threshold^2 == +inf) without pose output: the count is popc(AND) + 3 unless (R, T) is
+    // non-finite, and with finite samples of ordinary magnitude every step of the fit stays finite (the SVD of a
+    // rank-deficient H does too, like cv::SVD) — so the double-precision Jacobi solve is skipped.  Samples with a
+    // non-finite or astronomically large coordinate (where float products could overflow) take the full path.
+    bool tame = true;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) tame = tame && fabsf(st[i][d]) < 1e15f && fabsf(sq[i][d]) < 1e15f;
+    const bool need_fit = !exact_inf || Rout != nullptr || Tout != nullptr || !tame;
+    if (need_fit) {
     float Hf[3][3];
     {
       double Hd[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
@@ -210,6 +221,12 @@ k3_score_kernel(const K3Cluster *__restrict__ clusters, const float *__restrict_
     for (int i = 0; i < 9; ++i) rt_finite = rt_finite && isfinite(R[i]);
 #pragma unroll
     for (int i = 0; i < 3; ++i) rt_finite = rt_finite && isfinite(T[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) T[i] = 0.f;
+    }
     // finite[i] = all six coordinates of correspondence i are finite.  With threshold^2 == +inf the reference's test
     // `distSq < inf` only fails for NaN/inf distances, i.e. for non-finite points or a non-finite (R, T).
     const uint32_t *F = finite ? finite + cl.valid_offset : nullptr;

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "json_min.h"
+#include "nccl_dl.h"
 #include "tod_internal.h"
 
 using tod::DeviceBuffer;
@@ -37,6 +38,18 @@ struct tod_matcher {
   const void *map_q_ptr = nullptr;
   int64_t map_q_rows = -1;
   const char *last_kernel = "none";
+  // opt-in post-filters (ratio test / duplicate removal): global row per match slot + the (frame, row) hash table
+  DeviceBuffer d_rows, d_hkeys, d_hvals;
+  // sharded handle with a communicator (tod_matcher_set_comm)
+  tod::ncclComm_t comm = nullptr;
+  int comm_mode = 0;                 // 0 none, 1 NCCL, 2 NCCL + peer-shared bounds
+  DeviceBuffer d_keys_local, d_keys_all;
+  uint32_t *d_bounds = nullptr;      // 2 x bounds_cap u32 (double-buffered by step parity), exported over CUDA IPC
+  size_t bounds_cap = 0;
+  uint32_t *peer_bounds[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_peers = 0;
+  unsigned step_parity = 0;
+  int32_t reserved_nq = 0;
 };
 
 namespace {
@@ -66,12 +79,26 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
     }
     TOD_CUDA(m->d_gthr.reserve(size_t(nq) * sizeof(uint32_t)));
     TOD_CUDA(m->d_popq.reserve(size_t(nq) * sizeof(uint32_t)));
-    TOD_CUDA(tod::launch_expand_queries(d_query, m->d_q8.ptr, nq, m->d_popq.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
+    uint32_t *gthr = m->d_gthr.as<uint32_t>();
+    tod::K1Peers peers{};
+    const bool shared = m->comm_mode == 2 && size_t(nq) <= m->bounds_cap;
+    if (shared) {
+      // Peer-shared bounds: this step prunes with buffer `parity`, which was reset one step ago (or at set_comm) and
+      // receives the peers' pushes while K1 runs; the other buffer is reset now for the next step.  The collective
+      // that ends every step orders the resets against the peers' pushes (multi-GPU).
+      gthr = m->d_bounds + size_t(m->step_parity) * m->bounds_cap;
+      TOD_CUDA(cudaMemsetAsync(m->d_bounds + size_t(m->step_parity ^ 1u) * m->bounds_cap, 0xFF,
+                               m->bounds_cap * sizeof(uint32_t), st));
+      for (int i = 0; i < m->n_peers; ++i) peers.gthr[i] = m->peer_bounds[i] + size_t(m->step_parity) * m->bounds_cap;
+      peers.n = m->n_peers;
+      m->step_parity ^= 1u;
+    }
+    TOD_CUDA(tod::launch_expand_queries(d_query, m->d_q8.ptr, nq, m->d_popq.as<uint32_t>(), shared ? nullptr : gthr,
                                         st));
     TOD_CUDA(cudaEventRecord(m->ev0, st));
     TOD_CUDA(tod::launch_k1_mma(plan, m->map_q, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
-                                m->p.radius, m->d_partial.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
-                                m->d_popq.as<uint32_t>(), st));
+                                m->p.radius, m->d_partial.as<uint32_t>(), gthr, m->d_popq.as<uint32_t>(),
+                                shared ? &peers : nullptr, st));
     TOD_CUDA(cudaEventRecord(m->ev1, st));
     m->ev_valid = true;
     m->last_kernel = "mma";
@@ -90,6 +117,72 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
   return TOD_OK;
 }
 
+#define TOD_NCCL(expr)                                                                                \
+  do {                                                                                                \
+    int _r = (expr);                                                                                  \
+    if (_r != tod::kNcclSuccess)                                                                      \
+      return fail(TOD_ERR_CUDA, "%s failed: %s", #expr, tod::nccl_api().GetErrorString(_r));          \
+  } while (0)
+
+// Merge (+ radius cut, decode, 3-D gather) and the opt-in post-filters, from n_src key lists per query.
+int finalize(tod_matcher *m, const uint32_t *d_keys, int n_src, int nq, tod_match *d_matches, int32_t *d_counts,
+             float *d_points3d, cudaStream_t st) {
+  const int k = m->p.k;
+  const bool ratio = m->p.ratio_enabled != 0 && k >= 2;
+  const bool dedupe = m->p.remove_duplicates != 0;
+  uint32_t *rows = nullptr;
+  size_t slots = 0;
+  if (dedupe) {
+    TOD_CUDA(m->d_rows.reserve(size_t(nq) * k * sizeof(uint32_t)));
+    slots = 1024;
+    while (slots < 2 * size_t(nq) * size_t(k)) slots <<= 1;
+    TOD_CUDA(m->d_hkeys.reserve(slots * 8));
+    TOD_CUDA(m->d_hvals.reserve(slots * 8));
+    rows = m->d_rows.as<uint32_t>();
+  }
+  TOD_CUDA(tod::launch_finalize_matches(d_keys, n_src, nq, k, m->p.radius, m->d_offsets.as<uint32_t>(),
+                                        int(m->ids.size()), m->d_pts.as<float>(), d_matches, d_counts, d_points3d, st,
+                                        ratio ? 1 : 0, m->p.ratio, rows));
+  if (dedupe)
+    TOD_CUDA(tod::launch_remove_duplicates(d_matches, d_counts, d_points3d, rows, nq, k, m->p.frame_keypoints,
+                                           m->d_hkeys.ptr, m->d_hvals.ptr, slots, st));
+  return TOD_OK;
+}
+
+// The whole DescriptorMatcher.process on device buffers, enqueued on `st`: K1 on this shard, then (sharded) top-k
+// reduction -> ncclAllGather of the packed keys -> merge; or (one shard) merge of the chunk lists directly.
+int run_process(tod_matcher *m, const void *d_query, int nq, tod_match *d_matches, int32_t *d_counts,
+                float *d_points3d, cudaStream_t st) {
+  const int k = m->p.k;
+  tod::K1Plan plan;
+  if (m->p.shard_count == 1) {
+    if (int rc = run_k1(m, d_query, nq, st, &plan)) return rc;
+    return finalize(m, m->d_partial.as<uint32_t>(), plan.n_sources, nq, d_matches, d_counts, d_points3d, st);
+  }
+  if (!m->comm)
+    return fail(TOD_ERR_STATE, "this handle holds shard %d of %d: call tod_matcher_set_comm first (or use the "
+                               "*_device stage calls with your own exchange)", m->p.shard_rank, m->p.shard_count);
+  const size_t nk = size_t(nq) * k;
+  TOD_CUDA(m->d_keys_local.reserve(nk * sizeof(uint32_t)));
+  TOD_CUDA(m->d_keys_all.reserve(nk * sizeof(uint32_t) * size_t(m->p.shard_count)));
+  if (int rc = run_k1(m, d_query, nq, st, &plan)) return rc;
+  TOD_CUDA(tod::launch_reduce_keys(m->d_partial.as<uint32_t>(), plan.n_sources, nq, k, m->d_keys_local.as<uint32_t>(), st));
+  TOD_NCCL(tod::nccl_api().AllGather(m->d_keys_local.ptr, m->d_keys_all.ptr, nk, tod::kNcclUint32, m->comm, st));
+  return finalize(m, m->d_keys_all.as<uint32_t>(), m->p.shard_count, nq, d_matches, d_counts, d_points3d, st);
+}
+
+void close_comm(tod_matcher *m) {
+  for (int i = 0; i < m->n_peers; ++i)
+    if (m->peer_bounds[i]) cudaIpcCloseMemHandle(m->peer_bounds[i]);
+  m->n_peers = 0;
+  if (m->d_bounds) cudaFree(m->d_bounds);
+  m->d_bounds = nullptr;
+  m->bounds_cap = 0;
+  if (m->comm) tod::nccl_api().CommDestroy(m->comm);
+  m->comm = nullptr;
+  m->comm_mode = 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -104,6 +197,11 @@ void tod_matcher_default_params(tod_matcher_params *p) {
   p->shard_rank = 0;
   p->shard_count = 1;
   p->kernel = TOD_KERNEL_AUTO;
+  p->ratio_enabled = 0;
+  p->ratio = 0.f;
+  p->remove_duplicates = 0;
+  p->frame_keypoints = 0;
+  p->share_bounds = 1;
 }
 
 int tod_matcher_params_from_json(const char *search_json_params, tod_matcher_params *p) {
@@ -118,6 +216,11 @@ int tod_matcher_params_from_json(const char *search_json_params, tod_matcher_par
     TOD_REQUIRE(v.at("radius").type == tod::json::Value::Number && r >= 0 && r < 4294967296.0, "bad radius");
     p->radius = static_cast<uint32_t>(r);
   }
+  // `ratio` is kept as the real number the .ork file holds, but the test itself is an opt-in extension: the
+  // reference's block is empty (:223-227).  "ratio_enabled" / "remove_duplicates" are this library's own keys.
+  if (v.has("ratio") && v.at("ratio").type == tod::json::Value::Number) p->ratio = float(v.at("ratio").num);
+  if (v.has("ratio_enabled")) p->ratio_enabled = tod::json::truthy(v.at("ratio_enabled")) ? 1 : 0;
+  if (v.has("remove_duplicates")) p->remove_duplicates = tod::json::truthy(v.at("remove_duplicates")) ? 1 : 0;
   const tod::json::Value &type = v.at("type");
   TOD_REQUIRE(type.type == tod::json::Value::String, "search type missing");
   if (type.str == "LSH") {
@@ -150,6 +253,8 @@ int tod_matcher_create(const tod_matcher_params *p, tod_matcher **out) {
   TOD_REQUIRE(p->shard_count >= 1 && p->shard_rank >= 0 && p->shard_rank < p->shard_count, "bad shard %d/%d",
               p->shard_rank, p->shard_count);
   TOD_REQUIRE(p->search_type == TOD_SEARCH_EXACT || p->search_type == TOD_SEARCH_LSH, "bad search_type");
+  TOD_REQUIRE(!p->ratio_enabled || (p->k >= 2 && p->ratio > 0.f), "the ratio test needs k >= 2 and ratio > 0");
+  TOD_REQUIRE(p->frame_keypoints >= 0, "negative frame_keypoints");
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev <= 0)
@@ -177,8 +282,11 @@ int tod_matcher_create(const tod_matcher_params *p, tod_matcher **out) {
 void tod_matcher_destroy(tod_matcher *m) {
   if (!m) return;
   cudaSetDevice(m->p.device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  close_comm(m);
   for (DeviceBuffer *b : {&m->d_db, &m->d_pts, &m->d_offsets, &m->d_query, &m->d_partial, &m->d_matches,
-                          &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8, &m->d_gthr, &m->d_popq})
+                          &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8, &m->d_gthr, &m->d_popq, &m->d_rows,
+                          &m->d_hkeys, &m->d_hvals, &m->d_keys_local, &m->d_keys_all})
     b->release();
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -273,8 +381,6 @@ int tod_matcher_knn(tod_matcher *m, const uint8_t *descriptors, int32_t nq, tod_
   TOD_REQUIRE(m && matches && counts, "null argument");
   TOD_REQUIRE(nq >= 0 && (nq == 0 || descriptors), "bad query buffer");
   if (!m->trained) return fail(TOD_ERR_STATE, "tod_matcher_knn called before tod_matcher_train");
-  if (m->p.shard_count != 1)
-    return fail(TOD_ERR_STATE, "tod_matcher_knn needs the whole DB on one GPU; use the *_device stages when sharded");
   if (nq == 0) return TOD_OK;
   if (int rc = use_device(m)) return rc;
   const int k = m->p.k;
@@ -284,17 +390,153 @@ int tod_matcher_knn(tod_matcher *m, const uint8_t *descriptors, int32_t nq, tod_
   TOD_CUDA(m->d_counts.reserve(size_t(nq) * sizeof(int32_t)));
   TOD_CUDA(m->d_pts3d.reserve(nk * 3 * sizeof(float)));
   TOD_CUDA(cudaMemcpyAsync(m->d_query.ptr, descriptors, size_t(nq) * 32, cudaMemcpyHostToDevice, m->stream));
-  tod::K1Plan plan;
-  if (int rc = run_k1(m, m->d_query.ptr, nq, m->stream, &plan)) return rc;
-  TOD_CUDA(tod::launch_finalize_matches(m->d_partial.as<uint32_t>(), plan.n_sources, nq, k, m->p.radius,
-                                        m->d_offsets.as<uint32_t>(), int(m->ids.size()), m->d_pts.as<float>(),
-                                        m->d_matches.as<tod_match>(), m->d_counts.as<int32_t>(),
-                                        points3d ? m->d_pts3d.as<float>() : nullptr, m->stream));
+  if (int rc = run_process(m, m->d_query.ptr, nq, m->d_matches.as<tod_match>(), m->d_counts.as<int32_t>(),
+                           points3d ? m->d_pts3d.as<float>() : nullptr, m->stream))
+    return rc;
   TOD_CUDA(cudaMemcpyAsync(matches, m->d_matches.ptr, nk * sizeof(tod_match), cudaMemcpyDeviceToHost, m->stream));
   TOD_CUDA(cudaMemcpyAsync(counts, m->d_counts.ptr, size_t(nq) * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
   if (points3d)
     TOD_CUDA(cudaMemcpyAsync(points3d, m->d_pts3d.ptr, nk * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
   TOD_CUDA(cudaStreamSynchronize(m->stream));
+  return TOD_OK;
+}
+
+int tod_matcher_knn_device(tod_matcher *m, const void *d_descriptors, int32_t nq, tod_match *d_matches,
+                           int32_t *d_counts, float *d_points3d, void *stream) {
+  TOD_REQUIRE(m && d_matches && d_counts, "null argument");
+  TOD_REQUIRE(nq >= 0 && (nq == 0 || d_descriptors), "bad query buffer");
+  if (!m->trained) return fail(TOD_ERR_STATE, "tod_matcher_knn_device called before tod_matcher_train");
+  if (nq == 0) return TOD_OK;
+  if (int rc = use_device(m)) return rc;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : m->stream;
+  return run_process(m, d_descriptors, nq, d_matches, d_counts, d_points3d, st);
+}
+
+int tod_matcher_reserve(tod_matcher *m, int32_t max_nq) {
+  TOD_REQUIRE(m && max_nq >= 0, "bad argument");
+  if (!m->trained) return fail(TOD_ERR_STATE, "tod_matcher_reserve called before tod_matcher_train");
+  if (int rc = use_device(m)) return rc;
+  const size_t nq = size_t(std::max(max_nq, 1)), k = size_t(m->p.k), nk = nq * k;
+  // the candidate buffer depends on the chunk plan, which depends on nq: take the largest over every query-tile count
+  size_t partial = 0;
+  const int step = 256;
+  for (int64_t q = step; q < int64_t(nq) + step; q += step) {
+    const int qq = int(std::min<int64_t>(q, int64_t(nq)));
+    const tod::K1Plan pl = use_mma(m) ? tod::k1_mma_plan(qq, m->shard_rows, m->sm_count)
+                                      : tod::k1_popc_plan(qq, m->shard_rows, m->sm_count);
+    partial = std::max(partial, size_t(pl.n_sources) * size_t(qq) * k * sizeof(uint32_t));
+  }
+  TOD_CUDA(m->d_partial.reserve(partial));
+  TOD_CUDA(m->d_query.reserve(nq * 32));
+  TOD_CUDA(m->d_matches.reserve(nk * sizeof(tod_match)));
+  TOD_CUDA(m->d_counts.reserve(nq * sizeof(int32_t)));
+  TOD_CUDA(m->d_pts3d.reserve(nk * 3 * sizeof(float)));
+  if (use_mma(m)) {
+    TOD_CUDA(m->d_q8.reserve(nq * 256));
+    TOD_CUDA(m->d_gthr.reserve(nq * sizeof(uint32_t)));
+    TOD_CUDA(m->d_popq.reserve(nq * sizeof(uint32_t)));
+  }
+  if (m->p.shard_count > 1) {
+    TOD_CUDA(m->d_keys_local.reserve(nk * sizeof(uint32_t)));
+    TOD_CUDA(m->d_keys_all.reserve(nk * sizeof(uint32_t) * size_t(m->p.shard_count)));
+  }
+  if (m->p.remove_duplicates) {
+    size_t slots = 1024;
+    while (slots < 2 * nk) slots <<= 1;
+    TOD_CUDA(m->d_rows.reserve(nk * sizeof(uint32_t)));
+    TOD_CUDA(m->d_hkeys.reserve(slots * 8));
+    TOD_CUDA(m->d_hvals.reserve(slots * 8));
+  }
+  m->reserved_nq = std::max(m->reserved_nq, max_nq);
+  return TOD_OK;
+}
+
+int tod_comm_unique_id(void *id_out) {
+  TOD_REQUIRE(id_out, "null argument");
+  const tod::NcclApi &api = tod::nccl_api();
+  if (!api.ok) return fail(TOD_ERR_STATE, "libnccl.so.2 could not be loaded (%s)", dlerror() ? dlerror() : "missing symbols");
+  tod::ncclUniqueId id;
+  TOD_NCCL(api.GetUniqueId(&id));
+  static_assert(sizeof(id) == TOD_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  std::memcpy(id_out, &id, sizeof(id));
+  return TOD_OK;
+}
+
+int32_t tod_matcher_comm_mode(const tod_matcher *m) { return m ? m->comm_mode : 0; }
+
+int tod_matcher_set_comm(tod_matcher *m, const void *unique_id) {
+  TOD_REQUIRE(m && unique_id, "null argument");
+  const tod::NcclApi &api = tod::nccl_api();
+  if (!api.ok) return fail(TOD_ERR_STATE, "libnccl.so.2 could not be loaded");
+  if (int rc = use_device(m)) return rc;
+  TOD_CUDA(cudaStreamSynchronize(m->stream));
+  close_comm(m);
+  tod::ncclUniqueId id;
+  std::memcpy(&id, unique_id, sizeof(id));
+  const int world = m->p.shard_count, rank = m->p.shard_rank;
+  TOD_NCCL(api.CommInitRank(&m->comm, world, id, rank));
+  m->comm_mode = 1;
+  if (!m->p.share_bounds || world < 2 || world > 8) return TOD_OK;
+
+  // ---- peer-shared bounds: export this rank's double-buffered bound array, map everybody else's -------------------
+  struct Msg {
+    cudaIpcMemHandle_t handle;
+    uint64_t cap;
+    int32_t ok;
+    int32_t pad;
+  };
+  Msg mine{};
+  const size_t cap = size_t(std::max<int32_t>(m->reserved_nq, 1 << 18));
+  bool ok = cudaMalloc(reinterpret_cast<void **>(&m->d_bounds), 2 * cap * sizeof(uint32_t)) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(m->d_bounds, 0xFF, 2 * cap * sizeof(uint32_t), m->stream) == cudaSuccess;
+  if (ok) ok = cudaStreamSynchronize(m->stream) == cudaSuccess;
+  if (ok) ok = cudaIpcGetMemHandle(&mine.handle, m->d_bounds) == cudaSuccess;
+  cudaGetLastError();
+  mine.cap = cap;
+  mine.ok = ok ? 1 : 0;
+  DeviceBuffer d_mine, d_all;
+  TOD_CUDA(d_mine.reserve(sizeof(Msg)));
+  TOD_CUDA(d_all.reserve(sizeof(Msg) * size_t(world)));
+  std::vector<Msg> all;
+  all.resize(static_cast<size_t>(world));
+  TOD_CUDA(cudaMemcpyAsync(d_mine.ptr, &mine, sizeof(Msg), cudaMemcpyHostToDevice, m->stream));
+  TOD_NCCL(api.AllGather(d_mine.ptr, d_all.ptr, sizeof(Msg), tod::kNcclUint8, m->comm, m->stream));
+  TOD_CUDA(cudaMemcpyAsync(all.data(), d_all.ptr, sizeof(Msg) * size_t(world), cudaMemcpyDeviceToHost, m->stream));
+  TOD_CUDA(cudaStreamSynchronize(m->stream));
+  int32_t good = 1;
+  for (const Msg &x : all) good = good && x.ok && x.cap == cap;
+  int n = 0;
+  if (good) {
+    for (int r = 0; r < world && good; ++r) {
+      if (r == rank) continue;
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[size_t(r)].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        good = 0;
+        break;
+      }
+      m->peer_bounds[n++] = static_cast<uint32_t *>(ptr);
+    }
+  }
+  m->n_peers = n;
+  // everybody must agree: one rank that cannot map its peers turns the feature off for all (results never depend on it)
+  int32_t *d_flag = d_mine.as<int32_t>();
+  TOD_CUDA(cudaMemcpyAsync(d_flag, &good, sizeof(good), cudaMemcpyHostToDevice, m->stream));
+  TOD_NCCL(api.AllReduce(d_flag, d_flag, 1, tod::kNcclInt32, tod::kNcclMin, m->comm, m->stream));
+  TOD_CUDA(cudaMemcpyAsync(&good, d_flag, sizeof(good), cudaMemcpyDeviceToHost, m->stream));
+  TOD_CUDA(cudaStreamSynchronize(m->stream));
+  d_mine.release();
+  d_all.release();
+  if (good) {
+    m->bounds_cap = cap;
+    m->step_parity = 0;
+    m->comm_mode = 2;
+  } else {
+    for (int i = 0; i < m->n_peers; ++i) cudaIpcCloseMemHandle(m->peer_bounds[i]);
+    m->n_peers = 0;
+    cudaFree(m->d_bounds);
+    m->d_bounds = nullptr;
+  }
   return TOD_OK;
 }
 
@@ -320,10 +562,7 @@ int tod_matcher_merge_device(tod_matcher *m, const uint32_t *d_keys_all, int32_t
   if (nq == 0) return TOD_OK;
   if (int rc = use_device(m)) return rc;
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : m->stream;
-  TOD_CUDA(tod::launch_finalize_matches(d_keys_all, n_src, nq, m->p.k, m->p.radius, m->d_offsets.as<uint32_t>(),
-                                        int(m->ids.size()), m->d_pts.as<float>(), d_matches, d_counts, d_points3d,
-                                        st));
-  return TOD_OK;
+  return finalize(m, d_keys_all, n_src, nq, d_matches, d_counts, d_points3d, st);
 }
 
 float tod_matcher_last_k1_ms(const tod_matcher *m) {

@@ -145,10 +145,15 @@ int tod_snapshot_open(const char *path, tod_snapshot **out) {
   if (base == MAP_FAILED) return tod::fail(TOD_ERR_INVALID, "mmap of %s failed", path);
   const Header *h = static_cast<const Header *>(base);
   const uint64_t n = h->n_objects, rows = h->total_rows, size = uint64_t(st.st_size);
+  // Every bound is checked by subtraction against the file size (no u64 sum can wrap): the offsets are ordered,
+  // aligned, inside the file, and each region is large enough for the counts the header claims.
   bool ok = std::memcmp(h->magic, kMagic, 8) == 0 && h->version == kVersion && h->file_bytes == size &&
-            h->off_table >= sizeof(Header) && h->off_table + n * sizeof(Entry) <= h->off_desc &&
-            h->off_desc + rows * 32 <= h->off_pts && h->off_pts + rows * 12 <= h->off_ids && h->off_ids <= size &&
-            int64_t(rows) <= tod::kMaxGlobalRows;
+            int64_t(rows) <= tod::kMaxGlobalRows && n <= size / sizeof(Entry);
+  ok = ok && h->off_table >= sizeof(Header) && h->off_table <= size && h->off_table % 8 == 0 &&
+       h->off_desc <= size && h->off_pts <= size && h->off_ids <= size && h->off_table <= h->off_desc &&
+       h->off_desc <= h->off_pts && h->off_pts <= h->off_ids && h->off_desc % 4 == 0 && h->off_pts % 4 == 0;
+  ok = ok && n <= (h->off_desc - h->off_table) / sizeof(Entry) && rows <= (h->off_pts - h->off_desc) / 32 &&
+       rows <= (h->off_ids - h->off_pts) / 12;
   tod_snapshot *s = new tod_snapshot();
   s->base = base;
   s->bytes = size_t(st.st_size);

@@ -110,6 +110,7 @@ cudaError_t launch_k1_popc(const K1Plan &plan, const void *d_query, int nq, cons
 // memory).  launch_expand_queries also writes the queries' popcounts and resets their shared bounds to 511.
 K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count);
 cudaError_t launch_expand_db(const void *d_bits, void *d_int8, int64_t rows, cudaStream_t stream);
+// d_gthr may be null (bounds reset elsewhere: the peer-shared arrays are reset by a memset one step ahead).
 cudaError_t launch_expand_queries(const void *d_bits, void *d_int8, int64_t rows, uint32_t *d_popq, uint32_t *d_gthr,
                                   cudaStream_t stream);
 bool make_desc_tensor_map(void *map_out, const void *d_int8, int64_t rows, int box_rows);
@@ -118,9 +119,14 @@ int k1_mma_db_box_rows();
 size_t tensor_map_bytes();
 // d_gthr: nq u32 shared per-query bounds, must hold 511 (no bound) before the launch; d_popq: nq query popcounts
 // (both written by launch_expand_queries).
+// peers (may be null): the other shards' bound arrays, mapped over NVLink (CUDA IPC); K1 pushes improved bounds there.
+struct K1Peers {
+  uint32_t *gthr[7];
+  int n;
+};
 cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
-                          const uint32_t *d_popq, cudaStream_t stream);
+                          const uint32_t *d_popq, const K1Peers *peers, cudaStream_t stream);
 
 // Reduce n_src x nq x k key lists to nq x k keys (ascending).
 cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t *d_out,
@@ -129,7 +135,13 @@ cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k,
 cudaError_t launch_finalize_matches(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t radius,
                                     const uint32_t *d_obj_offsets, int n_objects, const float *d_points,
                                     tod_match *d_matches, int32_t *d_counts, float *d_points3d,
-                                    cudaStream_t stream);
+                                    cudaStream_t stream, int ratio_enabled = 0, float ratio = 0.f,
+                                    uint32_t *d_rows_out = nullptr);
+// Duplicate-match removal inside each frame (DescriptorMatcher.cpp:229 TODO): d_rows = the global DB row of every
+// match slot (written by launch_finalize_matches); the hash tables hold table_slots (a power of two) u64 each.
+cudaError_t launch_remove_duplicates(tod_match *d_matches, int32_t *d_counts, float *d_points3d,
+                                     const uint32_t *d_rows, int nq, int k, int frame_keypoints, void *d_hkeys,
+                                     void *d_hvals, size_t table_slots, cudaStream_t stream);
 
 // K2: one launch over all clusters. Device pointers.
 cudaError_t launch_fill_adjacency(int n_clusters, const int32_t *d_offsets, const int64_t *d_matrix_offsets,
