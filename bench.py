@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--no-pipeline", action="store_true", help="skip the C4 (matcher + guess generator) leg")
     ap.add_argument("--pipeline-frames", type=int, default=64)
     ap.add_argument("--c5-objects", type=int, default=100, help="objects in the C5 RANSAC-stress leg (0 = skip)")
-    ap.add_argument("--no-share-bounds", action="store_true", help="N > 1: keep K1's bounds local to each GPU")
+    ap.add_argument("--trace", action="store_true", help="progress lines on stderr (debugging a multi-rank run)")
     return ap.parse_args()
 
 
@@ -292,7 +292,7 @@ def hbm_roofline(kernel, alg_bytes, ms, hbm_peak, hbm_src, extra=None):
     return r
 
 
-def pipeline_leg(args, descs, points, m, hbm_peak, hbm_src):
+def pipeline_leg(args, descs, points, hbm_peak, hbm_src):
     """BASELINE config C4 through the reference-facing calls with HOST buffers: a batch of 64 synthetic 1280x960
     RGB-D frames x 4096 keypoints, DescriptorMatcher.process (k = 5, radius 35 as in conf/detection.ork) then the
     batched GuessGenerator.process — the whole north_star path.  Returns the `e2e_pipeline` and `stages` objects."""
@@ -357,7 +357,7 @@ def pipeline_leg(args, descs, points, m, hbm_peak, hbm_src):
                                  {"clusters": stats["n_clusters"], "correspondences": stats["n_correspondences"]}),
               "k3": hbm_roofline("k3_score_kernel", stats["k3_bytes"], stats["k3_ms"], hbm_peak, hbm_src,
                                  {"hypotheses": stats["n_hypotheses"], "rounds": stats["n_rounds"]}),
-              "guess_host_ms": stats["host_ms"], "gate_calls": stats["gate_calls"]}
+              "guess_host_ms": stats["host_ms"], "gate_calls": stats["gate_calls"], "gate_shape": stats["gate_shape"]}
     # the reference's CPU pipeline on a bounded sample of the same batch: exact matcher on one whole frame (all host
     # cores) + the reference's own geometry code (oracle/_ref, single-threaded like the reference) on that frame
     cpu = None
@@ -413,7 +413,8 @@ def c5_leg(args, hbm_peak, hbm_src):
                               {"clusters": st["n_clusters"], "correspondences": st["n_correspondences"]}),
            "k3": hbm_roofline("k3_score_kernel", st["k3_bytes"], st["k3_ms"], hbm_peak, hbm_src,
                               {"hypotheses": st["n_hypotheses"], "rounds": st["n_rounds"]}),
-           "guess_host_ms": st["host_ms"], "gate_calls": st["gate_calls"]}
+           "guess_host_ms": st["host_ms"], "gate_calls": st["gate_calls"], "gate_shape": st["gate_shape"],
+           "gate_thread_ms": st["gate_thread_ms"]}
     gg.close()
     return out
 
@@ -429,16 +430,25 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200; there is no CPU fallback")
+
+    def trace(msg):
+        if args.trace:
+            print("[bench rank %d %.1fs] %s" % (rank, time.perf_counter() - t_begin, msg), file=sys.stderr, flush=True)
+    t_begin = time.perf_counter()
+    if args.trace:
+        import faulthandler
+        faulthandler.dump_traceback_later(90, exit=False, file=sys.stderr)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)   # plumbing only: id broadcast, barriers, max over ranks
     lib = capi.load()
+    trace("process group up")
 
     descs, points, queries = workload(args)
     kernel = {"auto": capi.TOD_KERNEL_AUTO, "popc": capi.TOD_KERNEL_POPC, "mma": capi.TOD_KERNEL_MMA}[args.kernel]
     m = DescriptorMatcher(k=args.k, radius=args.radius, device=local_rank, shard_rank=rank, shard_count=world,
-                          kernel=kernel, share_bounds=not args.no_share_bounds)
+                          kernel=kernel)
     for i, (d, p) in enumerate(zip(descs, points)):
         m.add_object("object_%03d" % i, d, p)
     m.train()
@@ -450,7 +460,9 @@ def run_ours(args):
         # rank 0's library, handed over by the host-side plumbing)
         box = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
+        trace("unique id received")
         m.set_comm(box[0])
+        trace("communicator up, mode %d" % m.comm_mode)
 
     stream = torch.cuda.Stream(device=dev)     # explicit, non-legacy: K1 / NCCL / merge are all ordered on it
     torch.cuda.set_stream(stream)
@@ -473,7 +485,9 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    trace("warm-up enqueued")
     barrier()
+    trace("warm-up done")
 
     # ---- device-resident timing (value) ----
     gpu_id = str(local_rank)
@@ -486,7 +500,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    k1_ms = []
+    k1_ms, xch_ms = [], []
     barrier()
     wall0 = time.perf_counter()
     for s in range(args.steps):
@@ -495,6 +509,8 @@ def run_ours(args):
         step()
         ev[s][1].record(stream)
         k1_ms.append(m.last_k1_ms)   # CUDA events recorded by the library around the K1 launch, on the launch stream
+        if world > 1:
+            xch_ms.append(m.last_exchange_ms)   # ... and around the ncclAllGather
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
@@ -506,6 +522,7 @@ def run_ours(args):
     dev_ms = float(t.item())
     frames_total = args.steps * args.frames
     value = frames_total / (dev_ms * 1e-3)
+    trace("device-timed region done: %.1f frames/s" % value)
 
     # ---- end-to-end timing through host (pinned) buffers ----
     q_host = torch.from_numpy(queries).pin_memory()
@@ -552,6 +569,7 @@ def run_ours(args):
                 m.process(q_host.numpy(), out=out)      # tod_matcher_knn: H2D + K1 + merge + D2H, synchronous
 
     e2e_run(3)
+    trace("e2e warm-up enqueued")
     barrier()
     t0 = time.perf_counter()
     e2e_run(args.steps)
@@ -562,6 +580,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = frames_total / e2e_s
+    trace("e2e done: %.1f frames/s" % e2e_value)
     h2d = nqt * 32
     d2h = nqt * k * 16 + nqt * 4 + nqt * k * 12
     comm_mode = m.comm_mode
@@ -572,6 +591,15 @@ def run_ours(args):
         m.process(q_host.numpy(), out=out)
         assert (m_np == ref_m).all() and (c_host.numpy() == ref_c).all() and (p_host.numpy() == ref_p).all()
 
+    shard_rows, kern = m.shard_rows, m.last_kernel
+    per_rank = None
+    if world > 1:   # per-rank device times of K1 and of the exchange (the all-gather also waits for the slowest rank)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"rank": rank, "k1_ms": float(np.mean(k1_ms)),
+                                          "exchange_ms": float(np.mean(xch_ms)), "shard_rows": shard_rows})
+    barrier()
+    m.close()                                            # every rank tears its handle (and communicator) down together
+    trace("handle closed")
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -586,14 +614,12 @@ def run_ours(args):
     assert (c_host.numpy() == k).all() or args.radius > 0
 
     # ---- roofline of the dominant kernel (K1) ----
-    shard_rows = m.shard_rows
     cmp_per_launch = float(nqt) * shard_rows
     k1_avg_ms = float(np.mean(k1_ms))
     achieved_gcmp = cmp_per_launch / (k1_avg_ms * 1e-3) / 1e9
     peaks = load_int_peaks()
     hbm_peak, hbm_src = load_measured_peaks()
     alg_bytes = 32.0 * shard_rows + 32.0 * nqt + nqt * k * 4.0
-    kern = m.last_kernel
     if kern == "mma":
         # tensor form: 256 int8 MACs = 512 tensor ops per compare.  peak = the MEASURED dense int8 tcgen05 rate of this
         # pool's B200 (bare MMA loop, tools/mma_peak -> profiles/int_peaks.json; MEASURED_PEAKS.json only holds bf16),
@@ -659,14 +685,12 @@ def run_ours(args):
             "collective": (None if world == 1 else
                            {"where": "inside libtod_b200.so (ncclAllGather of packed top-k keys on the handle's "
                                      "stream); no torch.distributed collective in the timed region",
-                            "comm_mode": comm_mode,
-                            "peer_shared_bounds": comm_mode == 2}),
+                            "comm_mode": comm_mode, "per_rank": per_rank}),
             "gpu_launches": int(launches), "wall_s_timed_region": wall, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "cpu_baseline_lsh": lsh}
-    m.close()
     if world == 1 and not args.no_pipeline:
         torch.cuda.synchronize()
-        e2e_pipe, stages = pipeline_leg(args, descs, points, m, hbm_peak, hbm_src)
+        e2e_pipe, stages = pipeline_leg(args, descs, points, hbm_peak, hbm_src)
         line["e2e_pipeline"] = e2e_pipe
         line["stages"] = stages
         if args.c5_objects > 0:

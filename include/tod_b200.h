@@ -98,12 +98,10 @@ typedef struct tod_matcher_params {
                                  smallest (distance, queryIdx) survives; lists are compacted, order kept. */
   int32_t frame_keypoints;    /* scope of remove_duplicates in a batched call: queries [f*n, (f+1)*n) are frame f;
                                  0 = the whole call is one frame */
-  int32_t share_bounds;       /* sharded handles with a communicator: 1 (default) = K1's per-query pruning bounds are
-                                 pushed to the peer GPUs over NVLink while the kernel runs (results unchanged) */
 } tod_matcher_params;
 
 void tod_matcher_default_params(tod_matcher_params *p); /* k=5, radius=0, exact, device 0, 1 shard, auto, no ratio
-                                                           test, no duplicate removal, share_bounds=1 */
+                                                           test, no duplicate removal */
 
 /* configure(): parses the reference's "search_json_params" string — fields type, radius, ratio, n_tables, key_size,
  * multi_probe_level (DescriptorMatcher.cpp:159-181) — into *p (k stays 5, as hard-coded in the reference).
@@ -154,15 +152,16 @@ int tod_matcher_reserve(tod_matcher *m, int32_t max_nq);
 /* ---- communicator of a sharded matcher (one process per GPU) ----------------------------------------------------
  * tod_comm_unique_id: rank 0 creates a 128-byte NCCL unique id (ncclGetUniqueId) and hands it to the other ranks by
  * any host-side means (MPI, torch.distributed broadcast, a file).  tod_matcher_set_comm: collective over all
- * shard_count ranks — ncclCommInitRank on the handle's device with rank = shard_rank, world = shard_count; when
- * share_bounds is set it also exchanges CUDA IPC handles of the per-query bound buffers so that K1 can push its
- * pruning bounds straight into the peers' HBM over NVLink (falls back silently to local bounds if peer mapping is
- * not possible).  libnccl.so.2 is loaded with dlopen at this point; the library has no link-time NCCL dependency. */
+ * shard_count ranks — ncclCommInitRank on the handle's device with rank = shard_rank, world = shard_count.
+ * libnccl.so.2 is loaded with dlopen at this point; the library has no link-time NCCL dependency.  Destroying the
+ * handle tears the communicator down locally (ncclCommAbort after the stream has drained): no rank waits for another. */
 #define TOD_COMM_ID_BYTES 128
 int tod_comm_unique_id(void *id_out);
 int tod_matcher_set_comm(tod_matcher *m, const void *unique_id);
-/* 0 = no communicator, 1 = NCCL only, 2 = NCCL + peer-shared bounds */
+/* 0 = no communicator, 1 = NCCL communicator attached */
 int32_t tod_matcher_comm_mode(const tod_matcher *m);
+/* Device time (ms, CUDA events on the launch stream) of the ncclAllGather of the last sharded call; < 0 if none. */
+float tod_matcher_last_exchange_ms(const tod_matcher *m);
 
 /* Sharding of the concatenated DB over `shard_count` GPUs (host-only, no device needed): rank r holds the contiguous
  * global rows [*begin, *begin + *rows), ceil(total/shard_count) rows each except the last ranks.  tod_matcher_train

@@ -41,8 +41,8 @@ def test_host_only_entry_points(lib):
     p = capi.MatcherParams()
     lib.tod_matcher_default_params(ctypes.byref(p))
     assert (p.k, p.radius, p.shard_count) == (5, 0, 1)
-    assert (p.ratio_enabled, p.remove_duplicates, p.frame_keypoints, p.share_bounds) == (0, 0, 0, 1)
-    assert ctypes.sizeof(capi.MatcherParams) == 48
+    assert (p.ratio_enabled, p.remove_duplicates, p.frame_keypoints) == (0, 0, 0)
+    assert ctypes.sizeof(capi.MatcherParams) == 44
     # conf/detection.ork `search:` subtree as ORK core would serialise it
     js = b'{"type": "LSH", "module": "ecto_opencv.features2d", "key_size": 16, "multi_probe_level": 1, ' \
          b'"n_tables": 10, "radius": 35, "ratio": 0.8}'

@@ -1,8 +1,7 @@
 """GPU, >= 2 devices: the sharded matcher with the exchange INSIDE the library — one process per GPU, each handle holds
 one row range of the DB and an NCCL communicator (tod_matcher_set_comm); tod_matcher_knn / tod_matcher_knn_device then
 run K1 -> top-k reduction -> ncclAllGather -> merge on the handle's stream and every rank must return the complete,
-bit-exact result (oracle = exact Hamming k-NN over the whole DB), step after step with changing queries (the
-peer-shared bound buffers alternate by step parity), with and without peer sharing.
+bit-exact result (oracle = exact Hamming k-NN over the whole DB), step after step with changing query sets.
 
 Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_nccl_gpu.py -m gpu`."""
 import os
@@ -40,14 +39,14 @@ def _workload():
     return descs, points, steps
 
 
-def _rank_main(rank, world, uid, k, radius, share, out_dir):
+def _rank_main(rank, world, uid, k, radius, out_dir):
     sys.path.insert(0, ROOT)
     import torch
     from oracle import hamming_knn as hk
     from tod_b200 import DescriptorMatcher, capi
     torch.cuda.set_device(rank)
     descs, points, steps = _workload()
-    m = DescriptorMatcher(k=k, radius=radius, device=rank, shard_rank=rank, shard_count=world, share_bounds=share)
+    m = DescriptorMatcher(k=k, radius=radius, device=rank, shard_rank=rank, shard_count=world)
     for i, (d, p) in enumerate(zip(descs, points)):
         m.add_object("o%d" % i, d, p)
     m.train()
@@ -60,10 +59,10 @@ def _rank_main(rank, world, uid, k, radius, share, out_dir):
         assert e.code == capi.TOD_ERR_STATE
     m.set_comm(uid)
     mode = m.comm_mode
-    assert mode in (1, 2) and (share or mode == 1)
+    assert mode == 1
     dev = torch.device("cuda", rank)
     ok = True
-    for rep in range(2):                                                # twice through: parity flips every step
+    for rep in range(2):
         for q in steps:
             out = m.process(q)                                         # host buffers: H2D + K1 + all-gather + merge + D2H
             em, ec = hk.knn_c(q, descs, k, radius)
@@ -86,19 +85,21 @@ def _rank_main(rank, world, uid, k, radius, share, out_dir):
             same = same and (cd.cpu().numpy() == out["counts"]).all()
             ok = ok and bool(same)
     np.save(os.path.join(out_dir, "ok_%d.npy" % rank), np.array([int(ok), mode, m.shard_rows]))
+    if rank == 0:
+        import time
+        time.sleep(2.0)            # ranks tear their handles down at different times: nobody may wait for anybody
     m.close()
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("k,radius,share", [(2, 0, True), (5, 35, True), (5, 0, False)])
-def test_sharded_matcher_with_in_library_nccl(tmp_path, k, radius, share):
+@pytest.mark.parametrize("k,radius", [(2, 0), (5, 35)])
+def test_sharded_matcher_with_in_library_nccl(tmp_path, k, radius):
     import torch.multiprocessing as mp
     from tod_b200 import comm_unique_id
     world = min(_n_gpus(), 4)
     uid = comm_unique_id()
-    mp.spawn(_rank_main, args=(world, uid, k, radius, share, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_rank_main, args=(world, uid, k, radius, str(tmp_path)), nprocs=world, join=True)
     res = [np.load(os.path.join(str(tmp_path), "ok_%d.npy" % r)) for r in range(world)]
     assert all(int(r[0]) == 1 for r in res), res
-    assert len(set(int(r[1]) for r in res)) == 1                        # every rank agrees on the communicator mode
     descs, _, _ = _workload()
     assert sum(int(r[2]) for r in res) == sum(d.shape[0] for d in descs)

@@ -26,8 +26,7 @@ class MatcherParams(ctypes.Structure):
     _fields_ = [("k", ctypes.c_int32), ("radius", ctypes.c_uint32), ("search_type", ctypes.c_int32),
                 ("device", ctypes.c_int32), ("shard_rank", ctypes.c_int32), ("shard_count", ctypes.c_int32),
                 ("kernel", ctypes.c_int32), ("ratio_enabled", ctypes.c_int32), ("ratio", ctypes.c_float),
-                ("remove_duplicates", ctypes.c_int32), ("frame_keypoints", ctypes.c_int32),
-                ("share_bounds", ctypes.c_int32)]
+                ("remove_duplicates", ctypes.c_int32), ("frame_keypoints", ctypes.c_int32)]
 
 
 class GuessParams(ctypes.Structure):
@@ -70,6 +69,7 @@ SIGNATURES = [
     ("tod_comm_unique_id", ctypes.c_int, [_P]),
     ("tod_matcher_set_comm", ctypes.c_int, [_P, _P]),
     ("tod_matcher_comm_mode", _I32, [_P]),
+    ("tod_matcher_last_exchange_ms", _F, [_P]),
     ("tod_shard_range", ctypes.c_int, [_I64, _I32, _I32, ctypes.POINTER(_I64), ctypes.POINTER(_I64)]),
     ("tod_pack_key", _U32, [_U32, _U32]),
     ("tod_matcher_knn_keys_device", ctypes.c_int, [_P, _P, _I32, _P, _P]),

@@ -17,8 +17,7 @@ class DescriptorMatcher:
     """
 
     def __init__(self, search_json_params=None, k=None, radius=None, device=0, shard_rank=0, shard_count=1,
-                 kernel=capi.TOD_KERNEL_AUTO, ratio=None, remove_duplicates=None, frame_keypoints=0,
-                 share_bounds=True):
+                 kernel=capi.TOD_KERNEL_AUTO, ratio=None, remove_duplicates=None, frame_keypoints=0):
         lib = capi.load()
         p = capi.MatcherParams()
         lib.tod_matcher_default_params(ctypes.byref(p))
@@ -36,7 +35,6 @@ class DescriptorMatcher:
         if remove_duplicates is not None:
             p.remove_duplicates = 1 if remove_duplicates else 0
         p.frame_keypoints = int(frame_keypoints)
-        p.share_bounds = 1 if share_bounds else 0
         self.params = p
         self._h = ctypes.c_void_p()
         capi.check(lib.tod_matcher_create(ctypes.byref(p), ctypes.byref(self._h)))
@@ -124,7 +122,7 @@ class DescriptorMatcher:
         capi.check(self._lib.tod_matcher_reserve(self._h, int(max_nq)))
 
     def set_comm(self, unique_id):
-        """Collective over the shard_count ranks: NCCL communicator (+ peer-shared K1 bounds over NVLink)."""
+        """Collective over the shard_count ranks: attaches an NCCL communicator to the handle."""
         capi.preload_nccl()
         buf = ctypes.create_string_buffer(bytes(unique_id), capi.TOD_COMM_ID_BYTES)
         capi.check(self._lib.tod_matcher_set_comm(self._h, buf))
@@ -154,6 +152,10 @@ class DescriptorMatcher:
     @property
     def last_k1_ms(self):
         return float(self._lib.tod_matcher_last_k1_ms(self._h))
+
+    @property
+    def last_exchange_ms(self):
+        return float(self._lib.tod_matcher_last_exchange_ms(self._h))
 
     @property
     def last_kernel(self):

@@ -54,8 +54,8 @@ struct Cluster {
   std::vector<float> q, t, px;     // n x 3, n x 3, n x 2
   std::vector<uint32_t> qidx;      // query_indices_ (non-decreasing)
   std::vector<uint32_t> valid;     // W words: valid_indices_ as a mask
-  std::vector<uint16_t> sdeg;      // per correspondence: popc(S[v] & valid) for the current round (clique gate :209-213)
-  std::vector<uint32_t> core7;     // W words: 7-core of the valid sample graph this round — every 8-clique lives in it
+  std::vector<uint32_t> deg7;      // W words: valid vertices with >= 7 valid sample-neighbours this round (gate :209-213);
+                                   // computed by sample_degree_mask_kernel on the GPU, or by host_degree_mask
   std::vector<uint32_t> finite;    // W words: all six coordinates finite
   int n_valid = 0;
   int64_t point_offset = 0, matrix_offset = 0, valid_offset = 0;
@@ -367,20 +367,9 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
   const int W = c.W;
   const Clock::time_point t0 = Clock::now();
   g.filtered.clear();
-  for (uint32_t v : inliers)  // :209-213 — sample-degree inside the current valid set (precomputed per round)
-    if (size_t(c.sdeg[v]) >= minimal) g.filtered.push_back(v);
+  for (uint32_t v : inliers)  // :209-213 — sample-degree inside the current valid set (one mask per round)
+    if ((c.deg7[v >> 5] >> (v & 31)) & 1u) g.filtered.push_back(v);
   if (g.filtered.size() <= minimal) return false;
-  // Exact early "no": a clique of 8 vertices has minimum degree 7, so it lies inside the 7-core of the round's valid
-  // sample graph; with fewer than 8 candidates there the search below cannot return one and the gate fails (:260-265).
-  {
-    size_t in_core = 0;
-    for (uint32_t v : g.filtered) in_core += (c.core7[v >> 5] >> (v & 31)) & 1u;
-    if (in_core <= minimal) {
-      ++g.calls;
-      ++g.core_rejects;
-      return false;
-    }
-  }
   std::sort(g.filtered.begin(), g.filtered.end());
   g.mask.assign(size_t(W), 0u);
   for (uint32_t v : g.filtered) g.mask[v >> 5] |= 1u << (v & 31);
@@ -435,35 +424,16 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
   return ok;
 }
 
-// Per-round state of a cluster that the clique gate reads: sample-degrees inside the round's valid set (:209-213) and
-// the 7-core of the valid sample graph (peel vertices with fewer than 7 live neighbours until a fixed point).
-void prepare_round(Cluster &c) {
-  c.sdeg.assign(size_t(c.n), 0);
+// Host version of sample_degree_mask_kernel (k4_gate.cu), for the host-only entry points: valid vertices with at
+// least 7 valid neighbours in the sample graph (:209-213).
+void host_degree_mask(Cluster &c) {
+  c.deg7.assign(size_t(c.W), 0u);
   for (int v = 0; v < c.n; ++v) {
+    if (!((c.valid[size_t(v) >> 5] >> (v & 31)) & 1u)) continue;
     const uint32_t *row = c.S + size_t(v) * c.W;
     int d = 0;
     for (int w = 0; w < c.W; ++w) d += popc32(row[w] & c.valid[size_t(w)]);
-    c.sdeg[size_t(v)] = uint16_t(std::min(d, 65535));
-  }
-  c.core7 = c.valid;
-  std::vector<uint32_t> &core = c.core7;
-  bool changed = true;
-  while (changed) {
-    changed = false;
-    for (int w0 = 0; w0 < c.W; ++w0) {
-      uint32_t m = core[size_t(w0)];
-      while (m) {
-        const int v = w0 * 32 + __builtin_ctz(m);
-        m &= m - 1;
-        const uint32_t *row = c.S + size_t(v) * c.W;
-        int d = 0;
-        for (int w = 0; w < c.W; ++w) d += popc32(row[w] & core[size_t(w)]);
-        if (d < 7) {
-          core[size_t(v) >> 5] &= ~(1u << (v & 31));
-          changed = true;
-        }
-      }
-    }
+    if (d >= 7) c.deg7[size_t(v) >> 5] |= 1u << (v & 31);
   }
 }
 
@@ -472,8 +442,9 @@ void prepare_round(Cluster &c) {
 struct tod_guess {
   tod_guess_params p{};
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   DeviceBuffer d_off, d_mo, d_q, d_t, d_px, d_sp, d_P, d_S, d_desc, d_valid, d_finite, d_hyps, d_counts, d_R, d_T;
+  DeviceBuffer d_deg, d_active, d_floor, d_verdict;  // K4: degree masks, active-cluster list, per-cluster best, verdicts
   tod::PinnedBuffer h_P, h_S;  // host copies of the bit-matrices (read by the sampler and the gate)
   float k2_ms = 0, k3_ms = 0;
   double k2_bytes = 0, k3_bytes = 0;  // algorithmic bytes of the last call's K2 / K3 launches (SURVEY.md §8d units)
@@ -529,7 +500,7 @@ int32_t tod_select_inliers(int32_t n, const uint32_t *physical_bits, const uint3
   c.valid.assign(valid_bits, valid_bits + c.W);
   c.n_valid = mask_count(c.valid.data(), c.W);
   c.finite.assign(size_t(c.W), 0xFFFFFFFFu);
-  prepare_round(c);
+  host_degree_mask(c);
   std::vector<uint32_t> list;
   hypothesis_inliers(c, triple, true, std::numeric_limits<double>::infinity(), nullptr, nullptr, list);
   GateScratch gs;
@@ -567,6 +538,8 @@ int tod_guess_create(const tod_guess_params *p, tod_guess **out) {
   cudaError_t ce = cudaStreamCreate(&g->stream);
   if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev1);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev2);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev3);
   if (ce != cudaSuccess) {
     tod_guess_destroy(g);
     return fail(TOD_ERR_CUDA, "creating the guess generator's stream/events failed: %s", cudaGetErrorString(ce));
@@ -579,10 +552,13 @@ void tod_guess_destroy(tod_guess *g) {
   if (!g) return;
   cudaSetDevice(g->p.device);
   for (DeviceBuffer *b : {&g->d_off, &g->d_mo, &g->d_q, &g->d_t, &g->d_px, &g->d_sp, &g->d_P, &g->d_S, &g->d_desc,
-                          &g->d_valid, &g->d_finite, &g->d_hyps, &g->d_counts, &g->d_R, &g->d_T})
+                          &g->d_valid, &g->d_finite, &g->d_hyps, &g->d_counts, &g->d_R, &g->d_T, &g->d_deg,
+                          &g->d_active, &g->d_floor, &g->d_verdict})
     b->release();
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->ev2) cudaEventDestroy(g->ev2);
+  if (g->ev3) cudaEventDestroy(g->ev3);
   if (g->stream) cudaStreamDestroy(g->stream);
   g->h_P.release();
   g->h_S.release();
@@ -766,6 +742,16 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   TOD_CUDA(g->d_desc.reserve(desc.size()));
   TOD_CUDA(g->d_valid.reserve(all_valid.size() * 4));
   TOD_CUDA(g->d_finite.reserve(all_finite.size() * 4));
+  TOD_CUDA(g->d_deg.reserve(all_valid.size() * 4));
+  TOD_CUDA(g->d_active.reserve(size_t(nc) * 4));
+  TOD_CUDA(g->d_floor.reserve(size_t(nc) * 4));
+  std::vector<uint32_t> all_deg(all_valid.size(), 0u);
+  std::vector<int32_t> floor_by_cluster(static_cast<size_t>(nc), 0);
+  std::vector<uint8_t> batch_verdict;
+  int max_W = 0;
+  for (const Cluster *c : clusters) max_W = std::max(max_W, c->W);
+  long k4_fails_used = 0, k4_host_used = 0;
+  float k4_ms = 0.f;
   TOD_CUDA(cudaMemcpyAsync(g->d_off.ptr, offsets.data(), offsets.size() * 4, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(g->d_mo.ptr, mo.data(), mo.size() * 8, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(g->d_q.ptr, all_q.data(), all_q.size() * 4, cudaMemcpyHostToDevice, st));
@@ -807,6 +793,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     SamplerScratch sampler;
     std::vector<uint32_t> inliers;
     std::string error;
+    long k4_fails = 0, k4_host = 0;
   };
   std::vector<ThreadScratch> ts(static_cast<size_t>(n_thr));
   std::vector<std::vector<Found>> found_by_cluster(clusters.size());
@@ -837,9 +824,20 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     if (active_idx.empty()) break;
     ++g->n_rounds;
     t_phase = Clock::now();
-    pool.run(int(active_idx.size()), [&](int ai, int) { prepare_round(*clusters[size_t(active_idx[size_t(ai)])]); });
-    g->prof[4] += ms_since(t_phase);
     TOD_CUDA(cudaMemcpyAsync(g->d_valid.ptr, all_valid.data(), all_valid.size() * 4, cudaMemcpyHostToDevice, st));
+    // the gate's degree filter (:209-213) for this round: one mask per active cluster, computed on the GPU (K4 reads
+    // it there) and copied back for the few gates that end on the host
+    {
+      int max_active_n = 0;
+      for (int ci : active_idx) max_active_n = std::max(max_active_n, clusters[size_t(ci)]->n);
+      TOD_CUDA(cudaMemcpyAsync(g->d_active.ptr, active_idx.data(), active_idx.size() * 4, cudaMemcpyHostToDevice, st));
+      TOD_CUDA(tod::launch_sample_degree_mask(g->d_desc.ptr, g->d_active.as<int32_t>(), int(active_idx.size()),
+                                              max_active_n, g->d_S.as<uint32_t>(), g->d_valid.as<uint32_t>(),
+                                              g->d_deg.as<uint32_t>(), 7, st));
+      TOD_CUDA(cudaMemcpyAsync(all_deg.data(), g->d_deg.ptr, all_deg.size() * 4, cudaMemcpyDeviceToHost, st));
+    }
+    bool deg_on_host = false;
+    g->prof[4] += ms_since(t_phase);
 
     // computeModel (ransac.h:80-143): hypotheses are drawn and scored in growing batches; the replay below consumes
     // them in order and stops exactly where the reference's loop would.
@@ -893,6 +891,25 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
             inf_thr ? nullptr : g->d_R.as<float>(), inf_thr ? nullptr : g->d_T.as<float>(), st));
         TOD_CUDA(cudaEventRecord(g->ev1, st));
         TOD_CUDA(cudaMemcpyAsync(batch_counts.data(), g->d_counts.ptr, size_t(H) * 4, cudaMemcpyDeviceToHost, st));
+        if (inf_thr) {
+          // K4: the gate's exact pre-checks for every hypothesis of the batch that beats its cluster's best so far
+          for (int ci : active_idx) {
+            const Cluster *c = clusters[size_t(ci)];
+            floor_by_cluster[size_t(ci)] = c->n_best < 0 ? 0 : c->n_best;
+          }
+          batch_verdict.resize(size_t(H));
+          TOD_CUDA(g->d_verdict.reserve(size_t(H)));
+          TOD_CUDA(cudaMemcpyAsync(g->d_floor.ptr, floor_by_cluster.data(), floor_by_cluster.size() * 4,
+                                   cudaMemcpyHostToDevice, st));
+          TOD_CUDA(cudaEventRecord(g->ev2, st));
+          TOD_CUDA(tod::launch_gate_prechecks(g->d_desc.ptr, g->d_P.as<uint32_t>(), g->d_S.as<uint32_t>(),
+                                              g->d_valid.as<uint32_t>(), g->d_finite.as<uint32_t>(),
+                                              g->d_deg.as<uint32_t>(), H, g->d_hyps.as<uint32_t>(),
+                                              g->d_counts.as<int32_t>(), g->d_floor.as<int32_t>(), max_W,
+                                              g->d_verdict.as<uint8_t>(), st));
+          TOD_CUDA(cudaEventRecord(g->ev3, st));
+          TOD_CUDA(cudaMemcpyAsync(batch_verdict.data(), g->d_verdict.ptr, size_t(H), cudaMemcpyDeviceToHost, st));
+        }
         if (!inf_thr) {
           TOD_CUDA(cudaMemcpyAsync(batch_R.data(), g->d_R.ptr, size_t(H) * 36, cudaMemcpyDeviceToHost, st));
           TOD_CUDA(cudaMemcpyAsync(batch_T.data(), g->d_T.ptr, size_t(H) * 12, cudaMemcpyDeviceToHost, st));
@@ -901,6 +918,17 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         float ms = 0.f;
         TOD_CUDA(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
         g->k3_ms += ms;
+        if (inf_thr) {
+          TOD_CUDA(cudaEventElapsedTime(&ms, g->ev2, g->ev3));
+          k4_ms += ms;
+        }
+        if (!deg_on_host) {  // the round's degree masks arrived with this synchronisation
+          for (int ci : active_idx) {
+            Cluster *c = clusters[size_t(ci)];
+            c->deg7.assign(all_deg.begin() + c->valid_offset, all_deg.begin() + c->valid_offset + c->W);
+          }
+          deg_on_host = true;
+        }
         g->n_hyp_total += H;
         for (int ci : active_idx) {  // per hypothesis: 3 physical rows + valid + finite masks, samples, triple, result
           const Cluster *c = clusters[size_t(ci)];
@@ -917,6 +945,19 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
       // the best-so-far, so it may be evaluated ahead of the sequential scan.  Returns -1 on an internal error.
       auto evaluate = [&](Cluster *c, int h, ThreadScratch &sc) -> int {
         const int pre = batch_counts[size_t(c->batch_begin + h)];
+        if (inf_thr && pre > 7) {
+          const uint8_t v = batch_verdict[size_t(c->batch_begin + h)];
+          if (v == tod::kGateFails) {  // K4 proved that the gate clears this list
+            sc.inliers.clear();
+            ++sc.k4_fails;
+            return 0;
+          }
+          if (v == tod::kGateNeedsHost) ++sc.k4_host;
+          else {
+            sc.error = "K4 left a hypothesis that beats its cluster's best unevaluated";
+            return -1;
+          }
+        }
         const uint32_t *s = c->hyps.data() + size_t(h) * 3;
         const float *R = inf_thr ? nullptr : batch_R.data() + size_t(c->batch_begin + h) * 9;
         const float *T = inf_thr ? nullptr : batch_T.data() + size_t(c->batch_begin + h) * 3;
@@ -1160,7 +1201,12 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     g->prof[9] += sc.gate.ms_proof;
     g->prof[10] += sc.gate.ms_search;
     for (int i = 0; i < 24; ++i) g->gate_hist[i] += sc.gate.hist[i];
+    k4_fails_used += sc.k4_fails;
+    k4_host_used += sc.k4_host;
   }
+  g->gate_hist[21] = k4_fails_used;
+  g->gate_hist[22] = k4_host_used;
+  g->gate_hist[23] = int64_t(k4_ms * 1000.f);
   g->prof[7] = ms_since(t_total);
   if (int64_t(found.size()) > max_poses)
     return fail(TOD_ERR_LIMIT, "%zu poses found but max_poses = %d", found.size(), max_poses);

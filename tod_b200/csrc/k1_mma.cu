@@ -253,8 +253,7 @@ int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_
                                              uint32_t p5, uint32_t p6, uint32_t p7, uint32_t p8, uint32_t p9,
                                              uint32_t p10, uint32_t p11, uint32_t p12, uint32_t p13, uint32_t p14,
                                              uint32_t p15, uint32_t list, int k, uint32_t thr_init, uint32_t grow,
-                                             int n_valid, int thr_dot, uint32_t *gthr, int popx,
-                                             const K1Peers &peers, int qi, uint32_t g_seen) {
+                                             int n_valid, int thr_dot, uint32_t *gthr, int popx) {
   constexpr uint32_t kStride = 4u * kBlockM;  // bytes between consecutive slots of one list
   const uint32_t v[16] = {p0, p1, p2, p3, p4, p5, p6, p7, p8, p9, p10, p11, p12, p13, p14, p15};
   // Hit mask, 3 instructions per register: d = v - (thr + 1) per int16 half (VIADD.16x2, no carry between halves;
@@ -325,16 +324,7 @@ int k1_mma_slow_scan(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_
     const uint32_t kth = worst >> kKeyRowBits;   // 511 while the list is not full
     // publish as a fire-and-forget reduction (RED.MIN): a returning atomic would stall the warp for a full L2
     // round trip on every insert.  Everyone, this list included, picks the bound up at its next per-tile refresh.
-    if (kth < 511u) {
-      atomicMin(gthr, kth);
-      // Sharded DB: the same query is being matched against the other shards on the peer GPUs right now.  A bound that
-      // improves on the shared one is pushed into every peer's bound array over NVLink (fire-and-forget RED.MIN on
-      // peer memory): any list's k-th distance bounds the GLOBAL k-th distance from above, whatever rows it covers.
-      if (kth < g_seen) {
-#pragma unroll 1
-        for (int p = 0; p < peers.n; ++p) atomicMin(peers.gthr[p] + qi, kth);
-      }
-    }
+    if (kth < 511u) atomicMin(gthr, kth);
   }
   return thr_dot;
 }
@@ -346,8 +336,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1)
 #endif
 k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, int nq,
               int shard_rows, uint32_t global_row_base, int rows_per_chunk, int n_chunks, uint32_t thr_init, int K,
-              uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, const uint32_t *__restrict__ popq,
-              const __grid_constant__ K1Peers peers
+              uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, const uint32_t *__restrict__ popq
 #if TOD_K1_STATS
               , int debug_mode   // ablation knobs of the instrumented build only (tools/k1_stats.py)
 #endif
@@ -503,7 +492,6 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     int thr_dot = popx - int(thr_init);                   // distance < thr  <=>  dot > popx - thr
     uint32_t *const my_gthr = (qi < nq && !(debug_mode & 16)) ? gthr + qi : nullptr;
     uint32_t g_next = 511u;                               // shared bound, loaded one tile ahead of its use
-    uint32_t g_seen = 511u;                               // the shared bound this thread currently prunes with
     const uint32_t acc_empty_leader = mapa_u32(ptx::smem_u32(&acc_empty[j]), 0);
     const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(j * kBlockN);
 
@@ -518,7 +506,7 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     auto slow32 = [&](const uint32_t (&v)[32], int o, uint32_t grow, int n_valid) {
       thr_dot = k1_mma_slow_scan(v[o + 0], v[o + 1], v[o + 2], v[o + 3], v[o + 4], v[o + 5], v[o + 6], v[o + 7],
                                  v[o + 8], v[o + 9], v[o + 10], v[o + 11], v[o + 12], v[o + 13], v[o + 14], v[o + 15],
-                                 my_list, K, thr_init, grow, n_valid, thr_dot, my_gthr, popx, peers, qi, g_seen);
+                                 my_list, K, thr_init, grow, n_valid, thr_dot, my_gthr, popx);
     };
 
     for (int t = 0; t < n_tiles; ++t) {
@@ -540,9 +528,7 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       tmem_ld64_pack16(taddr + 192u, vd);
       // shared bound of this query: use the value loaded during the previous tile, start the next load now
       thr_dot = max(thr_dot, popx - int(g_next) - 1);    // distance <= g  <=>  dot > popx - g - 1
-      g_seen = g_next;
-      // (a peer-shared bound array is reset with a byte memset: 0xFFFFFFFF = no bound yet)
-      if (my_gthr) g_next = min(*reinterpret_cast<volatile uint32_t *>(my_gthr), 511u);
+      if (my_gthr) g_next = *reinterpret_cast<volatile uint32_t *>(my_gthr);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
@@ -641,7 +627,7 @@ __global__ void __launch_bounds__(256) expand_query_kernel(const uint8_t *__rest
   out[i] = make_uint2(lo * 0xFEu + 0x01010101u, hi * 0xFEu + 0x01010101u);        // bit 0 -> 0xFF, bit 1 -> 0x01
   if ((threadIdx.x & 31) == 0) {
     popq[i >> 5] = pop;
-    if (gthr) gthr[i >> 5] = 511u;
+    gthr[i >> 5] = 511u;
   }
 }
 
@@ -752,10 +738,8 @@ size_t tensor_map_bytes() { return sizeof(CUtensorMap); }
 
 cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
-                          const uint32_t *d_popq, const K1Peers *peers, cudaStream_t stream) {
+                          const uint32_t *d_popq, cudaStream_t stream) {
   if (k < 1 || k > TOD_MAX_K) return cudaErrorInvalidValue;
-  K1Peers no_peers{};
-  if (!peers) peers = &no_peers;
   const uint32_t thr_init = radius ? min(radius + 1u, 511u) : 511u;
   {  // per device and per context, so not cached in a static: a process may hold handles on several GPUs
     cudaError_t e = cudaFuncSetAttribute(k1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMma);
@@ -771,7 +755,7 @@ cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map
   k1_mma_kernel<<<grid, kThreadsMma, kSmemMma, stream>>>(*static_cast<const CUtensorMap *>(map_q),
                                                          *static_cast<const CUtensorMap *>(map_db), nq, int(shard_rows),
                                                          global_row_base, plan.rows_per_chunk, plan.n_chunks, thr_init, k, d_partial,
-                                                         d_gthr, d_popq, *peers
+                                                         d_gthr, d_popq
 #if TOD_K1_STATS
                                                          , debug_mode
 #endif

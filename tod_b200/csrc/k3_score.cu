@@ -128,14 +128,7 @@ __device__ __forceinline__ bool within(const float (&R)[9], const float (&T)[3],
   return double(d2) < thr2;
 }
 
-// hyp[h] = (s0, s1, s2, cluster).  Per cluster: n, row words W, offsets of its points / matrix / valid vector.
-struct K3Cluster {
-  int32_t n;
-  int32_t W;
-  int64_t point_offset;   // in points
-  int64_t matrix_offset;  // in u32 words
-  int64_t valid_offset;   // in u32 words (offset into both the `valid` and the `finite` bit-vectors)
-};
+// hyp[h] = (s0, s1, s2, cluster); clusters are described by K3Cluster records (tod_internal.h).
 
 // One warp scores 32 consecutive hypotheses.
 //   phase 1: lane l fits ITS OWN hypothesis h0 + l (32 different Kabsch solves per warp instruction instead of the same

@@ -1,0 +1,295 @@
+// K4: the clique gate's exact pre-checks on the GPU, batched over hypotheses.
+//
+// Replaces, for the hypotheses that can still win a RANSAC round, the cheap part of selectWithinDistance
+// (src/common/sac_model_registration_graph.h:203-265 of the reference): the degree filter (:209-218), the
+// neighbourhood test (:222-238), and two exact proofs that the bounded clique search (:258-265 ->
+// maximum_clique.cpp:286-369) cannot return a clique of more than 7 vertices — whatever its visiting order, early stop
+// and step budget — because the induced sample sub-graph contains NO clique of 8:
+//   * its 7-core (iterated removal of vertices with fewer than 7 live neighbours) has fewer than 8 vertices;
+//   * a greedy colouring of the core needs fewer than 8 colours;
+//   * (cores of at most 128 vertices) an exhaustive depth-first search over 128-bit candidate sets finds no 8-clique.
+// Only hypotheses whose sub-graph DOES hold an 8-clique — where the reference's exact stepping decides between "found
+// 8" and "stopped at an exact 7"  — go back to the host search.  The gate can only keep or zero a
+// count, so a certain "fails" is all the host replay needs.
+//
+// One warp per hypothesis.  Bit-rows of the sample graph are read straight from K2's output; masks live in shared
+// memory (W words per warp).  Reference-faithful (+inf threshold) mode only: the candidate set is
+// P[s0] & P[s1] & P[s2] & valid & finite, plus the three samples.
+#include "tod_internal.h"
+
+namespace tod {
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kSmallCore = 128;   // exhaustive search limit (two 64-bit words per set)
+constexpr int kMaxSweeps = 64;
+constexpr int kDfsBudget = 6000;  // node expansions per lane before giving the hypothesis back to the host
+
+__global__ void __launch_bounds__(256)
+sample_degree_mask_kernel(const K3Cluster *__restrict__ clusters, const int32_t *__restrict__ active,
+                          const uint32_t *__restrict__ sample, const uint32_t *__restrict__ valid,
+                          uint32_t *__restrict__ deg_mask, int min_degree) {
+  const K3Cluster cl = clusters[active[blockIdx.y]];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t *S = sample + cl.matrix_offset;
+  const uint32_t *V = valid + cl.valid_offset;
+  uint32_t *D = deg_mask + cl.valid_offset;
+  // a warp owns 32 consecutive rows = one word of the mask: no atomics
+  for (int w0 = blockIdx.x * kWarpsPerCta + warp; w0 < cl.W; w0 += gridDim.x * kWarpsPerCta) {
+    const uint32_t vw = __ldg(V + w0);
+    uint32_t out = 0;
+    uint32_t m = vw;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t *row = S + size_t(w0 * 32 + b) * cl.W;
+      int d = 0;
+      for (int w = lane; w < cl.W; w += 32) d += __popc(__ldg(row + w) & __ldg(V + w));
+      d = __reduce_add_sync(0xffffffffu, d);
+      if (d >= min_degree) out |= 1u << b;
+    }
+    if (lane == 0) D[w0] = out;
+  }
+}
+
+struct U128 {
+  unsigned long long lo, hi;
+};
+__device__ __forceinline__ int popc128(U128 a) { return __popcll(a.lo) + __popcll(a.hi); }
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restrict__ physical,
+               const uint32_t *__restrict__ sample, const uint32_t *__restrict__ valid,
+               const uint32_t *__restrict__ finite, const uint32_t *__restrict__ deg_mask, int n_hyp,
+               const uint4 *__restrict__ hyps, const int32_t *__restrict__ counts, const int32_t *__restrict__ floor_,
+               int max_words, uint8_t *__restrict__ verdict) {
+  extern __shared__ uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int h = blockIdx.x * kWarpsPerCta + warp;
+  if (h >= n_hyp) return;
+  // per warp: alive[max_words] | work[max_words] | ids[128] (u16) | adj[128] (U128)
+  const int per_warp = 2 * max_words + kSmallCore / 2 + kSmallCore * 4;
+  uint32_t *alive = smem + size_t(warp) * per_warp;
+  uint32_t *work = alive + max_words;
+  uint16_t *ids = reinterpret_cast<uint16_t *>(work + max_words);
+  U128 *adj = reinterpret_cast<U128 *>(work + max_words + kSmallCore / 2);
+
+  const int cnt = __ldg(counts + h);
+  const uint4 hy = __ldg(hyps + h);
+  auto finish = [&](int v) {
+    if (lane == 0) verdict[h] = uint8_t(v);
+  };
+  if (cnt <= 7 || cnt <= __ldg(floor_ + hy.w)) return finish(kGateNotEvaluated);
+  const K3Cluster cl = clusters[hy.w];
+  const int W = cl.W;
+  if (W > max_words) return finish(kGateNeedsHost);
+  const uint32_t *P = physical + cl.matrix_offset;
+  const uint32_t *S = sample + cl.matrix_offset;
+  const uint32_t *V = valid + cl.valid_offset;
+  const uint32_t *F = finite + cl.valid_offset;
+  const uint32_t *D = deg_mask + cl.valid_offset;
+
+  // ---- filtered = (common valid physical neighbours of the samples + the samples) with sample-degree >= 7 ----------
+  const uint32_t *r0 = P + size_t(hy.x) * W, *r1 = P + size_t(hy.y) * W, *r2 = P + size_t(hy.z) * W;
+  int nf = 0;
+  for (int w = lane; w < W; w += 32) {
+    uint32_t m = __ldg(r0 + w) & __ldg(r1 + w) & __ldg(r2 + w) & __ldg(V + w) & __ldg(F + w);
+    if (int(hy.x >> 5) == w) m |= 1u << (hy.x & 31);  // the samples pass the +inf test themselves (count > 7 implies
+    if (int(hy.y >> 5) == w) m |= 1u << (hy.y & 31);  // finite samples and a finite fit)
+    if (int(hy.z >> 5) == w) m |= 1u << (hy.z & 31);
+    m &= __ldg(D + w);
+    alive[w] = m;
+    nf += __popc(m);
+  }
+  nf = __reduce_add_sync(0xffffffffu, nf);
+  if (nf <= 7) return finish(kGateFails);  // :214-218
+  __syncwarp();
+
+  // ---- neighbourhood test (:222-238) and 7-core: Jacobi sweeps of "degree inside the live set" ------------------------
+  int n_alive = nf;
+  for (int sweep = 0;; ++sweep) {
+    if (sweep >= kMaxSweeps) return finish(kGateNeedsHost);
+    int max_d = 0, removed = 0;
+    for (int w0 = 0; w0 < W; ++w0) {
+      uint32_t m = alive[w0];
+      uint32_t drop = 0;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t *row = S + size_t(w0 * 32 + b) * W;
+        int d = 0;
+        for (int w = lane; w < W; w += 32) d += __popc(__ldg(row + w) & alive[w]);
+        d = __reduce_add_sync(0xffffffffu, d);
+        max_d = max(max_d, d);
+        if (d < 7) {
+          drop |= 1u << b;
+          ++removed;
+        }
+      }
+      if (lane == 0) work[w0] = drop;
+    }
+    // the reference scans for ONE filtered vertex with more than 7 sample-neighbours inside filtered
+    if (sweep == 0 && max_d <= 7) return finish(kGateFails);
+    if (removed == 0) break;
+    __syncwarp();
+    for (int w = lane; w < W; w += 32) alive[w] &= ~work[w];
+    n_alive -= removed;
+    __syncwarp();
+    if (n_alive < 8) return finish(kGateFails);  // an 8-clique lives inside the 7-core
+  }
+
+  // ---- greedy colouring of the core: fewer than 8 colours bound the clique number below 8 ---------------------------
+  __syncwarp();
+  for (int w = lane; w < W; w += 32) work[w] = alive[w];  // uncoloured
+  __syncwarp();
+  int colours = 0;
+  bool undecided = false;
+  for (int left = n_alive; left > 0;) {
+    if (++colours >= 8) {
+      undecided = true;
+      break;
+    }
+    // candidates of this colour class: uncoloured vertices without a neighbour in the class so far (<= 4 words/lane)
+    uint32_t q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = (lane + 32 * i < W) ? work[lane + 32 * i] : 0u;
+    for (;;) {
+      int mine = 0x7fffffff;
+#pragma unroll
+      for (int i = 3; i >= 0; --i)
+        if (q[i]) mine = (lane + 32 * i) * 32 + __ffs(q[i]) - 1;
+      const int v = __reduce_min_sync(0xffffffffu, mine);
+      if (v == 0x7fffffff) break;
+      --left;
+      const uint32_t *row = S + size_t(v) * W;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int w = lane + 32 * i;
+        if (w < W) {
+          if (w == (v >> 5)) {
+            q[i] &= ~(1u << (v & 31));
+            work[w] &= ~(1u << (v & 31));
+          }
+          q[i] &= ~__ldg(row + w);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (!undecided) return finish(kGateFails);
+  if (n_alive > kSmallCore) return finish(kGateNeedsHost);
+
+  // ---- small core: exhaustive search for an 8-clique over 128-bit sets ------------------------------------------------
+  __syncwarp();
+  if (lane == 0) {
+    int k = 0;
+    for (int w = 0; w < W; ++w) {
+      uint32_t m = alive[w];
+      while (m) {
+        ids[k++] = uint16_t(w * 32 + __ffs(m) - 1);
+        m &= m - 1;
+      }
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < n_alive; i += 32) {
+    const uint32_t *row = S + size_t(ids[i]) * W;
+    U128 a{0ull, 0ull};
+    for (int j = 0; j < n_alive; ++j) {
+      const uint32_t u = ids[j];
+      const unsigned long long bit = (__ldg(row + (u >> 5)) >> (u & 31)) & 1u;
+      if (j < 64) a.lo |= bit << j;
+      else a.hi |= bit << (j - 64);
+    }
+    adj[i] = a;
+  }
+  __syncwarp();
+  bool found = false, overflow = false;
+  for (int root = lane; root < n_alive && !found && !overflow; root += 32) {
+    // cliques are enumerated with increasing core indices: candidates of level 1 = neighbours of root above root
+    U128 st[8];
+    U128 above{~0ull, ~0ull};
+    if (root < 63) above.lo = ~0ull << (root + 1);
+    else {
+      above.lo = 0ull;
+      above.hi = root >= 127 ? 0ull : ~0ull << (root - 63);
+    }
+    st[1].lo = adj[root].lo & above.lo;
+    st[1].hi = adj[root].hi & above.hi;
+    int size = 1, steps = 0;
+    while (size >= 1) {
+      U128 p = st[size];
+      if (popc128(p) < 8 - size) {
+        --size;
+        continue;
+      }
+      int v;
+      if (p.lo) {
+        v = __ffsll(p.lo) - 1;
+        p.lo &= p.lo - 1;
+      } else {
+        v = 64 + __ffsll(p.hi) - 1;
+        p.hi &= p.hi - 1;
+      }
+      st[size] = p;  // v consumed at this level; what is left of p lies above v
+      if (size + 1 == 8) {
+        found = true;
+        break;
+      }
+      U128 nx;
+      nx.lo = p.lo & adj[v].lo;
+      nx.hi = p.hi & adj[v].hi;
+      if (popc128(nx) >= 8 - (size + 1)) {
+        ++size;
+        st[size] = nx;
+      }
+      if (++steps > kDfsBudget) {
+        overflow = true;
+        break;
+      }
+    }
+  }
+  const bool any_found = __any_sync(0xffffffffu, found);
+  const bool any_overflow = __any_sync(0xffffffffu, overflow);
+  finish((any_found || any_overflow) ? kGateNeedsHost : kGateFails);
+}
+
+}  // namespace
+
+cudaError_t launch_sample_degree_mask(const void *d_clusters, const int32_t *d_active, int n_active, int max_n,
+                                      const uint32_t *d_sample, const uint32_t *d_valid, uint32_t *d_deg_mask,
+                                      int min_degree, cudaStream_t stream) {
+  if (n_active <= 0 || max_n <= 0) return cudaSuccess;
+  const int max_w = adjacency_row_words(max_n);
+  const int bx = std::max(1, std::min(64, (max_w + kWarpsPerCta - 1) / kWarpsPerCta));
+  for (int c0 = 0; c0 < n_active; c0 += 65535) {
+    dim3 grid(bx, std::min(65535, n_active - c0));
+    sample_degree_mask_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(static_cast<const K3Cluster *>(d_clusters),
+                                                                      d_active + c0, d_sample, d_valid, d_deg_mask,
+                                                                      min_degree);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_physical, const uint32_t *d_sample,
+                                  const uint32_t *d_valid, const uint32_t *d_finite, const uint32_t *d_deg_mask,
+                                  int n_hyp, const uint32_t *d_hyps, const int32_t *d_counts, const int32_t *d_floor,
+                                  int max_words, uint8_t *d_verdict, cudaStream_t stream) {
+  if (n_hyp <= 0) return cudaSuccess;
+  max_words = std::min(max_words, 128);  // clusters of more than 4096 correspondences go to the host search
+  max_words = std::max(max_words, 4);
+  const size_t smem = size_t(kWarpsPerCta) * (2 * size_t(max_words) + kSmallCore / 2 + kSmallCore * 4) * sizeof(uint32_t);
+  cudaError_t e = cudaFuncSetAttribute(k4_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  const int blocks = (n_hyp + kWarpsPerCta - 1) / kWarpsPerCta;
+  k4_gate_kernel<<<blocks, kWarpsPerCta * 32, smem, stream>>>(
+      static_cast<const K3Cluster *>(d_clusters), d_physical, d_sample, d_valid, d_finite, d_deg_mask, n_hyp,
+      reinterpret_cast<const uint4 *>(d_hyps), d_counts, d_floor, max_words, d_verdict);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace tod

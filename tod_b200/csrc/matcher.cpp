@@ -42,13 +42,10 @@ struct tod_matcher {
   DeviceBuffer d_rows, d_hkeys, d_hvals;
   // sharded handle with a communicator (tod_matcher_set_comm)
   tod::ncclComm_t comm = nullptr;
-  int comm_mode = 0;                 // 0 none, 1 NCCL, 2 NCCL + peer-shared bounds
+  int comm_mode = 0;                 // 0 none, 1 NCCL
   DeviceBuffer d_keys_local, d_keys_all;
-  uint32_t *d_bounds = nullptr;      // 2 x bounds_cap u32 (double-buffered by step parity), exported over CUDA IPC
-  size_t bounds_cap = 0;
-  uint32_t *peer_bounds[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int n_peers = 0;
-  unsigned step_parity = 0;
+  cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;  // around the all-gather of the last sharded call
+  bool ev_x_valid = false;
   int32_t reserved_nq = 0;
 };
 
@@ -79,26 +76,12 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
     }
     TOD_CUDA(m->d_gthr.reserve(size_t(nq) * sizeof(uint32_t)));
     TOD_CUDA(m->d_popq.reserve(size_t(nq) * sizeof(uint32_t)));
-    uint32_t *gthr = m->d_gthr.as<uint32_t>();
-    tod::K1Peers peers{};
-    const bool shared = m->comm_mode == 2 && size_t(nq) <= m->bounds_cap;
-    if (shared) {
-      // Peer-shared bounds: this step prunes with buffer `parity`, which was reset one step ago (or at set_comm) and
-      // receives the peers' pushes while K1 runs; the other buffer is reset now for the next step.  The collective
-      // that ends every step orders the resets against the peers' pushes (multi-GPU).
-      gthr = m->d_bounds + size_t(m->step_parity) * m->bounds_cap;
-      TOD_CUDA(cudaMemsetAsync(m->d_bounds + size_t(m->step_parity ^ 1u) * m->bounds_cap, 0xFF,
-                               m->bounds_cap * sizeof(uint32_t), st));
-      for (int i = 0; i < m->n_peers; ++i) peers.gthr[i] = m->peer_bounds[i] + size_t(m->step_parity) * m->bounds_cap;
-      peers.n = m->n_peers;
-      m->step_parity ^= 1u;
-    }
-    TOD_CUDA(tod::launch_expand_queries(d_query, m->d_q8.ptr, nq, m->d_popq.as<uint32_t>(), shared ? nullptr : gthr,
+    TOD_CUDA(tod::launch_expand_queries(d_query, m->d_q8.ptr, nq, m->d_popq.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
                                         st));
     TOD_CUDA(cudaEventRecord(m->ev0, st));
     TOD_CUDA(tod::launch_k1_mma(plan, m->map_q, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
-                                m->p.radius, m->d_partial.as<uint32_t>(), gthr, m->d_popq.as<uint32_t>(),
-                                shared ? &peers : nullptr, st));
+                                m->p.radius, m->d_partial.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
+                                m->d_popq.as<uint32_t>(), st));
     TOD_CUDA(cudaEventRecord(m->ev1, st));
     m->ev_valid = true;
     m->last_kernel = "mma";
@@ -167,18 +150,20 @@ int run_process(tod_matcher *m, const void *d_query, int nq, tod_match *d_matche
   TOD_CUDA(m->d_keys_all.reserve(nk * sizeof(uint32_t) * size_t(m->p.shard_count)));
   if (int rc = run_k1(m, d_query, nq, st, &plan)) return rc;
   TOD_CUDA(tod::launch_reduce_keys(m->d_partial.as<uint32_t>(), plan.n_sources, nq, k, m->d_keys_local.as<uint32_t>(), st));
+  TOD_CUDA(cudaEventRecord(m->ev_x0, st));
   TOD_NCCL(tod::nccl_api().AllGather(m->d_keys_local.ptr, m->d_keys_all.ptr, nk, tod::kNcclUint32, m->comm, st));
+  TOD_CUDA(cudaEventRecord(m->ev_x1, st));
+  m->ev_x_valid = true;
   return finalize(m, m->d_keys_all.as<uint32_t>(), m->p.shard_count, nq, d_matches, d_counts, d_points3d, st);
 }
 
 void close_comm(tod_matcher *m) {
-  for (int i = 0; i < m->n_peers; ++i)
-    if (m->peer_bounds[i]) cudaIpcCloseMemHandle(m->peer_bounds[i]);
-  m->n_peers = 0;
-  if (m->d_bounds) cudaFree(m->d_bounds);
-  m->d_bounds = nullptr;
-  m->bounds_cap = 0;
-  if (m->comm) tod::nccl_api().CommDestroy(m->comm);
+  // ncclCommDestroy waits for the peer ranks (it hung a run whose ranks closed their handles at different times);
+  // the handle's stream is idle here, so the communicator is torn down locally with ncclCommAbort instead.
+  if (m->comm) {
+    if (tod::nccl_api().CommAbort) tod::nccl_api().CommAbort(m->comm);
+    else tod::nccl_api().CommDestroy(m->comm);
+  }
   m->comm = nullptr;
   m->comm_mode = 0;
 }
@@ -201,7 +186,6 @@ void tod_matcher_default_params(tod_matcher_params *p) {
   p->ratio = 0.f;
   p->remove_duplicates = 0;
   p->frame_keypoints = 0;
-  p->share_bounds = 1;
 }
 
 int tod_matcher_params_from_json(const char *search_json_params, tod_matcher_params *p) {
@@ -271,6 +255,8 @@ int tod_matcher_create(const tod_matcher_params *p, tod_matcher **out) {
   if (ce == cudaSuccess) ce = cudaStreamCreate(&m->stream);
   if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev1);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev_x0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev_x1);
   if (ce != cudaSuccess) {
     tod_matcher_destroy(m);
     return fail(TOD_ERR_CUDA, "creating the matcher's stream/events failed: %s", cudaGetErrorString(ce));
@@ -290,6 +276,8 @@ void tod_matcher_destroy(tod_matcher *m) {
     b->release();
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->ev_x0) cudaEventDestroy(m->ev_x0);
+  if (m->ev_x1) cudaEventDestroy(m->ev_x1);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -476,68 +464,15 @@ int tod_matcher_set_comm(tod_matcher *m, const void *unique_id) {
   const int world = m->p.shard_count, rank = m->p.shard_rank;
   TOD_NCCL(api.CommInitRank(&m->comm, world, id, rank));
   m->comm_mode = 1;
-  if (!m->p.share_bounds || world < 2 || world > 8) return TOD_OK;
-
-  // ---- peer-shared bounds: export this rank's double-buffered bound array, map everybody else's -------------------
-  struct Msg {
-    cudaIpcMemHandle_t handle;
-    uint64_t cap;
-    int32_t ok;
-    int32_t pad;
-  };
-  Msg mine{};
-  const size_t cap = size_t(std::max<int32_t>(m->reserved_nq, 1 << 18));
-  bool ok = cudaMalloc(reinterpret_cast<void **>(&m->d_bounds), 2 * cap * sizeof(uint32_t)) == cudaSuccess;
-  if (ok) ok = cudaMemsetAsync(m->d_bounds, 0xFF, 2 * cap * sizeof(uint32_t), m->stream) == cudaSuccess;
-  if (ok) ok = cudaStreamSynchronize(m->stream) == cudaSuccess;
-  if (ok) ok = cudaIpcGetMemHandle(&mine.handle, m->d_bounds) == cudaSuccess;
-  cudaGetLastError();
-  mine.cap = cap;
-  mine.ok = ok ? 1 : 0;
-  DeviceBuffer d_mine, d_all;
-  TOD_CUDA(d_mine.reserve(sizeof(Msg)));
-  TOD_CUDA(d_all.reserve(sizeof(Msg) * size_t(world)));
-  std::vector<Msg> all;
-  all.resize(static_cast<size_t>(world));
-  TOD_CUDA(cudaMemcpyAsync(d_mine.ptr, &mine, sizeof(Msg), cudaMemcpyHostToDevice, m->stream));
-  TOD_NCCL(api.AllGather(d_mine.ptr, d_all.ptr, sizeof(Msg), tod::kNcclUint8, m->comm, m->stream));
-  TOD_CUDA(cudaMemcpyAsync(all.data(), d_all.ptr, sizeof(Msg) * size_t(world), cudaMemcpyDeviceToHost, m->stream));
-  TOD_CUDA(cudaStreamSynchronize(m->stream));
-  int32_t good = 1;
-  for (const Msg &x : all) good = good && x.ok && x.cap == cap;
-  int n = 0;
-  if (good) {
-    for (int r = 0; r < world && good; ++r) {
-      if (r == rank) continue;
-      void *ptr = nullptr;
-      if (cudaIpcOpenMemHandle(&ptr, all[size_t(r)].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        cudaGetLastError();
-        good = 0;
-        break;
-      }
-      m->peer_bounds[n++] = static_cast<uint32_t *>(ptr);
-    }
-  }
-  m->n_peers = n;
-  // everybody must agree: one rank that cannot map its peers turns the feature off for all (results never depend on it)
-  int32_t *d_flag = d_mine.as<int32_t>();
-  TOD_CUDA(cudaMemcpyAsync(d_flag, &good, sizeof(good), cudaMemcpyHostToDevice, m->stream));
-  TOD_NCCL(api.AllReduce(d_flag, d_flag, 1, tod::kNcclInt32, tod::kNcclMin, m->comm, m->stream));
-  TOD_CUDA(cudaMemcpyAsync(&good, d_flag, sizeof(good), cudaMemcpyDeviceToHost, m->stream));
-  TOD_CUDA(cudaStreamSynchronize(m->stream));
-  d_mine.release();
-  d_all.release();
-  if (good) {
-    m->bounds_cap = cap;
-    m->step_parity = 0;
-    m->comm_mode = 2;
-  } else {
-    for (int i = 0; i < m->n_peers; ++i) cudaIpcCloseMemHandle(m->peer_bounds[i]);
-    m->n_peers = 0;
-    cudaFree(m->d_bounds);
-    m->d_bounds = nullptr;
-  }
   return TOD_OK;
+}
+
+float tod_matcher_last_exchange_ms(const tod_matcher *m) {
+  if (!m || !m->ev_x_valid) return -1.f;
+  if (cudaEventSynchronize(m->ev_x1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, m->ev_x0, m->ev_x1) != cudaSuccess) return -1.f;
+  return ms;
 }
 
 int tod_matcher_knn_keys_device(tod_matcher *m, const void *d_descriptors, int32_t nq, uint32_t *d_keys,

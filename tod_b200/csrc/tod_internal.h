@@ -110,7 +110,6 @@ cudaError_t launch_k1_popc(const K1Plan &plan, const void *d_query, int nq, cons
 // memory).  launch_expand_queries also writes the queries' popcounts and resets their shared bounds to 511.
 K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count);
 cudaError_t launch_expand_db(const void *d_bits, void *d_int8, int64_t rows, cudaStream_t stream);
-// d_gthr may be null (bounds reset elsewhere: the peer-shared arrays are reset by a memset one step ahead).
 cudaError_t launch_expand_queries(const void *d_bits, void *d_int8, int64_t rows, uint32_t *d_popq, uint32_t *d_gthr,
                                   cudaStream_t stream);
 bool make_desc_tensor_map(void *map_out, const void *d_int8, int64_t rows, int box_rows);
@@ -119,14 +118,9 @@ int k1_mma_db_box_rows();
 size_t tensor_map_bytes();
 // d_gthr: nq u32 shared per-query bounds, must hold 511 (no bound) before the launch; d_popq: nq query popcounts
 // (both written by launch_expand_queries).
-// peers (may be null): the other shards' bound arrays, mapped over NVLink (CUDA IPC); K1 pushes improved bounds there.
-struct K1Peers {
-  uint32_t *gthr[7];
-  int n;
-};
 cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
-                          const uint32_t *d_popq, const K1Peers *peers, cudaStream_t stream);
+                          const uint32_t *d_popq, cudaStream_t stream);
 
 // Reduce n_src x nq x k key lists to nq x k keys (ascending).
 cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t *d_out,
@@ -149,7 +143,17 @@ cudaError_t launch_fill_adjacency(int n_clusters, const int32_t *d_offsets, cons
                                   const float *d_spans, float sensor_error, uint32_t *d_physical,
                                   uint32_t *d_sample, int max_cluster, cudaStream_t stream);
 
-// K3: hypotheses (s0, s1, s2, cluster) of a batch of clusters described by K3Cluster records (k3_score.cu).
+// One (frame, object) cluster of correspondences as the geometry kernels see it: n, row words W, and the offsets of
+// its points / bit-matrices / W-word bit-vectors (valid, finite, degree mask) inside the batch-wide buffers.
+struct K3Cluster {
+  int32_t n;
+  int32_t W;
+  int64_t point_offset;   // in points
+  int64_t matrix_offset;  // in u32 words
+  int64_t valid_offset;   // in u32 words (offset into the `valid`, `finite` and `deg_mask` bit-vectors)
+};
+
+// K3: hypotheses (s0, s1, s2, cluster) of a batch of clusters described by K3Cluster records.
 // d_finite may be null (all points finite).
 cudaError_t launch_score_hypotheses_batched(const void *d_clusters, const float *d_query, const float *d_train,
                                             const uint32_t *d_physical, const uint32_t *d_valid,
@@ -159,6 +163,23 @@ cudaError_t launch_score_hypotheses_batched(const void *d_clusters, const float 
 size_t k3_cluster_desc_size();
 void k3_fill_cluster_desc(void *dst, int32_t n, int32_t W, int64_t point_offset, int64_t matrix_offset,
                           int64_t valid_offset);
+
+// Per round, for the clusters listed in d_active: deg_mask bit v <=> v is valid and has at least `min_degree` valid
+// neighbours in the sample graph (the degree filter of the clique gate, sac_model_registration_graph.h:209-213).
+// deg_mask words of the listed clusters are overwritten.
+cudaError_t launch_sample_degree_mask(const void *d_clusters, const int32_t *d_active, int n_active, int max_n,
+                                      const uint32_t *d_sample, const uint32_t *d_valid, uint32_t *d_deg_mask,
+                                      int min_degree, cudaStream_t stream);
+
+// K4: the clique gate's exact pre-checks for every hypothesis whose pre-gate count beats both 7 and its cluster's
+// current best (d_floor, per cluster).  verdict: 0 = not evaluated, 1 = the gate FAILS for certain (no clique of 8 can
+// be returned by the reference's search), 2 = undecided: run the exact host search.  Reference-faithful (+inf
+// threshold) mode only.
+enum { kGateNotEvaluated = 0, kGateFails = 1, kGateNeedsHost = 2 };
+cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_physical, const uint32_t *d_sample,
+                                  const uint32_t *d_valid, const uint32_t *d_finite, const uint32_t *d_deg_mask,
+                                  int n_hyp, const uint32_t *d_hyps, const int32_t *d_counts, const int32_t *d_floor,
+                                  int max_words, uint8_t *d_verdict, cudaStream_t stream);
 
 inline int adjacency_row_words(int n) { return ((n + 31) / 32 + 3) & ~3; }
 
