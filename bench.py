@@ -53,6 +53,10 @@ def parse_args():
     ap.add_argument("--no-pipeline", action="store_true", help="skip the C4 (matcher + guess generator) leg")
     ap.add_argument("--pipeline-frames", type=int, default=64)
     ap.add_argument("--c5-objects", type=int, default=100, help="objects in the C5 RANSAC-stress leg (0 = skip)")
+    ap.add_argument("--exchange", default="library", choices=["library", "torch"],
+                    help="N > 1, device-timed loop only: 'torch' moves the key all-gather out of the library "
+                         "(stage calls + torch.distributed), for A/B comparison; the default and the e2e loop use the "
+                         "in-library ncclAllGather")
     ap.add_argument("--trace", action="store_true", help="progress lines on stderr (debugging a multi-rank run)")
     return ap.parse_args()
 
@@ -473,10 +477,19 @@ def run_ours(args):
     pts3d = torch.empty((nqt, k, 3), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step():
-        # DescriptorMatcher.process on device buffers, one C-ABI call: K1 -> [top-k reduction -> ncclAllGather of the
-        # packed keys] -> merge / radius cut / decode / matches_3d gather
-        m.process_device(q_dev.data_ptr(), nqt, matches.data_ptr(), counts.data_ptr(), pts3d.data_ptr(), sptr)
+    if world > 1 and args.exchange == "torch":
+        keys = torch.empty((nqt, k), dtype=torch.int32, device=dev)
+        keys_all = torch.empty((world, nqt, k), dtype=torch.int32, device=dev)
+
+        def step():   # A/B variant: the same kernels, the all-gather issued by torch.distributed between two stage calls
+            m.knn_keys_device(q_dev.data_ptr(), nqt, keys.data_ptr(), sptr)
+            dist.all_gather_into_tensor(keys_all.view(-1), keys.view(-1))
+            m.merge_device(keys_all.data_ptr(), world, nqt, matches.data_ptr(), counts.data_ptr(), pts3d.data_ptr(), sptr)
+    else:
+        def step():
+            # DescriptorMatcher.process on device buffers, one C-ABI call: K1 -> [top-k reduction -> ncclAllGather of
+            # the packed keys] -> merge / radius cut / decode / matches_3d gather
+            m.process_device(q_dev.data_ptr(), nqt, matches.data_ptr(), counts.data_ptr(), pts3d.data_ptr(), sptr)
 
     def barrier():
         if world > 1:
@@ -509,8 +522,6 @@ def run_ours(args):
         step()
         ev[s][1].record(stream)
         k1_ms.append(m.last_k1_ms)   # CUDA events recorded by the library around the K1 launch, on the launch stream
-        if world > 1:
-            xch_ms.append(m.last_exchange_ms)   # ... and around the ncclAllGather
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
@@ -593,10 +604,18 @@ def run_ours(args):
 
     shard_rows, kern = m.shard_rows, m.last_kernel
     per_rank = None
-    if world > 1:   # per-rank device times of K1 and of the exchange (the all-gather also waits for the slowest rank)
+    if world > 1:
+        # a short profiling loop OUTSIDE the timed regions: the exchange bracketed by events (off in the timed loops)
+        m.set_stage_timing(True)
+        for _ in range(5):
+            m.process_device(q_dev.data_ptr(), nqt, matches.data_ptr(), counts.data_ptr(), pts3d.data_ptr(), sptr)
+            xch_ms.append(m.last_exchange_ms)
+        m.set_stage_timing(False)
+        xch_ms = xch_ms[1:]   # per-rank device times of K1 and of the exchange (the all-gather also waits for the slowest rank)
         per_rank = [None] * world
         dist.all_gather_object(per_rank, {"rank": rank, "k1_ms": float(np.mean(k1_ms)),
-                                          "exchange_ms": float(np.mean(xch_ms)), "shard_rows": shard_rows})
+                                          "exchange_ms": float(np.mean(xch_ms)) if xch_ms else None,
+                                          "shard_rows": shard_rows})
     barrier()
     m.close()                                            # every rank tears its handle (and communicator) down together
     trace("handle closed")
@@ -685,7 +704,7 @@ def run_ours(args):
             "collective": (None if world == 1 else
                            {"where": "inside libtod_b200.so (ncclAllGather of packed top-k keys on the handle's "
                                      "stream); no torch.distributed collective in the timed region",
-                            "comm_mode": comm_mode, "per_rank": per_rank}),
+                            "comm_mode": comm_mode, "device_timed_exchange": args.exchange, "per_rank": per_rank}),
             "gpu_launches": int(launches), "wall_s_timed_region": wall, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "cpu_baseline_lsh": lsh}
     if world == 1 and not args.no_pipeline:

@@ -160,7 +160,10 @@ int tod_comm_unique_id(void *id_out);
 int tod_matcher_set_comm(tod_matcher *m, const void *unique_id);
 /* 0 = no communicator, 1 = NCCL communicator attached */
 int32_t tod_matcher_comm_mode(const tod_matcher *m);
-/* Device time (ms, CUDA events on the launch stream) of the ncclAllGather of the last sharded call; < 0 if none. */
+/* Device time (ms, CUDA events on the launch stream) of the ncclAllGather of the last sharded call; < 0 if none.
+ * The two extra event records cost a few microseconds per step, so they are off unless stage timing is switched on
+ * (profiling runs); the K1 events behind tod_matcher_last_k1_ms are always recorded. */
+void tod_matcher_set_stage_timing(tod_matcher *m, int32_t on);
 float tod_matcher_last_exchange_ms(const tod_matcher *m);
 
 /* Sharding of the concatenated DB over `shard_count` GPUs (host-only, no device needed): rank r holds the contiguous

@@ -51,6 +51,25 @@ def test_product_clique_finder_equals_compiled_reference():
 
 
 @needs_ref
+@pytest.mark.parametrize("n,p,seed", [(150, 0.85, 1), (300, 0.83, 2), (420, 0.9, 3), (260, 0.6, 4), (500, 0.97, 5)])
+def test_product_clique_finder_on_large_dense_graphs(n, p, seed):
+    """The gate's dense regime (inlier graphs are ~85 % dense, hundreds of vertices): the class-by-class colouring
+    must reproduce the reference's sequential ColorSort exactly — identical vertex lists in gate mode."""
+    rng = np.random.default_rng(seed)
+    a = np.triu(rng.random((n, n)) < p, 1)
+    low = rng.choice(n, n // 10, replace=False)                # a few low-degree vertices: the search visits them first
+    for v in low:
+        keep = rng.random(n) < 0.06
+        a[v, :] &= keep
+        a[:, v] &= keep
+    edges = np.argwhere(a)
+    exp = ref.find_clique(n, edges, 7, sorted_insert=True)
+    got, more = clique_find(n, edges, 7)
+    assert got == exp
+    assert more == (len(exp) > 7)
+
+
+@needs_ref
 def test_product_rigid_fit_equals_reference():
     lib = capi.load()
     for n, seed in ((3, 1), (10, 2), (200, 3)):

@@ -69,6 +69,7 @@ SIGNATURES = [
     ("tod_comm_unique_id", ctypes.c_int, [_P]),
     ("tod_matcher_set_comm", ctypes.c_int, [_P, _P]),
     ("tod_matcher_comm_mode", _I32, [_P]),
+    ("tod_matcher_set_stage_timing", None, [_P, _I32]),
     ("tod_matcher_last_exchange_ms", _F, [_P]),
     ("tod_shard_range", ctypes.c_int, [_I64, _I32, _I32, ctypes.POINTER(_I64), ctypes.POINTER(_I64)]),
     ("tod_pack_key", _U32, [_U32, _U32]),

@@ -153,6 +153,9 @@ class DescriptorMatcher:
     def last_k1_ms(self):
         return float(self._lib.tod_matcher_last_k1_ms(self._h))
 
+    def set_stage_timing(self, on):
+        self._lib.tod_matcher_set_stage_timing(self._h, 1 if on else 0)
+
     @property
     def last_exchange_ms(self):
         return float(self._lib.tod_matcher_last_exchange_ms(self._h))

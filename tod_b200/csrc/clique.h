@@ -24,8 +24,10 @@ class CliqueFinder {
  public:
   // adjacency is kept as n rows of 64-bit words
   explicit CliqueFinder(int n_vertices)
-      : n_(n_vertices), words_((n_vertices + 63) / 64), bits_(size_t(n_vertices) * size_t((n_vertices + 63) / 64), 0ull),
-        degree_(size_t(n_vertices), 0u) {}
+      : n_(n_vertices), id_space_(n_vertices), words_((n_vertices + 63) / 64),
+        bits_(size_t(n_vertices) * size_t((n_vertices + 63) / 64), 0ull) {
+    rows_ = bits_.data();
+  }
 
   // from a dense symmetric n x ceil(n/32) bit-matrix of 32-bit words (no self-loops)
   CliqueFinder(int n_vertices, const uint32_t *adjacency) : CliqueFinder(n_vertices) {
@@ -33,26 +35,28 @@ class CliqueFinder {
     for (int v = 0; v < n_; ++v) {
       const uint32_t *src = adjacency + size_t(v) * w32;
       uint64_t *dst = bits_.data() + size_t(v) * words_;
-      unsigned d = 0;
-      for (int w = 0; w < w32; ++w) {
-        dst[w >> 1] |= uint64_t(src[w]) << (32 * (w & 1));
-        d += unsigned(__builtin_popcount(src[w]));
-      }
-      degree_[size_t(v)] = d;
+      for (int w = 0; w < w32; ++w) dst[w >> 1] |= uint64_t(src[w]) << (32 * (w & 1));
     }
   }
 
-  void add_edge(int a, int b) {
+  // VIEW of a larger graph: the sub-graph induced by `vertices` (ascending ids) of a graph whose rows (`words64`
+  // 64-bit words each, id_space rows) stay where they are — no induced copy is built.  Every set operation below is
+  // masked by the current vertex set, and ids keep the order of their ranks, so the search steps exactly as it would
+  // on the renumbered induced graph (the reference builds that one, sac_model_registration_graph.h:241-255).
+  CliqueFinder(int id_space, int words64, const uint64_t *rows, const uint32_t *vertices, int n_vertices)
+      : n_(n_vertices), id_space_(id_space), words_(words64), rows_(rows) {
+    view_.assign(vertices, vertices + n_vertices);
+  }
+
+  void add_edge(int a, int b) {  // owned storage only
     if (a == b || connected(a, b)) return;
     bits_[size_t(a) * words_ + (b >> 6)] |= 1ull << (b & 63);
     bits_[size_t(b) * words_ + (a >> 6)] |= 1ull << (a & 63);
-    ++degree_[size_t(a)];
-    ++degree_[size_t(b)];
   }
 
   int steps() const { return steps_; }  // search steps of the last find()
 
-  bool connected(int a, int b) const { return (bits_[size_t(a) * words_ + (b >> 6)] >> (b & 63)) & 1ull; }
+  bool connected(int a, int b) const { return (rows_[size_t(a) * words_ + (b >> 6)] >> (b & 63)) & 1ull; }
 
   // The gate's question (sac_model_registration_graph.h:260-265): would find(minimal_size) return MORE than
   // minimal_size vertices?  Same search, same answer, but it stops as soon as the answer is certain.
@@ -71,15 +75,18 @@ class CliqueFinder {
     minimal_ = minimal_size;
     steps_ = 1;
     ratio_limit_ = 0.025;
+    std::vector<int> order(static_cast<size_t>(n_));
+    if (view_.empty())
+      for (int i = 0; i < n_; ++i) order[size_t(i)] = i;
+    else
+      for (int i = 0; i < n_; ++i) order[size_t(i)] = int(view_[size_t(i)]);
+    sort_by_degree(order);  // leaves (degree inside the graph, vertex) ascending in pairs_
     {
       unsigned long long twice_edges = 0;
-      for (unsigned d : degree_) twice_edges += d;
+      for (const auto &pr : pairs_) twice_edges += pr.first;
       dense_ = 2ull * twice_edges > (unsigned long long)(n_) * (unsigned long long)(n_ - 1);
     }
-    std::vector<int> order(static_cast<size_t>(n_));
-    for (int i = 0; i < n_; ++i) order[size_t(i)] = i;
-    sort_by_degree(order);
-    const unsigned top = degree_[size_t(order[0])];
+    const unsigned top = pairs_.back().first;
     colour_.assign(size_t(n_), 0u);
     for (unsigned i = 0; i < top && i < unsigned(n_); ++i) colour_[i] = i + 1;
     for (unsigned i = top; i < unsigned(n_); ++i) colour_[i] = top + 1;
@@ -100,7 +107,7 @@ class CliqueFinder {
     for (int v : r) set_mask_[size_t(v) >> 6] |= 1ull << (v & 63);
     pairs_.resize(m);
     for (size_t i = 0; i < m; ++i) {
-      const uint64_t *row = bits_.data() + size_t(r[i]) * words_;
+      const uint64_t *row = rows_ + size_t(r[i]) * words_;
       unsigned d = 0;
       for (int w = 0; w < words_; ++w) d += unsigned(__builtin_popcountll(row[w] & set_mask_[size_t(w)]));
       pairs_[i] = std::make_pair(d, r[i]);
@@ -116,60 +123,38 @@ class CliqueFinder {
   void colour_sort(std::vector<int> &r) {
     const int gap = int(best_.size()) - int(current_.size()) + 1;
     const unsigned min_k = unsigned(std::max(1, gap));
+    if (dense_) {
+      colour_sort_dense(r, min_k);
+      return;
+    }
     size_t n_classes = 2;
     if (classes_.size() < 2) classes_.resize(2);
     classes_[0].clear();
     classes_[1].clear();
     set_mask_.assign(size_t(words_), 0ull);          // vertices already pushed into a class
-    if (class_of_.size() < size_t(n_)) class_of_.resize(size_t(n_));
+    if (class_of_.size() < size_t(id_space_)) class_of_.resize(size_t(id_space_));
     if (used_.size() < r.size() + 3) used_.resize(r.size() + 3, 0u);
-    if (count_.size() < r.size() + 3) count_.resize(r.size() + 3, 0u);
     size_t keep = 0;
     snapshot_.assign(r.begin(), r.end());
-    size_t first_empty = 1;  // smallest k >= 1 whose class has no member yet, or n_classes when there is none
     for (int p : snapshot_) {
-      const uint64_t *row = bits_.data() + size_t(p) * words_;
+      const uint64_t *row = rows_ + size_t(p) * words_;
       if (++stamp_ == 0u) {  // wrapped: start over with clean stamps
         std::fill(used_.begin(), used_.end(), 0u);
         stamp_ = 1u;
       }
-      size_t k;
-      if (!dense_) {
-        // walk p's already-coloured NEIGHBOURS and stamp their classes; first unstamped class wins
-        for (int w = 0; w < words_; ++w) {
-          uint64_t m = row[w] & set_mask_[size_t(w)];
-          while (m) {
-            const int v = w * 64 + __builtin_ctzll(m);
-            m &= m - 1;
-            used_[size_t(class_of_[size_t(v)])] = stamp_;
-          }
+      // walk p's already-coloured NEIGHBOURS and stamp their classes; first unstamped class wins
+      for (int w = 0; w < words_; ++w) {
+        uint64_t m = row[w] & set_mask_[size_t(w)];
+        while (m) {
+          const int v = w * 64 + __builtin_ctzll(m);
+          m &= m - 1;
+          used_[size_t(class_of_[size_t(v)])] = stamp_;
         }
-        k = 1;
-        while (used_[k] == stamp_) {
-          ++k;
-          if (k >= n_classes) break;
-        }
-      } else {
-        // dense graph: walk p's already-coloured NON-neighbours instead (far fewer) and count them per class — a
-        // class is free of neighbours of p exactly when all its members are non-neighbours; empty classes are free too
-        touched_.clear();
-        for (int w = 0; w < words_; ++w) {
-          uint64_t m = ~row[w] & set_mask_[size_t(w)];
-          while (m) {
-            const int v = w * 64 + __builtin_ctzll(m);
-            m &= m - 1;
-            const size_t c = size_t(class_of_[size_t(v)]);
-            if (used_[c] != stamp_) {
-              used_[c] = stamp_;
-              count_[c] = 0u;
-              touched_.push_back(int(c));
-            }
-            ++count_[c];
-          }
-        }
-        k = first_empty;
-        for (int c : touched_)
-          if (size_t(c) < k && count_[size_t(c)] == classes_[size_t(c)].size()) k = size_t(c);
+      }
+      size_t k = 1;
+      while (used_[k] == stamp_) {
+        ++k;
+        if (k >= n_classes) break;
       }
       if (k >= n_classes) {  // every existing class holds a neighbour of p: open a new one
         k = n_classes;
@@ -184,7 +169,6 @@ class CliqueFinder {
         class_of_[size_t(p)] = int(k);
         set_mask_[size_t(p) >> 6] |= 1ull << (p & 63);
       }
-      while (first_empty < n_classes && !classes_[first_empty].empty()) ++first_empty;
     }
     if (keep > 0) colour_[keep - 1] = 0;
     size_t pos = keep;
@@ -194,6 +178,83 @@ class CliqueFinder {
         colour_[pos] = unsigned(k);
         ++pos;
       }
+  }
+
+  // The same colouring for dense graphs (the inlier graphs of the gate are ~85 % dense), built CLASS BY CLASS on bit
+  // sets: class k = the uncoloured vertices, taken in the order of r, that have no neighbour among the members chosen
+  // before them.  That is exactly the class the sequential rule ("smallest class without a neighbour of p") gives
+  // every vertex: p lands in class k iff each earlier class already held a neighbour of p when p was reached, and
+  // class k did not.  One AND-NOT over the row per vertex instead of a walk over its coloured non-neighbours.
+  void colour_sort_dense(std::vector<int> &r, unsigned min_k) {
+    const size_t m = r.size();
+    if (m == 0) return;
+    if (min_k > 1) {
+      // classes below min_k never receive members (their vertices are only kept in front, ColorSort :245-248), so
+      // class 1 stays empty, every vertex gets k = 1 < min_k and R keeps its order
+      colour_[m - 1] = 0;
+      return;
+    }
+    if (rank_.size() < size_t(id_space_)) rank_.resize(size_t(id_space_));
+    snapshot_.assign(r.begin(), r.end());
+    set_mask_.assign(size_t(words_), 0ull);  // uncoloured vertices
+    for (size_t i = 0; i < m; ++i) {
+      const int v = snapshot_[i];
+      rank_[size_t(v)] = int(i);
+      set_mask_[size_t(v) >> 6] |= 1ull << (v & 63);
+    }
+    cand_.resize(size_t(words_));
+    size_t first = 0, pos = 0;
+    unsigned k = 0;
+    while (pos < m) {
+      ++k;
+      while (!((set_mask_[size_t(snapshot_[first]) >> 6] >> (snapshot_[first] & 63)) & 1ull)) ++first;
+      int v = snapshot_[first];
+      size_t at = first;  // position of the last member in the order
+      bool more = true;
+      for (bool first_member = true; more; first_member = false) {
+        // take v: out of the uncoloured set, into the class; the candidates lose v's neighbours
+        set_mask_[size_t(v) >> 6] &= ~(1ull << (v & 63));
+        r[pos] = v;
+        colour_[pos] = k;
+        ++pos;
+        const uint64_t *row = rows_ + size_t(v) * words_;
+        uint64_t any = 0;
+        if (first_member) {
+          for (int w = 0; w < words_; ++w) any |= (cand_[size_t(w)] = set_mask_[size_t(w)] & ~row[w]);
+        } else {
+          cand_[size_t(v) >> 6] &= ~(1ull << (v & 63));
+          for (int w = 0; w < words_; ++w) any |= (cand_[size_t(w)] &= ~row[w]);
+        }
+        if (!any) break;
+        // next member = the candidate that comes first in the order of r; it lies behind the last member.  Look a few
+        // positions ahead (a hit is likely while the candidate set is large), else take the minimum rank directly.
+        more = false;
+        const size_t lim = std::min(m, at + 1 + 12);
+        for (size_t i = at + 1; i < lim; ++i) {
+          const int u = snapshot_[i];
+          if ((cand_[size_t(u) >> 6] >> (u & 63)) & 1ull) {
+            v = u;
+            at = i;
+            more = true;
+            break;
+          }
+        }
+        if (!more) {
+          int best_rank = int(m);
+          for (int w = 0; w < words_; ++w) {
+            uint64_t x = cand_[size_t(w)];
+            while (x) {
+              const int u = w * 64 + __builtin_ctzll(x);
+              x &= x - 1;
+              if (rank_[size_t(u)] < best_rank) best_rank = rank_[size_t(u)];
+            }
+          }
+          v = snapshot_[size_t(best_rank)];
+          at = size_t(best_rank);
+          more = true;
+        }
+      }
+    }
   }
 
   unsigned colour_back() const {
@@ -251,11 +312,15 @@ class CliqueFinder {
   }
 
   bool decide_only_ = false, decided_ = false;
-  int n_;
+  int n_;         // vertices of the graph being searched
+  int id_space_;  // vertex ids are < id_space_ (== n_ unless this is a view)
   int words_;
+  const uint64_t *rows_ = nullptr;
+  std::vector<uint32_t> view_;
   std::vector<uint64_t> set_mask_;
-  std::vector<uint32_t> used_, count_;
-  std::vector<int> touched_;
+  std::vector<uint32_t> used_;
+  std::vector<int> rank_;
+  std::vector<uint64_t> cand_;
   bool dense_ = false;  // more than half of all vertex pairs are edges: colour_sort walks non-neighbours
   std::vector<int> class_of_;
   uint32_t stamp_ = 0u;
@@ -263,7 +328,6 @@ class CliqueFinder {
   std::vector<std::vector<int> > classes_;
   std::vector<int> snapshot_;
   std::vector<uint64_t> bits_;
-  std::vector<unsigned> degree_;
   std::vector<unsigned> colour_;
   long colour_size_ = 0;
   std::vector<unsigned> level_steps_, level_steps_old_;

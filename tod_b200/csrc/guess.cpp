@@ -362,7 +362,7 @@ inline bool have_bmi2() {
 #endif
 
 // The clique gate of selectWithinDistance (:203-268) on an inlier list of size > 7.  Returns true if the list stands.
-bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScratch &g) {
+bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScratch &g, bool proofs_done = false) {
   const size_t minimal = 7;  // std::min(best_inlier_number_, 7) with best_inlier_number_ >= 8 always (:85, :203)
   const int W = c.W;
   const Clock::time_point t0 = Clock::now();
@@ -382,11 +382,25 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
     if (reach > minimal) break;
   }
   if (reach <= minimal) return false;
+  const int nv = int(g.filtered.size());
+  ++g.calls;
+  if (2 * nv > c.n) {
+    // most of the cluster survives (one object fills the frame: thousands of vertices): search the cluster's own
+    // bit-rows through a view instead of compressing an induced copy.  No proofs here — K4 ran them where it could.
+    g.ms_setup += ms_since(t0);
+    const Clock::time_point ts = Clock::now();
+    tod::CliqueFinder finder(c.n, W / 2, reinterpret_cast<const uint64_t *>(c.S), g.filtered.data(), nv);
+    const bool ok = finder.finds_more_than(unsigned(minimal));
+    g.ms_search += ms_since(ts);
+    ++g.hist[size_bucket(nv)];
+    ++g.hist[18];
+    g.hist[19] += ok ? 1 : 0;
+    g.hist[20] += finder.steps();
+    return ok;
+  }
   // induced sample sub-graph on `filtered` (:241-255) as a dense nv x words bit-matrix: vertex a = a-th smallest
   // member of `filtered`, i.e. its rank inside the mask
-  const int nv = int(g.filtered.size());
   const int words = (nv + 31) / 32;
-  ++g.calls;
   g.rank.resize(size_t(W) + 1);
   g.rank[0] = 0;
   for (int w = 0; w < W; ++w) g.rank[size_t(w) + 1] = g.rank[size_t(w)] + popc32(g.mask[size_t(w)]);
@@ -404,11 +418,12 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
   }
   const Clock::time_point t1 = Clock::now();
   g.ms_setup += std::chrono::duration<double, std::milli>(t1 - t0).count();
-  const bool none = proves_no_clique(g, nv, words, int(minimal) + 1);
+  // (when K4 has already run the proofs on the GPU and could not settle the hypothesis, they are not repeated)
+  const bool none = proofs_done ? false : proves_no_clique(g, nv, words, int(minimal) + 1);
   const Clock::time_point t2 = Clock::now();
   g.ms_proof += std::chrono::duration<double, std::milli>(t2 - t1).count();
   ++g.hist[size_bucket(nv)];
-  ++g.hist[8 + size_bucket(g.last_core)];
+  if (!proofs_done) ++g.hist[8 + size_bucket(g.last_core)];
   if (none) {
     ++g.proved_empty;
     ++g.hist[g.last_core < int(minimal) + 1 ? 16 : 17];
@@ -945,8 +960,10 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
       // the best-so-far, so it may be evaluated ahead of the sequential scan.  Returns -1 on an internal error.
       auto evaluate = [&](Cluster *c, int h, ThreadScratch &sc) -> int {
         const int pre = batch_counts[size_t(c->batch_begin + h)];
+        bool proofs_done = false;
         if (inf_thr && pre > 7) {
           const uint8_t v = batch_verdict[size_t(c->batch_begin + h)];
+          proofs_done = c->W <= 128;  // K4 evaluates clusters of up to 4096 correspondences
           if (v == tod::kGateFails) {  // K4 proved that the gate clears this list
             sc.inliers.clear();
             ++sc.k4_fails;
@@ -969,7 +986,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
           sc.error = buf;
           return -1;
         }
-        if (sc.inliers.size() > 7 && !clique_gate(*c, sc.inliers, sc.gate)) {
+        if (sc.inliers.size() > 7 && !clique_gate(*c, sc.inliers, sc.gate, proofs_done)) {
           sc.inliers.clear();
           return 0;
         }

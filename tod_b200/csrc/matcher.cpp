@@ -46,6 +46,7 @@ struct tod_matcher {
   DeviceBuffer d_keys_local, d_keys_all;
   cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;  // around the all-gather of the last sharded call
   bool ev_x_valid = false;
+  bool stage_timing = false;         // tod_matcher_set_stage_timing: also bracket the exchange with events
   int32_t reserved_nq = 0;
 };
 
@@ -150,10 +151,10 @@ int run_process(tod_matcher *m, const void *d_query, int nq, tod_match *d_matche
   TOD_CUDA(m->d_keys_all.reserve(nk * sizeof(uint32_t) * size_t(m->p.shard_count)));
   if (int rc = run_k1(m, d_query, nq, st, &plan)) return rc;
   TOD_CUDA(tod::launch_reduce_keys(m->d_partial.as<uint32_t>(), plan.n_sources, nq, k, m->d_keys_local.as<uint32_t>(), st));
-  TOD_CUDA(cudaEventRecord(m->ev_x0, st));
+  if (m->stage_timing) TOD_CUDA(cudaEventRecord(m->ev_x0, st));
   TOD_NCCL(tod::nccl_api().AllGather(m->d_keys_local.ptr, m->d_keys_all.ptr, nk, tod::kNcclUint32, m->comm, st));
-  TOD_CUDA(cudaEventRecord(m->ev_x1, st));
-  m->ev_x_valid = true;
+  if (m->stage_timing) TOD_CUDA(cudaEventRecord(m->ev_x1, st));
+  m->ev_x_valid = m->stage_timing;
   return finalize(m, m->d_keys_all.as<uint32_t>(), m->p.shard_count, nq, d_matches, d_counts, d_points3d, st);
 }
 
@@ -465,6 +466,10 @@ int tod_matcher_set_comm(tod_matcher *m, const void *unique_id) {
   TOD_NCCL(api.CommInitRank(&m->comm, world, id, rank));
   m->comm_mode = 1;
   return TOD_OK;
+}
+
+void tod_matcher_set_stage_timing(tod_matcher *m, int32_t on) {
+  if (m) m->stage_timing = on != 0;
 }
 
 float tod_matcher_last_exchange_ms(const tod_matcher *m) {
