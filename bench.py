@@ -310,7 +310,8 @@ def pipeline_leg(args, descs, points, hbm_peak, hbm_src):
         frames.append(synth.make_frame(descs, points, vis, n_kp, height=H, width=W, seed=synth.BASE_SEED + 400 + f))
     q_all = np.ascontiguousarray(np.concatenate([f["descriptors"] for f in frames]))
     clouds = np.stack([f["cloud"] for f in frames])
-    kps = [f["keypoints_xy"] for f in frames]
+    # keypoints as the reference's feature cell hands them over: one cv::KeyPoint-shaped record each
+    kps = GuessGenerator.pack_keypoints([f["keypoints_xy"] for f in frames])
     m5 = DescriptorMatcher(search_json_params='{"type": "LSH", "radius": %d, "ratio": 0.8, "n_tables": 10, '
                                               '"key_size": 16, "multi_probe_level": 1}' % RADIUS)
     assert m5.k == K

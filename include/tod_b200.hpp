@@ -12,6 +12,7 @@
 #ifndef TOD_B200_HPP_
 #define TOD_B200_HPP_
 
+#include <algorithm>
 #include <cstdint>
 #include <map>
 #include <stdexcept>
@@ -162,7 +163,8 @@ class GuessGenerator {
     if (size_t(n) != matcher.counts().size()) throw std::runtime_error("keypoints and matches disagree in size");
     const std::vector<float> spans = matcher.spans_by_index();
     std::vector<tod_pose> poses(256);
-    std::vector<int32_t> inl(size_t(n) * 2 + 1);
+    // a keypoint can be an inlier of one pose per object it matched: at most min(k, n_objects) times
+    std::vector<int32_t> inl(size_t(n) * size_t(std::max<int32_t>(1, std::min<int32_t>(matcher.k(), int32_t(spans.size())))) + 1);
     int32_t n_poses = 0;
     check(tod_guess_process(h_, keypoints.data(), n, points3d, height, width, matcher.flat_matches().data(),
                             matcher.counts().data(), matcher.k(), matcher.flat_points3d().data(), spans.data(),

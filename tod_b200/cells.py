@@ -264,25 +264,36 @@ class GuessGenerator:
         return {"pose_results": poses, "Rs": poses["R"].reshape(-1, 3, 3).copy(), "Ts": poses["T"].copy(),
                 "inliers": inliers}
 
+    @staticmethod
+    def pack_keypoints(keypoints_list):
+        """Per-frame (n_f, 2) pixel coordinates (or KEYPOINT_DTYPE arrays) -> (one KEYPOINT_DTYPE array, int32 offsets):
+        the form tod_guess_process_batch takes.  A caller that already holds its keypoints as cv::KeyPoint-shaped
+        records (what the reference's feature cell emits) passes that tuple to process_batch directly."""
+        sizes = [a.shape[0] for a in keypoints_list]
+        off = np.zeros(len(sizes) + 1, np.int32)
+        np.cumsum(sizes, out=off[1:])
+        if keypoints_list and all(a.dtype == capi.KEYPOINT_DTYPE for a in keypoints_list):
+            return np.ascontiguousarray(np.concatenate(keypoints_list)), off
+        raw = np.zeros((int(off[-1]), 7), np.float32)             # x, y, size, angle, response, octave, class_id
+        if sizes:
+            raw[:, :2] = np.concatenate([np.asarray(a, np.float32).reshape(-1, 2) for a in keypoints_list])
+        return raw.view(capi.KEYPOINT_DTYPE).reshape(-1), off
+
     def process_batch(self, keypoints_list, clouds, matches, counts, matches_3d, spans_by_index, max_poses=None):
         """A batch of frames in one call (tod_guess_process_batch).  keypoints_list: per frame (n_f, 2) pixel coords or
-        KEYPOINT_DTYPE arrays; clouds: F x H x W x 3 f32; matches / counts / matches_3d: concatenated over the frames'
+        KEYPOINT_DTYPE arrays, or the tuple (KEYPOINT_DTYPE array of all frames, int32 offsets[F + 1]) from
+        pack_keypoints(); clouds: F x H x W x 3 f32; matches / counts / matches_3d: concatenated over the frames'
         keypoints (the matcher's output for the concatenated descriptors).  Returns a list of per-frame dicts like
         process()."""
-        kps = []
-        for kpf in keypoints_list:
-            if kpf.dtype != capi.KEYPOINT_DTYPE:
-                xy = np.asarray(kpf, np.float32).reshape(-1, 2)
-                kk = np.zeros(xy.shape[0], capi.KEYPOINT_DTYPE)
-                kk["x"], kk["y"] = xy[:, 0], xy[:, 1]
-                kps.append(kk)
-            else:
-                kps.append(np.ascontiguousarray(kpf))
-        off = np.concatenate([[0], np.cumsum([a.shape[0] for a in kps])]).astype(np.int32)
-        kp = np.ascontiguousarray(np.concatenate(kps)) if kps else np.zeros(0, capi.KEYPOINT_DTYPE)
+        if isinstance(keypoints_list, tuple):
+            kp, off = keypoints_list
+            assert kp.dtype == capi.KEYPOINT_DTYPE and kp.flags.c_contiguous
+            off = np.ascontiguousarray(off, np.int32)
+        else:
+            kp, off = self.pack_keypoints(keypoints_list)
         clouds = np.ascontiguousarray(clouds, np.float32)
         F, H, W = clouds.shape[0], clouds.shape[1], clouds.shape[2]
-        assert F == len(kps)
+        assert F == off.shape[0] - 1
         m = np.ascontiguousarray(matches)
         assert m.dtype == capi.MATCH_DTYPE and m.shape[0] == kp.shape[0]
         k = m.shape[1]
@@ -291,27 +302,28 @@ class GuessGenerator:
         sp = np.ascontiguousarray(spans_by_index, np.float32)
         if max_poses is None:
             max_poses = 64 * F
-        poses = np.zeros(max_poses, capi.POSE_DTYPE)
-        frames = np.zeros(max_poses, np.int32)
-        n_poses = ctypes.c_int32(0)
         cap = max(1, kp.shape[0] * max(1, min(k, sp.shape[0])))
-        inl = np.zeros(cap, np.int32)
+        key = (max_poses, cap)
+        if getattr(self, "_out_key", None) != key:               # output buffers are kept between calls
+            self._out = (np.zeros(max_poses, capi.POSE_DTYPE), np.zeros(max_poses, np.int32), np.zeros(cap, np.int32))
+            self._out_key = key
+        poses, frames, inl = self._out
+        n_poses = ctypes.c_int32(0)
         capi.check(self._lib.tod_guess_process_batch(self._h, F, capi._ptr(off), capi._ptr(kp), capi._ptr(clouds), H, W,
                                                      capi._ptr(m), capi._ptr(c), k, capi._ptr(p3), capi._ptr(sp),
                                                      sp.shape[0], capi._ptr(poses), capi._ptr(frames), max_poses,
                                                      ctypes.byref(n_poses), capi._ptr(inl), cap))
-        poses, frames = poses[:n_poses.value], frames[:n_poses.value]
-        out = [{"pose_results": [], "inliers": []} for _ in range(F)]
-        o = 0
-        for p, f in zip(poses, frames):
-            out[int(f)]["pose_results"].append(p)
-            out[int(f)]["inliers"].append(inl[o:o + int(p["n_inliers"])].copy())
-            o += int(p["n_inliers"])
-        for d in out:
-            pr = np.array(d["pose_results"], capi.POSE_DTYPE) if d["pose_results"] else np.zeros(0, capi.POSE_DTYPE)
-            d["pose_results"] = pr
-            d["Rs"] = pr["R"].reshape(-1, 3, 3).copy()
-            d["Ts"] = pr["T"].copy()
+        n = n_poses.value
+        poses, frames = poses[:n].copy(), frames[:n].copy()
+        ends = np.cumsum(poses["n_inliers"]) if n else np.zeros(0, np.int64)
+        starts = ends - poses["n_inliers"] if n else ends
+        first = np.searchsorted(frames, np.arange(F + 1))        # poses come out in frame order
+        out = []
+        for f in range(F):
+            lo, hi = int(first[f]), int(first[f + 1])
+            pr = poses[lo:hi]
+            out.append({"pose_results": pr, "Rs": pr["R"].reshape(-1, 3, 3), "Ts": pr["T"],
+                        "inliers": [inl[int(starts[i]):int(ends[i])].copy() for i in range(lo, hi)]})
         return out
 
     def last_stats(self):

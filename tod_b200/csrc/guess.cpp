@@ -456,8 +456,8 @@ void host_degree_mask(Cluster &c) {
 
 struct tod_guess {
   tod_guess_params p{};
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_k2 = nullptr, ev_S = nullptr, ev_P = nullptr;
   DeviceBuffer d_off, d_mo, d_q, d_t, d_px, d_sp, d_P, d_S, d_desc, d_valid, d_finite, d_hyps, d_counts, d_R, d_T;
   DeviceBuffer d_deg, d_active, d_floor, d_verdict;  // K4: degree masks, active-cluster list, per-cluster best, verdicts
   tod::PinnedBuffer h_P, h_S;  // host copies of the bit-matrices (read by the sampler and the gate)
@@ -551,6 +551,10 @@ int tod_guess_create(const tod_guess_params *p, tod_guess **out) {
   tod_guess *g = new tod_guess();
   g->p = *p;
   cudaError_t ce = cudaStreamCreate(&g->stream);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&g->ev_k2, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&g->ev_S, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&g->ev_P, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev1);
   if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev2);
@@ -574,6 +578,10 @@ void tod_guess_destroy(tod_guess *g) {
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->ev2) cudaEventDestroy(g->ev2);
   if (g->ev3) cudaEventDestroy(g->ev3);
+  if (g->ev_k2) cudaEventDestroy(g->ev_k2);
+  if (g->ev_S) cudaEventDestroy(g->ev_S);
+  if (g->ev_P) cudaEventDestroy(g->ev_P);
+  if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
   if (g->stream) cudaStreamDestroy(g->stream);
   g->h_P.release();
   g->h_S.release();
@@ -782,9 +790,17 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   TOD_CUDA(cudaEventRecord(g->ev1, st));
   TOD_CUDA(g->h_P.reserve(mat_words * 4));
   TOD_CUDA(g->h_S.reserve(mat_words * 4));
-  TOD_CUDA(cudaMemcpyAsync(g->h_P.ptr, g->d_P.ptr, mat_words * 4, cudaMemcpyDeviceToHost, st));
-  TOD_CUDA(cudaMemcpyAsync(g->h_S.ptr, g->d_S.ptr, mat_words * 4, cudaMemcpyDeviceToHost, st));
-  TOD_CUDA(cudaStreamSynchronize(st));
+  // The sample matrix comes back first (the sampler of round 0 needs it at once); the physical matrix follows on the
+  // copy stream while the first hypotheses are already being drawn and scored — the host reads it only when it builds
+  // the inlier list of a hypothesis that reaches the host gate.
+  TOD_CUDA(cudaEventRecord(g->ev_k2, st));
+  TOD_CUDA(cudaStreamWaitEvent(g->copy_stream, g->ev_k2, 0));
+  TOD_CUDA(cudaMemcpyAsync(g->h_S.ptr, g->d_S.ptr, mat_words * 4, cudaMemcpyDeviceToHost, g->copy_stream));
+  TOD_CUDA(cudaEventRecord(g->ev_S, g->copy_stream));
+  TOD_CUDA(cudaMemcpyAsync(g->h_P.ptr, g->d_P.ptr, mat_words * 4, cudaMemcpyDeviceToHost, g->copy_stream));
+  TOD_CUDA(cudaEventRecord(g->ev_P, g->copy_stream));
+  bool physical_on_host = false;
+  TOD_CUDA(cudaEventSynchronize(g->ev_S));
   TOD_CUDA(cudaEventElapsedTime(&g->k2_ms, g->ev0, g->ev1));
   for (Cluster *c : clusters) {
     c->P = g->h_P.as<uint32_t>() + c->matrix_offset;
@@ -954,6 +970,10 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
 
       // -- replay of computeModel's scan (ransac.h:95-135) + lazy clique gate ---------------------------------------------
       t_phase = Clock::now();
+      if (!physical_on_host) {
+        TOD_CUDA(cudaEventSynchronize(g->ev_P));
+        physical_on_host = true;
+      }
       std::atomic<int> more{0};
       // exact post-gate count of hypothesis h of cluster c (the gate keeps or zeroes the pre-gate count); the inlier
       // list is left in sc.inliers (cleared when the gate fails).  Depends only on h and the round's state, never on
@@ -1205,6 +1225,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     g->prof[4] += ms_since(t_phase);
   }
 
+  if (!physical_on_host) TOD_CUDA(cudaEventSynchronize(g->ev_P));  // nothing may still be in flight when we return
   // emission order of the reference: objects ascending (std::map), rounds in order (GuessGenerator.cpp:170-235);
   // `clusters` is already in ascending (frame, object) order and every cluster appended its rounds in order
   std::vector<Found> found;
