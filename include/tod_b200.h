@@ -319,7 +319,9 @@ void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_
 /* Shape of the clique gate's work in the last process call (24 counters): [0..7] gates that reached the induced
  * sub-graph stage by sub-graph size (buckets <= 16, 32, 64, 128, 256, 512, 1024, more), [8..15] the same by the size
  * of the sub-graph's 7-core, [16] settled because the core has fewer than 8 vertices, [17] settled by the colouring
- * bound, [18] bounded searches run, [19] of those, passes, [20] search steps summed; the rest reserved. */
+ * bound, [18] bounded searches run, [19] of those, passes, [20] search steps summed, [21] hypotheses the replay
+ * settled with a K4 "fails" verdict, [22] hypotheses K4 left undecided that the replay sent to the host search,
+ * [23] device time of the K4 launches in microseconds. */
 void tod_guess_last_gate_stats(const tod_guess *g, int64_t *out24);
 /* Algorithmic bytes (SURVEY.md §8d units) moved by the K2 launch (32 n in + two n x W bit-matrices out, summed over
  * the clusters) and by all K3 launches ((3 rows + 2 masks) x W x 4 + 140 per hypothesis) of the last process call,

@@ -112,23 +112,49 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
   for (int sweep = 0;; ++sweep) {
     if (sweep >= kMaxSweeps) return finish(kGateNeedsHost);
     int max_d = 0, removed = 0;
-    for (int w0 = 0; w0 < W; ++w0) {
-      uint32_t m = alive[w0];
-      uint32_t drop = 0;
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t *row = S + size_t(w0 * 32 + b) * W;
-        int d = 0;
-        for (int w = lane; w < W; w += 32) d += __popc(__ldg(row + w) & alive[w]);
-        d = __reduce_add_sync(0xffffffffu, d);
-        max_d = max(max_d, d);
-        if (d < 7) {
-          drop |= 1u << b;
-          ++removed;
+    for (int w = lane; w < W; w += 32) work[w] = 0u;  // vertices to drop after this sweep
+    __syncwarp();
+    // The live vertices are visited kBatch at a time: their rows are loaded together (kBatch independent loads in
+    // flight per lane and step) before the popcounts are reduced — the sweep is latency-bound on row loads otherwise.
+    constexpr int kBatch = 8;
+    int w0 = 0;
+    uint32_t m = alive[0];
+    for (;;) {
+      int vid[kBatch];
+      int nb = 0;
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        while (m == 0 && w0 + 1 < W) m = alive[++w0];
+        if (m) {
+          vid[j] = w0 * 32 + __ffs(m) - 1;
+          m &= m - 1;
+          nb = j + 1;
+        } else {
+          vid[j] = -1;
         }
       }
-      if (lane == 0) work[w0] = drop;
+      if (nb == 0) break;
+      int d[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) d[j] = 0;
+      for (int w = lane; w < W; w += 32) {
+        const uint32_t a = alive[w];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j)
+          if (vid[j] >= 0) d[j] += __popc(__ldg(S + size_t(vid[j]) * W + w) & a);
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        if (vid[j] >= 0) {
+          const int dj = __reduce_add_sync(0xffffffffu, d[j]);
+          max_d = max(max_d, dj);
+          if (dj < 7) {
+            ++removed;
+            if (lane == 0) work[vid[j] >> 5] |= 1u << (vid[j] & 31);
+          }
+        }
+      }
+      if (nb < kBatch) break;
     }
     // the reference scans for ONE filtered vertex with more than 7 sample-neighbours inside filtered
     if (sweep == 0 && max_d <= 7) return finish(kGateFails);
