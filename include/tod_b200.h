@@ -208,6 +208,39 @@ int tod_snapshot_object(const tod_snapshot *s, int32_t index, const char **objec
 int tod_matcher_load_snapshot(tod_matcher *m, const char *path);
 
 /* ================================================================================================================
+ * Feature stage in front of the hot path: what TodDetector wires before the DescriptorMatcher —
+ * ecto_opencv's FeatureDescriptor cell = cv::ORB (python/object_recognition_tod/detector.py:27,74;
+ * conf/detection.ork:23-31: n_features 5000, n_levels 3, scale_factor 1.2) and DepthTo3d (detector.py:62-69).
+ * This round: orientation + descriptors for keypoints that are already detected, and depth -> 3-D.  Bit-exact against
+ * cv2.ORB (angles as exact floats, descriptors bit for bit; tests/test_orb_gpu.py); detection itself (FAST + Harris)
+ * is not done here yet.  The descriptors stay in HBM: *d_descriptors can be handed to tod_matcher_knn_device.
+ * ============================================================================================================== */
+
+typedef struct tod_orb tod_orb;
+typedef struct tod_orb_params {
+  int32_t n_levels;     /* pyramid levels, default 3 (conf/detection.ork:27) */
+  float scale_factor;   /* default 1.2 (conf/detection.ork:28) */
+  int32_t device;
+  int32_t reserved;
+} tod_orb_params;
+
+void tod_orb_default_params(tod_orb_params *p);
+int tod_orb_create(const tod_orb_params *p, tod_orb **out);
+void tod_orb_destroy(tod_orb *o);
+/* image: height x width u8 (host).  keypoints (host): x, y in level-0 pixel coordinates and octave are read; with
+ * compute_angles != 0 the angle field (degrees) is overwritten with ORB's intensity-centroid orientation, else it is
+ * used as given.  Keypoints closer than 22 pixels to the border of their pyramid level are refused (cv::ORB drops
+ * them: edgeThreshold 31).  descriptors (host, n x 32 u8) may be NULL; *d_descriptors (may be NULL) receives the device
+ * pointer of the same n x 32 bytes, valid until the next call on this handle. */
+int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, tod_keypoint *keypoints,
+                     int32_t n, int32_t compute_angles, uint8_t *descriptors, const void **d_descriptors);
+/* DepthTo3d: depth = height x width float32 metres (NaN = invalid) or, with depth_is_u16, uint16 millimetres (0 =
+ * invalid); K = 3 x 3 row-major camera matrix (float); points3d = height x width x 3 f32 (host): x = (u - cx) z / fx,
+ * y = (v - cy) z / fy, z — NaN where the depth is invalid: the `points3d` input of the GuessGenerator. */
+int tod_depth_to_3d(int32_t device, const void *depth, int32_t depth_is_u16, int32_t height, int32_t width,
+                    const float *K, float *points3d);
+
+/* ================================================================================================================
  * Geometry stages (adjacency_ransac.cpp, sac_model_registration_graph.h) — exposed for parity tests and reuse
  * ============================================================================================================== */
 

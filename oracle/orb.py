@@ -1,0 +1,208 @@
+"""TEST INFRASTRUCTURE — CPU restatement (numpy) of the feature stage that precedes the hot path in the reference's
+detection pipeline (python/object_recognition_tod/detector.py:26-27, 62-75): ecto_opencv's FeatureDescriptor cell =
+cv::ORB (n_features 5000, n_levels 3, scale_factor 1.2 — conf/detection.ork:23-31) and DepthTo3d.  Only tests/,
+__graft_entry__.smoke() and bench.py's CPU legs may import this module.
+
+OpenCV is un-vendored (package.xml:12-22 names no version) and its sources are not in this image; the arithmetic
+below was established against the cv2 4.13.0 binary of this image, stage by stage, and is pinned by
+tests/test_orb_oracle.py (bit-exact against cv2.ORB on synthetic frames) and the committed golden vectors
+tests/golden/orb_*.npz (made by tests/golden/make_orb_golden.py):
+
+  pyramid     level l = resize(level l-1, INTER_LINEAR_EXACT) to cvRound(size / scale_l), scale_l = (float) 1.2f^l:
+              two passes with 8-bit fixed-point weights, (sum + 2^15) >> 16.
+  smoothing   GaussianBlur(7 x 7, sigma 2, BORDER_REFLECT_101) on a sub-matrix takes OpenCV's float separable filter:
+              row pass s = k0 x0, s = fma(x_j, k_j, s) left to right; column pass centre first, then
+              fma(x_{+j} + x_{-j}, k_j, s); round half to even.  (FMA = what cv2 does on an AVX2/FMA host.)
+  orientation intensity centroid over the radius-15 disc (umax table), fastAtan2's degree-7 polynomial WITHOUT
+              contraction, result in degrees.
+  descriptor  steered BRIEF: 256 comparisons of the smoothed level image at pattern points rotated by the angle
+              (cosf / sinf of angle * pi/180 in float, products and differences in float, cvRound = half to even);
+              pattern = oracle/orb_pattern.npy (recovered from cv2, tools/recover_orb_pattern.py).
+  depth -> 3D x = (u - cx) z / fx, y = (v - cy) z / fy, z = depth (metres; uint16 = millimetres, 0 = invalid -> NaN):
+              the published formula of cv::rgbd::depthTo3d, which this image's cv2 does not ship — parity unpinned for
+              this one function (checked against a float64 evaluation only).
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+
+F32 = np.float32
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PATTERN = np.load(os.path.join(_HERE, "orb_pattern.npy")).astype(np.int64)     # 256 x (x_a, y_a, x_b, y_b)
+HALF_PATCH = 15
+
+# cv::getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) normalised in double, stored as float
+_g = np.exp(-(np.arange(7) - 3.0) ** 2 / 8.0)
+GAUSS7 = (_g / _g.sum()).astype(F32)
+
+_libm = ctypes.CDLL("libm.so.6")
+_libm.cosf.restype = _libm.sinf.restype = ctypes.c_float
+_libm.cosf.argtypes = _libm.sinf.argtypes = [ctypes.c_float]
+
+
+def _fma(a, b, c):
+    """float32 fma(a, b, c) for arrays a, c and a scalar b (the product of two floats is exact in float64)."""
+    return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(F32)
+
+
+def level_scales(n_levels, scale_factor=1.2):
+    sf = float(F32(scale_factor))                      # the parameter travels as a float, pow runs in double
+    return [F32(sf ** l) for l in range(n_levels)]
+
+
+def level_sizes(height, width, n_levels, scale_factor=1.2):
+    sc = level_scales(n_levels, scale_factor)
+    return [(int(np.rint(F32(height) / s)), int(np.rint(F32(width) / s))) for s in sc]
+
+
+def linear_exact_table(src, dst):
+    """Source indices and 8-bit weights of cv::resize(INTER_LINEAR_EXACT) along one axis."""
+    scale = 1.0 / (dst / src)
+    x = (np.arange(dst) + 0.5) * scale - 0.5
+    ix = np.floor(x).astype(np.int64)
+    f = np.floor((x - ix) * 256 + 0.5).astype(np.int64)
+    return np.clip(ix, 0, src - 1), np.clip(ix + 1, 0, src - 1), f
+
+
+def resize_linear_exact(img, dh, dw):
+    sh, sw = img.shape
+    x0, x1, fx = linear_exact_table(sw, dw)
+    y0, y1, fy = linear_exact_table(sh, dh)
+    im = img.astype(np.int64)
+    h = im[:, x0] * (256 - fx)[None, :] + im[:, x1] * fx[None, :]
+    v = h[y0, :] * (256 - fy)[:, None] + h[y1, :] * fy[:, None]
+    return ((v + (1 << 15)) >> 16).astype(np.uint8)
+
+
+def pyramid(img, n_levels=3, scale_factor=1.2):
+    levels = [np.ascontiguousarray(img, np.uint8)]
+    for l, (h, w) in enumerate(level_sizes(img.shape[0], img.shape[1], n_levels, scale_factor)):
+        if l:
+            levels.append(resize_linear_exact(levels[-1], h, w))
+    return levels
+
+
+def smooth(img):
+    h_, w_ = img.shape
+    p = np.pad(img, ((0, 0), (3, 3)), mode="reflect").astype(F32)
+    s = (p[:, 0:w_] * GAUSS7[0]).astype(F32)
+    for j in range(1, 7):
+        s = _fma(p[:, j:j + w_], GAUSS7[j], s)
+    q = np.pad(s, ((3, 3), (0, 0)), mode="reflect")
+    v = (q[3:3 + h_] * GAUSS7[3]).astype(F32)
+    for k in (1, 2, 3):
+        v = _fma((q[3 + k:3 + k + h_] + q[3 - k:3 - k + h_]).astype(F32), GAUSS7[3 + k], v)
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def umax_table(hp=HALF_PATCH):
+    umax = [0] * (hp + 2)
+    vmax = int(math.floor(hp * math.sqrt(2.0) / 2 + 1))
+    vmin = int(math.ceil(hp * math.sqrt(2.0) / 2))
+    for v in range(vmax + 1):
+        umax[v] = int(np.rint(math.sqrt(float(hp * hp - v * v))))
+    v0 = 0
+    for v in range(hp, vmin - 1, -1):
+        while umax[v0] == umax[v0 + 1]:
+            v0 += 1
+        umax[v] = v0
+        v0 += 1
+    return umax[:hp + 1]
+
+
+UMAX = umax_table()
+_P1 = F32(0.9997878412794807) * F32(180 / np.pi)
+_P3 = F32(-0.3258083974640975) * F32(180 / np.pi)
+_P5 = F32(0.1555786518463281) * F32(180 / np.pi)
+_P7 = F32(-0.04432655554792128) * F32(180 / np.pi)
+_EPS = F32(2.220446049250313e-16)
+
+
+def fast_atan2(y, x):
+    """cv::fastAtan2 (degrees, [0, 360)): scalar float arithmetic, no contraction."""
+    y, x = F32(y), F32(x)
+    ax, ay = abs(x), abs(y)
+
+    def poly(c):
+        c2 = F32(c * c)
+        r = F32(F32(_P7 * c2) + _P5)
+        r = F32(F32(r * c2) + _P3)
+        r = F32(F32(r * c2) + _P1)
+        return F32(r * c)
+    if ax >= ay:
+        a = poly(F32(ay / F32(ax + _EPS)))
+    else:
+        a = F32(F32(90.0) - poly(F32(ax / F32(ay + _EPS))))
+    if x < 0:
+        a = F32(F32(180.0) - a)
+    if y < 0:
+        a = F32(F32(360.0) - a)
+    return a
+
+
+def level_center(x, y, scale):
+    inv = F32(1.0) / scale
+    return int(np.rint(F32(x) * inv)), int(np.rint(F32(y) * inv))
+
+
+def ic_angle(level_img, cx, cy):
+    """Orientation of the patch centred at (cx, cy) of an UNSMOOTHED pyramid level."""
+    m01 = m10 = 0
+    row = level_img[cy].astype(np.int64)
+    u = np.arange(-HALF_PATCH, HALF_PATCH + 1)
+    m10 += int((u * row[cx - HALF_PATCH:cx + HALF_PATCH + 1]).sum())
+    for v in range(1, HALF_PATCH + 1):
+        d = UMAX[v]
+        uu = np.arange(-d, d + 1)
+        vp = level_img[cy + v, cx - d:cx + d + 1].astype(np.int64)
+        vm = level_img[cy - v, cx - d:cx + d + 1].astype(np.int64)
+        m10 += int((uu * (vp + vm)).sum())
+        m01 += v * int((vp - vm).sum())
+    return fast_atan2(m01, m10)
+
+
+def describe(img, xs, ys, octaves, angles=None, n_levels=3, scale_factor=1.2):
+    """Angles (computed when `angles` is None) and 32-byte descriptors of keypoints given in level-0 coordinates."""
+    levels = pyramid(img, n_levels, scale_factor)
+    sc = level_scales(n_levels, scale_factor)
+    smoothed = [smooth(l) for l in levels]
+    n = len(xs)
+    out_angles = np.zeros(n, F32)
+    desc = np.zeros((n, 32), np.uint8)
+    px = PATTERN[:, [0, 2]].reshape(-1).astype(F32)        # a0, b0, a1, b1, ...
+    py = PATTERN[:, [1, 3]].reshape(-1).astype(F32)
+    for i in range(n):
+        l = int(octaves[i])
+        cx, cy = level_center(xs[i], ys[i], sc[l])
+        ang = ic_angle(levels[l], cx, cy) if angles is None else F32(angles[i])
+        out_angles[i] = ang
+        rad = F32(ang * F32(np.pi / 180.0))
+        a, b = F32(_libm.cosf(rad)), F32(_libm.sinf(rad))
+        x = ((px * a).astype(F32) - (py * b).astype(F32)).astype(F32)
+        y = ((px * b).astype(F32) + (py * a).astype(F32)).astype(F32)
+        ix, iy = np.rint(x).astype(np.int64), np.rint(y).astype(np.int64)
+        v = smoothed[l][cy + iy, cx + ix]
+        desc[i] = np.packbits((v[0::2] < v[1::2]).astype(np.uint8), bitorder="little")
+    return out_angles, desc
+
+
+def depth_to_3d(depth, K):
+    """H x W x 3 float32 point image from a depth image (float32 metres, or uint16 millimetres) and the 3 x 3 camera
+    matrix K: the cell detector.py:62-69 wires in front of the GuessGenerator.  Invalid depth (NaN, or 0 for uint16)
+    -> NaN point."""
+    K = np.asarray(K, np.float64).reshape(3, 3)
+    fx, fy, cx, cy = F32(K[0, 0]), F32(K[1, 1]), F32(K[0, 2]), F32(K[1, 2])
+    if depth.dtype == np.uint16:
+        z = np.where(depth == 0, np.nan, depth.astype(F32) * F32(0.001)).astype(F32)
+    else:
+        z = depth.astype(F32)
+    h, w = z.shape
+    u = np.arange(w, dtype=F32)[None, :]
+    v = np.arange(h, dtype=F32)[:, None]
+    x = ((u - cx).astype(F32) * z).astype(F32) / fx
+    y = ((v - cy).astype(F32) * z).astype(F32) / fy
+    out = np.stack([x.astype(F32), y.astype(F32), z], axis=2)
+    out[np.isnan(z)] = np.nan
+    return out

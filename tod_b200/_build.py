@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
           "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall"]
 # per-file extra flags: the adjacency kernel must not contract mul+add into FMA (bit-exact vs the reference's x86 code)
-EXTRA = {"k2_adjacency.cu": ["--fmad=false"], "k3_score.cu": ["--fmad=false"]}
+EXTRA = {"k2_adjacency.cu": ["--fmad=false"], "k3_score.cu": ["--fmad=false"], "orb.cu": ["--fmad=false"]}
 
 
 def sources():

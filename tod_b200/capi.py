@@ -35,6 +35,11 @@ class GuessParams(ctypes.Structure):
                 ("seed", ctypes.c_uint64), ("host_threads", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
+class OrbParams(ctypes.Structure):
+    _fields_ = [("n_levels", ctypes.c_int32), ("scale_factor", ctypes.c_float), ("device", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
 class TodError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("tod_b200 error %d: %s" % (code, msg))
@@ -85,6 +90,11 @@ SIGNATURES = [
     ("tod_snapshot_object", ctypes.c_int, [_P, _I32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_P),
                                            ctypes.POINTER(_P), ctypes.POINTER(_I32), ctypes.POINTER(_F)]),
     ("tod_matcher_load_snapshot", ctypes.c_int, [_P, ctypes.c_char_p]),
+    ("tod_orb_default_params", None, [ctypes.POINTER(OrbParams)]),
+    ("tod_orb_create", ctypes.c_int, [ctypes.POINTER(OrbParams), ctypes.POINTER(_P)]),
+    ("tod_orb_destroy", None, [_P]),
+    ("tod_orb_describe", ctypes.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _P, ctypes.POINTER(_P)]),
+    ("tod_depth_to_3d", ctypes.c_int, [_I32, _P, _I32, _I32, _I32, _P, _P]),
     ("tod_adjacency_row_words", _I32, [_I32]),
     ("tod_fill_adjacency", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _F, _P, _P, _P]),
     ("tod_score_hypotheses", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _I32, _P, _D, _P, _P, _P]),

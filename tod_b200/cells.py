@@ -351,6 +351,55 @@ class GuessGenerator:
                 "gate_thread_ms": {"setup": prof[8], "proof": prof[9], "search": prof[10]}}
 
 
+class FeatureDescriptor:
+    """The describe half of ecto_opencv's FeatureDescriptor cell (cv::ORB, detector.py:27,74; conf/detection.ork:23-31)
+    on the GPU: pyramid, smoothing, orientation and rBRIEF descriptors for keypoints that are already detected —
+    bit-exact against cv2.ORB.  The descriptors also stay on the device (`last_device_descriptors`) for
+    DescriptorMatcher.process_device."""
+
+    def __init__(self, n_levels=3, scale_factor=1.2, device=0):
+        lib = capi.load()
+        p = capi.OrbParams()
+        lib.tod_orb_default_params(ctypes.byref(p))
+        p.n_levels, p.scale_factor, p.device = int(n_levels), float(scale_factor), int(device)
+        self._h = ctypes.c_void_p()
+        capi.check(lib.tod_orb_create(ctypes.byref(p), ctypes.byref(self._h)))
+        self._lib = lib
+        self.last_device_descriptors = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tod_orb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def describe(self, image, keypoints, compute_angles=True):
+        """image: H x W u8; keypoints: KEYPOINT_DTYPE array (x, y, octave read; angle written when compute_angles).
+        Returns (keypoints, descriptors[n, 32] u8)."""
+        img = np.ascontiguousarray(image, np.uint8)
+        kp = np.ascontiguousarray(keypoints).copy()
+        assert kp.dtype == capi.KEYPOINT_DTYPE and img.ndim == 2
+        desc = np.zeros((kp.shape[0], 32), np.uint8)
+        dptr = ctypes.c_void_p()
+        capi.check(self._lib.tod_orb_describe(self._h, capi._ptr(img), img.shape[0], img.shape[1], capi._ptr(kp),
+                                              kp.shape[0], 1 if compute_angles else 0, capi._ptr(desc),
+                                              ctypes.byref(dptr)))
+        self.last_device_descriptors = dptr.value
+        return kp, desc
+
+
+def depth_to_3d(depth, K, device=0):
+    """DepthTo3d (detector.py:62-69) on the GPU: depth H x W float32 metres or uint16 millimetres -> H x W x 3 f32."""
+    d = np.ascontiguousarray(depth)
+    assert d.dtype in (np.float32, np.uint16) and d.ndim == 2
+    k = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
+    out = np.empty((d.shape[0], d.shape[1], 3), np.float32)
+    capi.check(capi.load().tod_depth_to_3d(int(device), capi._ptr(d), 1 if d.dtype == np.uint16 else 0, d.shape[0],
+                                           d.shape[1], capi._ptr(k), capi._ptr(out)))
+    return out
+
+
 # ---- the `.ork` pipeline parameters, as TodDetector forwards them (python/object_recognition_tod/detector.py:34-62) ----
 def ork_parameters(parameters):
     """`parameters` = the `pipelineN.parameters` subtree of a detection `.ork` file (conf/detection.ork:21-46) as a

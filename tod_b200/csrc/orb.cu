@@ -1,0 +1,410 @@
+// Feature stage in front of the hot path: ORB orientation + descriptors and depth -> 3-D on the
+// GPU, so that the descriptors K1 consumes never leave HBM.
+//
+// Replaces, for keypoints that are already detected, the `FeatureDescriptor` cell (cv::ORB, n_features 5000, n_levels 3,
+// scale_factor 1.2 — python/object_recognition_tod/detector.py:27,74; conf/detection.ork:23-31) and the `DepthTo3d`
+// cell (detector.py:62-69).  OpenCV is un-vendored; the arithmetic follows oracle/orb.py, which restates what the
+// cv2 4.13.0 binary does, stage by stage, and is pinned bit for bit against it (tests/test_orb_oracle.py):
+//   pyramid      INTER_LINEAR_EXACT: two passes with 8-bit fixed-point weights (tables built on the host in double)
+//   smoothing    7 x 7 Gaussian, sigma 2, BORDER_REFLECT_101, OpenCV's float separable filter: row pass an FMA chain
+//                left to right, column pass centre first then fma(x[+j] + x[-j], k[j], s); round half to even
+//   orientation  intensity centroid over the radius-15 disc, cv::fastAtan2's polynomial without contraction
+//   descriptor   steered BRIEF, 256 comparisons at pattern points rotated by the angle (float products, cvRound)
+// Every float operation that decides a bit is written with explicit rounding intrinsics (__fmul_rn / __fadd_rn /
+// __fmaf_rn): the compiler may neither fuse nor split them.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "orb_pattern.h"
+#include "tod_internal.h"
+
+namespace tod {
+namespace {
+
+constexpr int kHalfPatch = 15;
+constexpr int kMaxLevels = 8;
+constexpr int kDescBorder = 22;  // the rotated pattern reaches ceil(15 * sqrt(2)) pixels from the centre
+
+__constant__ signed char c_pattern[256][4];
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+// cv::getGaussianKernel(7, 2, CV_32F): centre, +-1, +-2, +-3
+__constant__ float c_gauss[4] = {0x1.ba95cp-3f, 0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+__global__ void __launch_bounds__(256)
+resize_exact_kernel(const uint8_t *__restrict__ src, int sw, uint8_t *__restrict__ dst, int dw, int dh,
+                    const int *__restrict__ x0, const int *__restrict__ x1, const int *__restrict__ fx,
+                    const int *__restrict__ y0, const int *__restrict__ y1, const int *__restrict__ fy) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw || y >= dh) return;
+  const int a0 = x0[x], a1 = x1[x], wx = fx[x], b0 = y0[y], b1 = y1[y], wy = fy[y];
+  const int h0 = int(src[size_t(b0) * sw + a0]) * (256 - wx) + int(src[size_t(b0) * sw + a1]) * wx;
+  const int h1 = int(src[size_t(b1) * sw + a0]) * (256 - wx) + int(src[size_t(b1) * sw + a1]) * wx;
+  dst[size_t(y) * dw + x] = uint8_t((h0 * (256 - wy) + h1 * wy + (1 << 15)) >> 16);
+}
+
+__global__ void __launch_bounds__(256)
+smooth_rows_kernel(const uint8_t *__restrict__ src, int w, int h, float *__restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const uint8_t *row = src + size_t(y) * w;
+  // s = k[0] x[0]; s = fma(x[j], k[j], s), taps left to right (k[0] = the +-3 coefficient)
+  const float k3 = c_gauss[3], k2 = c_gauss[2], k1 = c_gauss[1], k0 = c_gauss[0];
+  float s = __fmul_rn(float(row[reflect101(x - 3, w)]), k3);
+  s = __fmaf_rn(float(row[reflect101(x - 2, w)]), k2, s);
+  s = __fmaf_rn(float(row[reflect101(x - 1, w)]), k1, s);
+  s = __fmaf_rn(float(row[x]), k0, s);
+  s = __fmaf_rn(float(row[reflect101(x + 1, w)]), k1, s);
+  s = __fmaf_rn(float(row[reflect101(x + 2, w)]), k2, s);
+  s = __fmaf_rn(float(row[reflect101(x + 3, w)]), k3, s);
+  out[size_t(y) * w + x] = s;
+}
+
+__global__ void __launch_bounds__(256)
+smooth_cols_kernel(const float *__restrict__ src, int w, int h, uint8_t *__restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  float s = __fmul_rn(src[size_t(y) * w + x], c_gauss[0]);
+#pragma unroll
+  for (int j = 1; j <= 3; ++j) {
+    const float a = src[size_t(reflect101(y + j, h)) * w + x], b = src[size_t(reflect101(y - j, h)) * w + x];
+    s = __fmaf_rn(__fadd_rn(a, b), c_gauss[j], s);
+  }
+  out[size_t(y) * w + x] = uint8_t(min(255, max(0, __float2int_rn(s))));
+}
+
+struct LevelDesc {
+  const uint8_t *img;     // unsmoothed level
+  const uint8_t *smooth;  // smoothed level
+  int w, h;
+  float inv_scale;        // 1.f / layerScale
+};
+struct Levels {
+  LevelDesc l[kMaxLevels];
+};
+
+// cv::fastAtan2 (degrees), operation by operation
+__device__ float fast_atan2_deg(float y, float x) {
+  const float p1 = 0x1.ca44dep+5f, p3 = -0x1.2aaddcp+4f, p5 = 0x1.1d3f7ep+3f, p7 = -0x1.4515b2p+1f;
+  const float eps = 0x1p-52f;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a;
+  if (ax >= ay) {
+    const float c = __fdiv_rn(ay, __fadd_rn(ax, eps)), c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    const float c = __fdiv_rn(ax, __fadd_rn(ay, eps)), c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2),
+                                            p1), c));
+  }
+  if (x < 0.f) a = __fsub_rn(180.f, a);
+  if (y < 0.f) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// One warp per keypoint: lane v sums row +-v of the disc (integers, exact), lane 0 turns the moments into the angle.
+__global__ void __launch_bounds__(256)
+orb_angle_kernel(Levels lv, const float *__restrict__ kx, const float *__restrict__ ky, const int *__restrict__ octave,
+                 int n, float *__restrict__ angle) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const LevelDesc L = lv.l[octave[i]];
+  const int cx = __float2int_rn(__fmul_rn(kx[i], L.inv_scale)), cy = __float2int_rn(__fmul_rn(ky[i], L.inv_scale));
+  int m10 = 0, m01 = 0;
+  if (lane <= kHalfPatch) {
+    const int v = lane, d = c_umax[v];
+    const uint8_t *rp = L.img + size_t(cy + v) * L.w + cx, *rm = L.img + size_t(cy - v) * L.w + cx;
+    if (v == 0) {
+      for (int u = -kHalfPatch; u <= kHalfPatch; ++u) m10 += u * int(rp[u]);
+    } else {
+      int vs = 0;
+      for (int u = -d; u <= d; ++u) {
+        const int p = rp[u], q = rm[u];
+        vs += p - q;
+        m10 += u * (p + q);
+      }
+      m01 = v * vs;
+    }
+  }
+  m10 = __reduce_add_sync(0xffffffffu, m10);
+  m01 = __reduce_add_sync(0xffffffffu, m01);
+  if (lane == 0) angle[i] = fast_atan2_deg(float(m01), float(m10));
+}
+
+// One warp per keypoint, one descriptor byte per lane.
+__global__ void __launch_bounds__(256)
+orb_describe_kernel(Levels lv, const float *__restrict__ kx, const float *__restrict__ ky,
+                    const int *__restrict__ octave, const float *__restrict__ angle, int n,
+                    uint8_t *__restrict__ desc) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const LevelDesc L = lv.l[octave[i]];
+  const int cx = __float2int_rn(__fmul_rn(kx[i], L.inv_scale)), cy = __float2int_rn(__fmul_rn(ky[i], L.inv_scale));
+  // a = cosf(angle * pi/180), b = sinf(...): evaluated in double and rounded once, which is the correctly rounded
+  // float — what the host libm returns
+  const float rad = __fmul_rn(angle[i], 0x1.1df46ap-6f);
+  const float a = float(cos(double(rad))), b = float(sin(double(rad)));
+  const uint8_t *center = L.smooth + size_t(cy) * L.w + cx;
+  unsigned byte = 0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const signed char *p = c_pattern[lane * 8 + t];
+    const float xa = p[0], ya = p[1], xb = p[2], yb = p[3];
+    const int ixa = __float2int_rn(__fsub_rn(__fmul_rn(xa, a), __fmul_rn(ya, b)));
+    const int iya = __float2int_rn(__fadd_rn(__fmul_rn(xa, b), __fmul_rn(ya, a)));
+    const int ixb = __float2int_rn(__fsub_rn(__fmul_rn(xb, a), __fmul_rn(yb, b)));
+    const int iyb = __float2int_rn(__fadd_rn(__fmul_rn(xb, b), __fmul_rn(yb, a)));
+    const int va = center[iya * L.w + ixa], vb = center[iyb * L.w + ixb];
+    byte |= unsigned(va < vb) << t;
+  }
+  desc[size_t(i) * 32 + lane] = uint8_t(byte);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+depth_to_3d_kernel(const T *__restrict__ depth, int w, int h, float fx, float fy, float cx, float cy,
+                   float *__restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  float z;
+  if (sizeof(T) == 2) {
+    const unsigned d = unsigned(depth[size_t(y) * w + x]);
+    z = d == 0 ? __int_as_float(0x7fc00000) : __fmul_rn(float(d), 0.001f);
+  } else {
+    z = float(depth[size_t(y) * w + x]);
+  }
+  float *o = out + (size_t(y) * w + x) * 3;
+  if (isnan(z)) {
+    o[0] = o[1] = o[2] = __int_as_float(0x7fc00000);
+    return;
+  }
+  o[0] = __fdiv_rn(__fmul_rn(__fsub_rn(float(x), cx), z), fx);
+  o[1] = __fdiv_rn(__fmul_rn(__fsub_rn(float(y), cy), z), fy);
+  o[2] = z;
+}
+
+void linear_exact_table(int src, int dst, std::vector<int> &i0, std::vector<int> &i1, std::vector<int> &f) {
+  i0.resize(size_t(dst));
+  i1.resize(size_t(dst));
+  f.resize(size_t(dst));
+  const double scale = 1.0 / (double(dst) / double(src));
+  for (int i = 0; i < dst; ++i) {
+    const double x = (double(i) + 0.5) * scale - 0.5;
+    const double fl = std::floor(x);
+    const int ix = int(fl);
+    f[size_t(i)] = int(std::floor((x - fl) * 256.0 + 0.5));
+    i0[size_t(i)] = std::min(std::max(ix, 0), src - 1);
+    i1[size_t(i)] = std::min(std::max(ix + 1, 0), src - 1);
+  }
+}
+
+}  // namespace
+}  // namespace tod
+
+using tod::DeviceBuffer;
+using tod::fail;
+
+struct tod_orb {
+  tod_orb_params p{};
+  cudaStream_t stream = nullptr;
+  int height = 0, width = 0;  // geometry the pyramid buffers are built for
+  int lw[tod::kMaxLevels] = {0}, lh[tod::kMaxLevels] = {0};
+  float scale[tod::kMaxLevels] = {0};
+  DeviceBuffer d_img[tod::kMaxLevels], d_smooth[tod::kMaxLevels], d_rowf, d_tables[tod::kMaxLevels];
+  DeviceBuffer d_kx, d_ky, d_oct, d_angle, d_desc;
+  bool pattern_uploaded = false;
+};
+
+extern "C" {
+
+void tod_orb_default_params(tod_orb_params *p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->n_levels = 3;          // conf/detection.ork:27
+  p->scale_factor = 1.2f;   // conf/detection.ork:28
+  p->device = 0;
+}
+
+int tod_orb_create(const tod_orb_params *p, tod_orb **out) {
+  TOD_REQUIRE(p && out, "null argument");
+  TOD_REQUIRE(p->n_levels >= 1 && p->n_levels <= tod::kMaxLevels, "n_levels must be in 1..%d", tod::kMaxLevels);
+  TOD_REQUIRE(p->scale_factor > 1.0f, "scale_factor must exceed 1");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return fail(TOD_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  TOD_REQUIRE(p->device >= 0 && p->device < n_dev, "device %d out of range (%d devices)", p->device, n_dev);
+  TOD_CUDA(cudaSetDevice(p->device));
+  tod_orb *o = new tod_orb();
+  o->p = *p;
+  if (cudaStreamCreate(&o->stream) != cudaSuccess) {
+    delete o;
+    return fail(TOD_ERR_CUDA, "creating the ORB stage's stream failed");
+  }
+  *out = o;
+  return TOD_OK;
+}
+
+void tod_orb_destroy(tod_orb *o) {
+  if (!o) return;
+  cudaSetDevice(o->p.device);
+  for (int l = 0; l < tod::kMaxLevels; ++l) {
+    o->d_img[l].release();
+    o->d_smooth[l].release();
+    o->d_tables[l].release();
+  }
+  for (DeviceBuffer *b : {&o->d_rowf, &o->d_kx, &o->d_ky, &o->d_oct, &o->d_angle, &o->d_desc}) b->release();
+  if (o->stream) cudaStreamDestroy(o->stream);
+  delete o;
+}
+
+int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, tod_keypoint *keypoints,
+                     int32_t n, int32_t compute_angles, uint8_t *descriptors, const void **d_descriptors) {
+  TOD_REQUIRE(o && image && (keypoints || n == 0), "null argument");
+  TOD_REQUIRE(height > 2 * tod::kDescBorder && width > 2 * tod::kDescBorder && n >= 0, "bad sizes");
+  TOD_CUDA(cudaSetDevice(o->p.device));
+  cudaStream_t st = o->stream;
+  const int L = o->p.n_levels;
+  if (!o->pattern_uploaded) {
+    TOD_CUDA(cudaMemcpyToSymbol(tod::c_pattern, tod::kOrbPattern, sizeof(tod::kOrbPattern)));
+    o->pattern_uploaded = true;
+  }
+  if (height != o->height || width != o->width) {
+    // level geometry: scale_l = (float) pow((double) scale_factor, l); size = cvRound(size0 / scale_l)
+    for (int l = 0; l < L; ++l) {
+      o->scale[l] = float(std::pow(double(o->p.scale_factor), double(l)));
+      o->lw[l] = int(std::lrintf(float(width) / o->scale[l]));
+      o->lh[l] = int(std::lrintf(float(height) / o->scale[l]));
+      TOD_REQUIRE(o->lw[l] > 2 * tod::kDescBorder && o->lh[l] > 2 * tod::kDescBorder, "image too small for level %d", l);
+      const size_t px = size_t(o->lw[l]) * size_t(o->lh[l]);
+      TOD_CUDA(o->d_img[l].reserve(px));
+      TOD_CUDA(o->d_smooth[l].reserve(px));
+      if (l) {  // INTER_LINEAR_EXACT tables from level l-1: x0 x1 fx (lw) y0 y1 fy (lh), all int32
+        std::vector<int> a0, a1, af, b0, b1, bf, all;
+        tod::linear_exact_table(o->lw[l - 1], o->lw[l], a0, a1, af);
+        tod::linear_exact_table(o->lh[l - 1], o->lh[l], b0, b1, bf);
+        for (auto *v : {&a0, &a1, &af, &b0, &b1, &bf}) all.insert(all.end(), v->begin(), v->end());
+        TOD_CUDA(o->d_tables[l].reserve(all.size() * sizeof(int)));
+        TOD_CUDA(cudaMemcpyAsync(o->d_tables[l].ptr, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        TOD_CUDA(cudaStreamSynchronize(st));  // `all` dies at the end of this block
+      }
+    }
+    TOD_CUDA(o->d_rowf.reserve(size_t(width) * size_t(height) * sizeof(float)));
+    o->height = height;
+    o->width = width;
+  }
+  // keypoints: level-0 coordinates and octave; every pattern / disc access must stay inside its level
+  std::vector<float> hx(static_cast<size_t>(n)), hy(static_cast<size_t>(n)), ha(static_cast<size_t>(n));
+  std::vector<int> ho(static_cast<size_t>(n));
+  for (int i = 0; i < n; ++i) {
+    const tod_keypoint &k = keypoints[i];
+    TOD_REQUIRE(k.octave >= 0 && k.octave < L, "keypoint %d: octave %d outside [0, %d)", i, k.octave, L);
+    const float inv = 1.f / o->scale[k.octave];
+    const long cx = std::lrintf(k.x * inv), cy = std::lrintf(k.y * inv);
+    TOD_REQUIRE(cx >= tod::kDescBorder && cy >= tod::kDescBorder && cx < o->lw[k.octave] - tod::kDescBorder &&
+                    cy < o->lh[k.octave] - tod::kDescBorder,
+                "keypoint %d at (%g, %g) octave %d is closer than %d pixels to the border of its level (cv::ORB drops "
+                "such keypoints: edgeThreshold)", i, k.x, k.y, k.octave, tod::kDescBorder);
+    hx[size_t(i)] = k.x;
+    hy[size_t(i)] = k.y;
+    ho[size_t(i)] = k.octave;
+    ha[size_t(i)] = k.angle;
+  }
+  // ---- pyramid + smoothing ----------------------------------------------------------------------------------------
+  TOD_CUDA(cudaMemcpyAsync(o->d_img[0].ptr, image, size_t(width) * size_t(height), cudaMemcpyHostToDevice, st));
+  tod::Levels lv{};
+  for (int l = 0; l < L; ++l) {
+    const int w = o->lw[l], h = o->lh[l];
+    dim3 grid((w + 255) / 256, h);
+    if (l) {
+      const int *t = o->d_tables[l].as<int>();
+      tod::resize_exact_kernel<<<grid, 256, 0, st>>>(o->d_img[l - 1].as<uint8_t>(), o->lw[l - 1],
+                                                     o->d_img[l].as<uint8_t>(), w, h, t, t + w, t + 2 * w, t + 3 * w,
+                                                     t + 3 * w + h, t + 3 * w + 2 * h);
+      tod::count_launch();
+    }
+    tod::smooth_rows_kernel<<<grid, 256, 0, st>>>(o->d_img[l].as<uint8_t>(), w, h, o->d_rowf.as<float>());
+    tod::smooth_cols_kernel<<<grid, 256, 0, st>>>(o->d_rowf.as<float>(), w, h, o->d_smooth[l].as<uint8_t>());
+    tod::count_launch(2);
+    lv.l[l].img = o->d_img[l].as<uint8_t>();
+    lv.l[l].smooth = o->d_smooth[l].as<uint8_t>();
+    lv.l[l].w = w;
+    lv.l[l].h = h;
+    lv.l[l].inv_scale = 1.f / o->scale[l];
+  }
+  TOD_CUDA(cudaGetLastError());
+  if (n == 0) {
+    TOD_CUDA(cudaStreamSynchronize(st));
+    if (d_descriptors) *d_descriptors = nullptr;
+    return TOD_OK;
+  }
+  // ---- orientation + descriptors -------------------------------------------------------------------------------------
+  const size_t nn = size_t(n);
+  TOD_CUDA(o->d_kx.reserve(nn * 4));
+  TOD_CUDA(o->d_ky.reserve(nn * 4));
+  TOD_CUDA(o->d_oct.reserve(nn * 4));
+  TOD_CUDA(o->d_angle.reserve(nn * 4));
+  TOD_CUDA(o->d_desc.reserve(nn * 32));
+  TOD_CUDA(cudaMemcpyAsync(o->d_kx.ptr, hx.data(), nn * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(o->d_ky.ptr, hy.data(), nn * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(o->d_oct.ptr, ho.data(), nn * 4, cudaMemcpyHostToDevice, st));
+  const int blocks = (n + 7) / 8;
+  if (compute_angles) {
+    tod::orb_angle_kernel<<<blocks, 256, 0, st>>>(lv, o->d_kx.as<float>(), o->d_ky.as<float>(), o->d_oct.as<int>(), n,
+                                                  o->d_angle.as<float>());
+    tod::count_launch();
+  } else {
+    TOD_CUDA(cudaMemcpyAsync(o->d_angle.ptr, ha.data(), nn * 4, cudaMemcpyHostToDevice, st));
+  }
+  tod::orb_describe_kernel<<<blocks, 256, 0, st>>>(lv, o->d_kx.as<float>(), o->d_ky.as<float>(), o->d_oct.as<int>(),
+                                                   o->d_angle.as<float>(), n, o->d_desc.as<uint8_t>());
+  tod::count_launch();
+  TOD_CUDA(cudaGetLastError());
+  if (compute_angles) TOD_CUDA(cudaMemcpyAsync(ha.data(), o->d_angle.ptr, nn * 4, cudaMemcpyDeviceToHost, st));
+  if (descriptors) TOD_CUDA(cudaMemcpyAsync(descriptors, o->d_desc.ptr, nn * 32, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  if (compute_angles)
+    for (int i = 0; i < n; ++i) keypoints[i].angle = ha[size_t(i)];
+  if (d_descriptors) *d_descriptors = o->d_desc.ptr;
+  return TOD_OK;
+}
+
+int tod_depth_to_3d(int32_t device, const void *depth, int32_t depth_is_u16, int32_t height, int32_t width,
+                    const float *K, float *points3d) {
+  TOD_REQUIRE(depth && K && points3d && height > 0 && width > 0, "bad argument");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return fail(TOD_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  TOD_REQUIRE(device >= 0 && device < n_dev, "device %d out of range", device);
+  TOD_CUDA(cudaSetDevice(device));
+  const size_t px = size_t(height) * size_t(width), in_bytes = px * (depth_is_u16 ? 2 : 4);
+  DeviceBuffer d_in, d_out;
+  TOD_CUDA(d_in.reserve(in_bytes));
+  TOD_CUDA(d_out.reserve(px * 12));
+  TOD_CUDA(cudaMemcpy(d_in.ptr, depth, in_bytes, cudaMemcpyHostToDevice));
+  dim3 grid((width + 255) / 256, height);
+  if (depth_is_u16)
+    tod::depth_to_3d_kernel<uint16_t><<<grid, 256>>>(d_in.as<uint16_t>(), width, height, K[0], K[4], K[2], K[5],
+                                                     d_out.as<float>());
+  else
+    tod::depth_to_3d_kernel<float><<<grid, 256>>>(d_in.as<float>(), width, height, K[0], K[4], K[2], K[5],
+                                                  d_out.as<float>());
+  tod::count_launch();
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaMemcpy(points3d, d_out.ptr, px * 12, cudaMemcpyDeviceToHost);
+  d_in.release();
+  d_out.release();
+  if (ce != cudaSuccess) return fail(TOD_ERR_CUDA, "depth -> 3-D failed: %s", cudaGetErrorString(ce));
+  return TOD_OK;
+}
+
+}  // extern "C"

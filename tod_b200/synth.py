@@ -175,3 +175,33 @@ def make_guess_inputs(n_objects, n_per_object, inlier_fraction, seed=BASE_SEED +
     spans = np.full(n_objects, np.float32(span), np.float32)
     return {"keypoints_xy": kps, "cloud": cloud, "matches": matches, "counts": counts, "points3d": p3,
             "spans": spans, "poses": poses}
+
+
+def make_textured_image(height=480, width=640, seed=BASE_SEED + 6, n_shapes=400):
+    """Deterministic grey image with corners for the feature stage (numpy integer arithmetic only, so every machine
+    regenerates the same bytes): overlapping random rectangles on a soft gradient, speckle, one 3 x 3 box pass."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width]
+    img = ((xx * 40) // max(1, width) + (yy * 30) // max(1, height) + 60).astype(np.int64)
+    for _ in range(n_shapes):
+        w, h = int(rng.integers(6, 60)), int(rng.integers(6, 60))
+        x, y = int(rng.integers(0, width - 5)), int(rng.integers(0, height - 5))
+        img[y:y + h, x:x + w] = int(rng.integers(0, 256))
+    img += rng.integers(-6, 7, img.shape)
+    img = np.clip(img, 0, 255)
+    p = np.pad(img, 1, mode="edge")
+    box = sum(p[dy:dy + height, dx:dx + width] for dy in range(3) for dx in range(3))
+    return ((box + 4) // 9).astype(np.uint8)
+
+
+def make_depth_image(height=480, width=640, seed=BASE_SEED + 7, invalid_fraction=0.1):
+    """Float32 depth in metres (a tilted plane with bumps, 0.5 - 2 m) with NaN holes, and its uint16 millimetre twin
+    (0 = invalid)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    z = (0.8 + 0.6 * xx / width + 0.3 * yy / height + 0.05 * np.sin(xx / 17.0) * np.cos(yy / 23.0)).astype(np.float32)
+    hole = rng.random((height, width)) < invalid_fraction
+    zf = z.copy()
+    zf[hole] = np.nan
+    mm = np.where(hole, 0, np.rint(z * 1000.0)).astype(np.uint16)
+    return zf, mm
