@@ -211,9 +211,9 @@ int tod_matcher_load_snapshot(tod_matcher *m, const char *path);
  * Feature stage in front of the hot path: what TodDetector wires before the DescriptorMatcher —
  * ecto_opencv's FeatureDescriptor cell = cv::ORB (python/object_recognition_tod/detector.py:27,74;
  * conf/detection.ork:23-31: n_features 5000, n_levels 3, scale_factor 1.2) and DepthTo3d (detector.py:62-69).
- * This round: orientation + descriptors for keypoints that are already detected, and depth -> 3-D.  Bit-exact against
- * cv2.ORB (angles as exact floats, descriptors bit for bit; tests/test_orb_gpu.py); detection itself (FAST + Harris)
- * is not done here yet.  The descriptors stay in HBM: *d_descriptors can be handed to tod_matcher_knn_device.
+ * Detection (FAST + Harris), orientation, descriptors and depth -> 3-D on the GPU, bit-exact against cv2.ORB (same
+ * keypoint set, angles and responses as exact floats, descriptors bit for bit; tests/test_orb_gpu.py).  The descriptors
+ * stay in HBM: *d_descriptors can be handed to tod_matcher_knn_device.
  * ============================================================================================================== */
 
 typedef struct tod_orb tod_orb;
@@ -234,6 +234,15 @@ void tod_orb_destroy(tod_orb *o);
  * pointer of the same n x 32 bytes, valid until the next call on this handle. */
 int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, tod_keypoint *keypoints,
                      int32_t n, int32_t compute_angles, uint8_t *descriptors, const void **d_descriptors);
+/* The whole cell: cv::ORB::detectAndCompute with ORB's defaults (FAST threshold 20, edgeThreshold 31, Harris score,
+ * patch 31) — FAST-9/16 + 3 x 3 non-maximum suppression on every level, the 2 N best FAST scores, Harris responses, the N
+ * best per level, orientation, descriptors.  keypoints (capacity max_keypoints; ties at the cut can exceed n_features)
+ * are returned ordered by (octave, row, column) — cv2's own order is an artefact of nth_element — with x, y in level-0
+ * coordinates, size = 31 * scale, angle, response = Harris, octave, class_id = -1.  The SET of keypoints, every field
+ * and every descriptor equal cv2.ORB_create(n_features, scale_factor, n_levels).detectAndCompute (tests/test_orb_gpu.py). */
+int tod_orb_detect_and_compute(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, int32_t n_features,
+                               tod_keypoint *keypoints, int32_t max_keypoints, int32_t *n_keypoints,
+                               uint8_t *descriptors, const void **d_descriptors);
 /* DepthTo3d: depth = height x width float32 metres (NaN = invalid) or, with depth_is_u16, uint16 millimetres (0 =
  * invalid); K = 3 x 3 row-major camera matrix (float); points3d = height x width x 3 f32 (host): x = (u - cx) z / fx,
  * y = (v - cy) z / fy, z — NaN where the depth is invalid: the `points3d` input of the GuessGenerator. */

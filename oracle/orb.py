@@ -15,6 +15,9 @@ tests/golden/orb_*.npz (made by tests/golden/make_orb_golden.py):
               fma(x_{+j} + x_{-j}, k_j, s); round half to even.  (FMA = what cv2 does on an AVX2/FMA host.)
   orientation intensity centroid over the radius-15 disc (umax table), fastAtan2's degree-7 polynomial WITHOUT
               contraction, result in degrees.
+  detection   FAST-9/16 score (threshold 20) with 3 x 3 non-maximum suppression per level, edgeThreshold 31, the 2 N
+              best FAST scores, Harris response (block 7, k = 0.04, float arithmetic operation by operation), the N
+              best responses per level (N from ORB's geometric series); keypoint sets and responses equal cv2's.
   descriptor  steered BRIEF: 256 comparisons of the smoothed level image at pattern points rotated by the angle
               (cosf / sinf of angle * pi/180 in float, products and differences in float, cvRound = half to even);
               pattern = oracle/orb_pattern.npy (recovered from cv2, tools/recover_orb_pattern.py).
@@ -186,6 +189,96 @@ def describe(img, xs, ys, octaves, angles=None, n_levels=3, scale_factor=1.2):
         v = smoothed[l][cy + iy, cx + ix]
         desc[i] = np.packbits((v[0::2] < v[1::2]).astype(np.uint8), bitorder="little")
     return out_angles, desc
+
+
+# ---- detection: cv::ORB::detect = FAST-9/16 (threshold 20, 3 x 3 non-maximum suppression) on every pyramid level, border
+# filter (edgeThreshold 31), the 2 N best FAST scores, Harris response (block 7, k 0.04), the N best Harris responses
+RING = [(0, 3), (1, 3), (2, 2), (3, 1), (3, 0), (3, -1), (2, -2), (1, -3), (0, -3), (-1, -3), (-2, -2), (-3, -1),
+        (-3, 0), (-3, 1), (-2, 2), (-1, 3)]
+
+
+def fast_scores(img, threshold=20):
+    """cv::FAST corner score of every pixel (0 = not a corner): the largest threshold that keeps it a corner."""
+    h, w = img.shape
+    im = img.astype(np.int64)
+    c = im[3:h - 3, 3:w - 3]
+    d = np.stack([im[3 + dy:h - 3 + dy, 3 + dx:w - 3 + dx] for dx, dy in RING]) - c[None]
+    best = np.full(c.shape, -10 ** 9)
+    for s in range(16):
+        idx = [(s + j) % 16 for j in range(9)]
+        best = np.maximum(best, np.maximum(d[idx].min(axis=0), (-d[idx]).min(axis=0)))
+    out = np.zeros((h, w), np.int64)
+    out[3:h - 3, 3:w - 3] = np.where(best > threshold, best - 1, 0)
+    return out
+
+
+def non_max_suppression(score):
+    h, w = score.shape
+    keep = score > 0
+    p = np.pad(score, 1)
+    for dy in range(3):
+        for dx in range(3):
+            if dx != 1 or dy != 1:
+                keep &= score > p[dy:dy + h, dx:dx + w]
+    return keep
+
+
+def harris_responses(level, xs, ys):
+    im = level.astype(np.int64)
+    ix = np.zeros_like(im)
+    iy = np.zeros_like(im)
+    ix[1:-1, 1:-1] = (im[1:-1, 2:] - im[1:-1, :-2]) * 2 + (im[:-2, 2:] - im[:-2, :-2]) + (im[2:, 2:] - im[2:, :-2])
+    iy[1:-1, 1:-1] = (im[2:, 1:-1] - im[:-2, 1:-1]) * 2 + (im[2:, :-2] - im[:-2, :-2]) + (im[2:, 2:] - im[:-2, 2:])
+    scale = F32(1.0) / F32(F32(4 * 7) * F32(255.0))
+    s4 = F32(F32(F32(scale * scale) * scale) * scale)
+    out = np.zeros(len(xs), F32)
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        bx, by = ix[y - 3:y + 4, x - 3:x + 4], iy[y - 3:y + 4, x - 3:x + 4]
+        fa, fb, fc = F32(int((bx * bx).sum())), F32(int((by * by).sum())), F32(int((bx * by).sum()))
+        t = F32(F32(F32(0.04) * F32(fa + fb)) * F32(fa + fb))
+        out[i] = F32(F32(F32(F32(fa * fb) - F32(fc * fc)) - t) * s4)
+    return out
+
+
+def retain_best(resp, n):
+    """KeyPointsFilter::retainBest as a mask: everything that reaches the n-th best response (ties are all kept)."""
+    if len(resp) <= n:
+        return np.ones(len(resp), bool)
+    if n == 0:
+        return np.zeros(len(resp), bool)
+    return resp >= np.sort(resp)[::-1][n - 1]
+
+
+def features_per_level(n_features, n_levels, scale_factor=1.2):
+    f = F32(1.0 / float(F32(scale_factor)))
+    nd = F32(F32(n_features) * F32(F32(1.0) - f) / F32(F32(1.0) - F32(float(f) ** n_levels)))
+    out, s = [], 0
+    for _ in range(n_levels - 1):
+        out.append(int(np.rint(nd)))
+        s += out[-1]
+        nd = F32(nd * f)
+    out.append(max(n_features - s, 0))
+    return out
+
+
+def detect(img, n_features=5000, n_levels=3, scale_factor=1.2):
+    """Keypoints of cv::ORB::detect as a list of (octave, x_level, y_level, harris_response), ordered by level, row,
+    column (cv2's own order is an artefact of nth_element)."""
+    levels = pyramid(img, n_levels, scale_factor)
+    per_level = features_per_level(n_features, n_levels, scale_factor)
+    out = []
+    for l, lev in enumerate(levels):
+        s = fast_scores(lev)
+        ys, xs = np.nonzero(non_max_suppression(s))
+        h, w = lev.shape
+        inside = (xs >= 31) & (xs < w - 31) & (ys >= 31) & (ys < h - 31)
+        xs, ys = xs[inside], ys[inside]
+        k1 = retain_best(s[ys, xs].astype(F32), 2 * per_level[l])
+        xs, ys = xs[k1], ys[k1]
+        hr = harris_responses(lev, xs, ys)
+        k2 = retain_best(hr, per_level[l])
+        out += [(l, int(x), int(y), F32(r)) for x, y, r in zip(xs[k2], ys[k2], hr[k2])]
+    return out
 
 
 def depth_to_3d(depth, K):

@@ -21,13 +21,15 @@ def main():
         img = synth.make_textured_image(h, w, seed=seed)
         orb = cv2.ORB_create(5000, 1.2, 3)
         kp, des = orb.detectAndCompute(img, None)
-        idx = np.linspace(0, len(kp) - 1, min(keep, len(kp))).astype(int)      # a spread over all octaves
+        idx = np.arange(len(kp))                                               # every keypoint cv2 selected
         out = os.path.join(ROOT, "tests", "golden", name + ".npz")
         np.savez_compressed(out, height=h, width=w, seed=seed, cv2_version=cv2.__version__,
                             x=np.array([kp[i].pt[0] for i in idx], np.float32),
                             y=np.array([kp[i].pt[1] for i in idx], np.float32),
                             octave=np.array([kp[i].octave for i in idx], np.int32),
                             angle=np.array([kp[i].angle for i in idx], np.float32),
+                            response=np.array([kp[i].response for i in idx], np.float32),
+                            size=np.array([kp[i].size for i in idx], np.float32),
                             descriptors=des[idx], n_detected=len(kp))
         print(out, len(idx), "of", len(kp), "keypoints; octaves", np.bincount([kp[i].octave for i in idx]))
 

@@ -75,6 +75,54 @@ def test_live_cv2_orb_1280x960():
     assert (desc == des).all()
 
 
+def as_records(kp):
+    return {(int(k["octave"]), float(k["x"]), float(k["y"])): (float(k["angle"]), float(k["response"]), float(k["size"]))
+            for k in kp}
+
+
+@pytest.mark.parametrize("name", ["orb_640x480.npz", "orb_333x517_ragged.npz"])
+def test_detect_and_compute_equals_cv2_golden(name):
+    """The whole cell on the GPU: same keypoint SET as cv2.ORB (positions, octave, angle, Harris response, size — exact
+    floats) and, keypoint by keypoint, the same 32 descriptor bytes."""
+    g = np.load(os.path.join(GOLDEN, name))
+    img = synth.make_textured_image(int(g["height"]), int(g["width"]), seed=int(g["seed"]))
+    fd = FeatureDescriptor(n_features=5000)
+    kp, desc = fd.process(img)
+    fd.close()
+    assert kp.shape[0] == int(g["n_detected"]) == desc.shape[0]
+    ref = {(int(o), float(x), float(y)): (float(a), float(r), float(s), i) for i, (x, y, o, a, r, s) in
+           enumerate(zip(g["x"], g["y"], g["octave"], g["angle"], g["response"], g["size"]))}
+    got = as_records(kp)
+    assert set(got) == set(ref)
+    for key, (a, r, s) in got.items():
+        assert (a, r, s) == ref[key][:3], key
+    order = [ref[(int(k["octave"]), float(k["x"]), float(k["y"]))][3] for k in kp]
+    assert (desc == g["descriptors"][order]).all()
+    assert (kp["class_id"] == -1).all()
+    key = kp["octave"].astype(np.int64)                          # ordered by octave
+    assert (np.diff(key) >= 0).all()
+
+
+def test_detect_and_compute_live_cv2_1280x960_n_features_cut():
+    """At 1280 x 960 the frame holds more corners than n_features: the two retainBest cuts (FAST score, then Harris) must
+    pick cv2's keypoints, ties included."""
+    cv2 = pytest.importorskip("cv2")
+    img = synth.make_textured_image(960, 1280, seed=41, n_shapes=1500)
+    for nf in (5000, 1200):
+        kps, des = cv2.ORB_create(nf, 1.2, 3).detectAndCompute(img, None)
+        fd = FeatureDescriptor(n_features=nf)
+        kp, desc = fd.process(img)
+        fd.close()
+        ref = {(k.octave, float(k.pt[0]), float(k.pt[1])): (float(k.angle), float(k.response), float(k.size), i)
+               for i, k in enumerate(kps)}
+        got = as_records(kp)
+        assert set(got) == set(ref) and len(kps) == kp.shape[0]
+        for key_, v in got.items():
+            assert v == ref[key_][:3]
+        order = [ref[(int(k["octave"]), float(k["x"]), float(k["y"]))][3] for k in kp]
+        assert (desc == des[order]).all()
+
+
 def test_border_keypoints_are_refused():
     img = synth.make_textured_image(200, 200, seed=1)
     fd = FeatureDescriptor()

@@ -66,6 +66,34 @@ def test_full_frame_against_live_cv2_orb():
     assert (mine == des[sel]).all()
 
 
+@pytest.mark.parametrize("name", ORB_GOLDENS)
+def test_oracle_detection_reproduces_cv2_keypoint_set(name):
+    """cv::ORB::detect restated (FAST score + NMS, border, 2 N best, Harris, N best): the same SET of keypoints with the
+    same Harris responses as the golden (cv2's order is an artefact of nth_element, so sets are compared)."""
+    g = np.load(os.path.join(GOLDEN, name))
+    img = synth.make_textured_image(int(g["height"]), int(g["width"]), seed=int(g["seed"]))
+    mine = oo.detect(img, 5000, 3, 1.2)
+    sc = oo.level_scales(3)
+    ref = {}
+    for x, y, o, r in zip(g["x"], g["y"], g["octave"], g["response"]):
+        cx, cy = oo.level_center(x, y, sc[int(o)])
+        ref[(int(o), cx, cy)] = np.float32(r)
+    got = {(l, x, y): r for l, x, y, r in mine}
+    assert set(got) == set(ref) and len(mine) == len(got) == int(g["n_detected"])
+    assert all(got[k] == ref[k] for k in ref)
+    assert oo.features_per_level(5000, 3) == [1978, 1648, 1374]
+
+
+def test_fast_and_nms_against_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    img = synth.make_textured_image(300, 400, seed=77)
+    kps = cv2.FastFeatureDetector_create(20, True).detect(img, None)
+    s = oo.fast_scores(img)
+    ys, xs = np.nonzero(oo.non_max_suppression(s))
+    assert {(int(k.pt[0]), int(k.pt[1])): int(k.response) for k in kps} == \
+        {(int(x), int(y)): int(s[y, x]) for x, y in zip(xs, ys)}
+
+
 def test_depth_to_3d():
     zf, mm = synth.make_depth_image(120, 160, seed=3)
     K = np.array([[525.0, 0, 79.5], [0, 525.0, 59.5], [0, 0, 1]])

@@ -352,12 +352,12 @@ class GuessGenerator:
 
 
 class FeatureDescriptor:
-    """The describe half of ecto_opencv's FeatureDescriptor cell (cv::ORB, detector.py:27,74; conf/detection.ork:23-31)
-    on the GPU: pyramid, smoothing, orientation and rBRIEF descriptors for keypoints that are already detected —
-    bit-exact against cv2.ORB.  The descriptors also stay on the device (`last_device_descriptors`) for
-    DescriptorMatcher.process_device."""
+    """ecto_opencv's FeatureDescriptor cell (cv::ORB, detector.py:27,74; conf/detection.ork:23-31) on the GPU: pyramid,
+    FAST + Harris detection, smoothing, orientation and rBRIEF descriptors — bit-exact against cv2.ORB.  The
+    descriptors also stay on the device (`last_device_descriptors`) for DescriptorMatcher.process_device."""
 
-    def __init__(self, n_levels=3, scale_factor=1.2, device=0):
+    def __init__(self, n_features=5000, n_levels=3, scale_factor=1.2, device=0):
+        self.n_features = int(n_features)
         lib = capi.load()
         p = capi.OrbParams()
         lib.tod_orb_default_params(ctypes.byref(p))
@@ -373,6 +373,21 @@ class FeatureDescriptor:
             self._h = None
 
     __del__ = close
+
+    def process(self, image):
+        """inputs["image"] (H x W u8) -> keypoints (KEYPOINT_DTYPE, ordered by octave, row, column), descriptors."""
+        img = np.ascontiguousarray(image, np.uint8)
+        assert img.ndim == 2
+        cap = 2 * self.n_features + 1024
+        kp = np.zeros(cap, capi.KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = ctypes.c_int32(0)
+        dptr = ctypes.c_void_p()
+        capi.check(self._lib.tod_orb_detect_and_compute(self._h, capi._ptr(img), img.shape[0], img.shape[1],
+                                                        self.n_features, capi._ptr(kp), cap, ctypes.byref(n),
+                                                        capi._ptr(desc), ctypes.byref(dptr)))
+        self.last_device_descriptors = dptr.value
+        return kp[:n.value].copy(), desc[:n.value].copy()
 
     def describe(self, image, keypoints, compute_angles=True):
         """image: H x W u8; keypoints: KEYPOINT_DTYPE array (x, y, octave read; angle written when compute_angles).

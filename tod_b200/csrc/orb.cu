@@ -12,8 +12,10 @@
 //   descriptor   steered BRIEF, 256 comparisons at pattern points rotated by the angle (float products, cvRound)
 // Every float operation that decides a bit is written with explicit rounding intrinsics (__fmul_rn / __fadd_rn /
 // __fmaf_rn): the compiler may neither fuse nor split them.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "orb_pattern.h"
@@ -191,6 +193,90 @@ depth_to_3d_kernel(const T *__restrict__ depth, int w, int h, float fx, float fy
   o[2] = z;
 }
 
+// ---- detection: FAST-9/16 score, 3 x 3 non-maximum suppression, Harris response ----------------------------------------
+// cv::FAST(threshold 20, nonmaxSuppression) as cv::ORB runs it on every pyramid level.  score = the largest threshold
+// for which the pixel is still a corner = max over the 16 arcs of 9 ring pixels of min(ring - p) (bright) or
+// min(p - ring) (dark), minus 1; 0 when that does not exceed the threshold.
+__constant__ int c_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+__constant__ int c_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+__global__ void __launch_bounds__(256)
+fast_score_kernel(const uint8_t *__restrict__ img, int w, int h, int threshold, uint8_t *__restrict__ score) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  int out = 0;
+  if (x >= 3 && y >= 3 && x < w - 3 && y < h - 3) {
+    const int p = img[size_t(y) * w + x];
+    int d[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = int(img[size_t(y + c_ring_dy[k]) * w + x + c_ring_dx[k]]) - p;
+    int best = -1000;
+#pragma unroll
+    for (int s0 = 0; s0 < 16; ++s0) {
+      int mb = 1000, md = 1000;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int v = d[(s0 + j) & 15];
+        mb = min(mb, v);
+        md = min(md, -v);
+      }
+      best = max(best, max(mb, md));
+    }
+    if (best > threshold) out = best - 1;
+  }
+  score[size_t(y) * w + x] = uint8_t(out);
+}
+
+// keeps a corner whose score beats its 8 neighbours (strictly) and that lies at least `border` pixels inside the level
+// (KeyPointsFilter::runByImageBorder with ORB's edgeThreshold); candidates are appended in arbitrary order.
+__global__ void __launch_bounds__(256)
+fast_nms_kernel(const uint8_t *__restrict__ score, int w, int h, int border, int level, int capacity,
+                int4 *__restrict__ out, int *__restrict__ count) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x < border || y < border || x >= w - border || y >= h - border) return;
+  const int s = score[size_t(y) * w + x];
+  if (s == 0) return;
+  bool keep = true;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx)
+      if (dx || dy) keep = keep && s > int(score[size_t(y + dy) * w + x + dx]);
+  if (!keep) return;
+  const int slot = atomicAdd(count, 1);
+  if (slot < capacity) out[slot] = make_int4(x, y, s, level);
+}
+
+// cv::ORB's HarrisResponses (blockSize 7, k = 0.04) on the unsmoothed level: integer sums of the Sobel products over the
+// 7 x 7 block, then ((float) a b - (float) c c - k ((float) a + b)^2) scale^4 in float, operation by operation.
+__global__ void __launch_bounds__(128)
+harris_kernel(Levels lv, const int4 *__restrict__ cand, int n, float *__restrict__ response) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 c4 = cand[i];
+  const LevelDesc L = lv.l[c4.w];
+  const uint8_t *base = L.img + size_t(c4.y) * L.w + c4.x;
+  int a = 0, b = 0, c = 0;
+  for (int dy = -3; dy <= 3; ++dy) {
+    const uint8_t *r0 = base + (dy - 1) * L.w, *r1 = base + dy * L.w, *r2 = base + (dy + 1) * L.w;
+    for (int dx = -3; dx <= 3; ++dx) {
+      const int ix = (int(r1[dx + 1]) - int(r1[dx - 1])) * 2 + (int(r0[dx + 1]) - int(r0[dx - 1])) +
+                     (int(r2[dx + 1]) - int(r2[dx - 1]));
+      const int iy = (int(r2[dx]) - int(r0[dx])) * 2 + (int(r2[dx - 1]) - int(r0[dx - 1])) +
+                     (int(r2[dx + 1]) - int(r0[dx + 1]));
+      a += ix * ix;
+      b += iy * iy;
+      c += ix * iy;
+    }
+  }
+  const float scale = __fdiv_rn(1.f, __fmul_rn(28.f, 255.f));
+  const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+  const float fa = float(a), fb = float(b), fc = float(c);
+  const float sum = __fadd_rn(fa, fb);
+  const float t = __fmul_rn(__fmul_rn(0.04f, sum), sum);
+  response[i] = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), t), s4);
+}
+
 void linear_exact_table(int src, int dst, std::vector<int> &i0, std::vector<int> &i1, std::vector<int> &f) {
   i0.resize(size_t(dst));
   i1.resize(size_t(dst));
@@ -220,6 +306,7 @@ struct tod_orb {
   float scale[tod::kMaxLevels] = {0};
   DeviceBuffer d_img[tod::kMaxLevels], d_smooth[tod::kMaxLevels], d_rowf, d_tables[tod::kMaxLevels];
   DeviceBuffer d_kx, d_ky, d_oct, d_angle, d_desc;
+  DeviceBuffer d_score, d_cand, d_count, d_resp;  // detection: FAST score image, candidate list, counter, Harris
   bool pattern_uploaded = false;
 };
 
@@ -261,67 +348,58 @@ void tod_orb_destroy(tod_orb *o) {
     o->d_smooth[l].release();
     o->d_tables[l].release();
   }
-  for (DeviceBuffer *b : {&o->d_rowf, &o->d_kx, &o->d_ky, &o->d_oct, &o->d_angle, &o->d_desc}) b->release();
+  for (DeviceBuffer *b : {&o->d_rowf, &o->d_kx, &o->d_ky, &o->d_oct, &o->d_angle, &o->d_desc, &o->d_score, &o->d_cand,
+                          &o->d_count, &o->d_resp})
+    b->release();
   if (o->stream) cudaStreamDestroy(o->stream);
   delete o;
 }
 
-int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, tod_keypoint *keypoints,
-                     int32_t n, int32_t compute_angles, uint8_t *descriptors, const void **d_descriptors) {
-  TOD_REQUIRE(o && image && (keypoints || n == 0), "null argument");
-  TOD_REQUIRE(height > 2 * tod::kDescBorder && width > 2 * tod::kDescBorder && n >= 0, "bad sizes");
-  TOD_CUDA(cudaSetDevice(o->p.device));
+}  // extern "C"
+
+namespace {
+
+// Level geometry and resize tables for a new image size.
+int orb_prepare(tod_orb *o, int height, int width) {
+  TOD_REQUIRE(height > 2 * tod::kDescBorder && width > 2 * tod::kDescBorder, "image too small");
+  if (height == o->height && width == o->width) return TOD_OK;
   cudaStream_t st = o->stream;
   const int L = o->p.n_levels;
+  // scale_l = (float) pow((double) scale_factor, l); size = cvRound(size0 / scale_l)
+  for (int l = 0; l < L; ++l) {
+    o->scale[l] = float(std::pow(double(o->p.scale_factor), double(l)));
+    o->lw[l] = int(std::lrintf(float(width) / o->scale[l]));
+    o->lh[l] = int(std::lrintf(float(height) / o->scale[l]));
+    TOD_REQUIRE(o->lw[l] > 2 * tod::kDescBorder && o->lh[l] > 2 * tod::kDescBorder, "image too small for level %d", l);
+    const size_t px = size_t(o->lw[l]) * size_t(o->lh[l]);
+    TOD_CUDA(o->d_img[l].reserve(px));
+    TOD_CUDA(o->d_smooth[l].reserve(px));
+    if (l) {  // INTER_LINEAR_EXACT tables from level l-1: x0 x1 fx (lw) y0 y1 fy (lh), all int32
+      std::vector<int> a0, a1, af, b0, b1, bf, all;
+      tod::linear_exact_table(o->lw[l - 1], o->lw[l], a0, a1, af);
+      tod::linear_exact_table(o->lh[l - 1], o->lh[l], b0, b1, bf);
+      for (auto *v : {&a0, &a1, &af, &b0, &b1, &bf}) all.insert(all.end(), v->begin(), v->end());
+      TOD_CUDA(o->d_tables[l].reserve(all.size() * sizeof(int)));
+      TOD_CUDA(cudaMemcpyAsync(o->d_tables[l].ptr, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      TOD_CUDA(cudaStreamSynchronize(st));  // `all` dies at the end of this block
+    }
+  }
+  TOD_CUDA(o->d_rowf.reserve(size_t(width) * size_t(height) * sizeof(float)));
+  TOD_CUDA(o->d_score.reserve(size_t(width) * size_t(height)));
+  o->height = height;
+  o->width = width;
+  return TOD_OK;
+}
+
+// Upload the frame, build the pyramid (unsmoothed + smoothed levels) on the handle's stream.
+int orb_build_pyramid(tod_orb *o, const uint8_t *image, tod::Levels *lv) {
+  cudaStream_t st = o->stream;
   if (!o->pattern_uploaded) {
     TOD_CUDA(cudaMemcpyToSymbol(tod::c_pattern, tod::kOrbPattern, sizeof(tod::kOrbPattern)));
     o->pattern_uploaded = true;
   }
-  if (height != o->height || width != o->width) {
-    // level geometry: scale_l = (float) pow((double) scale_factor, l); size = cvRound(size0 / scale_l)
-    for (int l = 0; l < L; ++l) {
-      o->scale[l] = float(std::pow(double(o->p.scale_factor), double(l)));
-      o->lw[l] = int(std::lrintf(float(width) / o->scale[l]));
-      o->lh[l] = int(std::lrintf(float(height) / o->scale[l]));
-      TOD_REQUIRE(o->lw[l] > 2 * tod::kDescBorder && o->lh[l] > 2 * tod::kDescBorder, "image too small for level %d", l);
-      const size_t px = size_t(o->lw[l]) * size_t(o->lh[l]);
-      TOD_CUDA(o->d_img[l].reserve(px));
-      TOD_CUDA(o->d_smooth[l].reserve(px));
-      if (l) {  // INTER_LINEAR_EXACT tables from level l-1: x0 x1 fx (lw) y0 y1 fy (lh), all int32
-        std::vector<int> a0, a1, af, b0, b1, bf, all;
-        tod::linear_exact_table(o->lw[l - 1], o->lw[l], a0, a1, af);
-        tod::linear_exact_table(o->lh[l - 1], o->lh[l], b0, b1, bf);
-        for (auto *v : {&a0, &a1, &af, &b0, &b1, &bf}) all.insert(all.end(), v->begin(), v->end());
-        TOD_CUDA(o->d_tables[l].reserve(all.size() * sizeof(int)));
-        TOD_CUDA(cudaMemcpyAsync(o->d_tables[l].ptr, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        TOD_CUDA(cudaStreamSynchronize(st));  // `all` dies at the end of this block
-      }
-    }
-    TOD_CUDA(o->d_rowf.reserve(size_t(width) * size_t(height) * sizeof(float)));
-    o->height = height;
-    o->width = width;
-  }
-  // keypoints: level-0 coordinates and octave; every pattern / disc access must stay inside its level
-  std::vector<float> hx(static_cast<size_t>(n)), hy(static_cast<size_t>(n)), ha(static_cast<size_t>(n));
-  std::vector<int> ho(static_cast<size_t>(n));
-  for (int i = 0; i < n; ++i) {
-    const tod_keypoint &k = keypoints[i];
-    TOD_REQUIRE(k.octave >= 0 && k.octave < L, "keypoint %d: octave %d outside [0, %d)", i, k.octave, L);
-    const float inv = 1.f / o->scale[k.octave];
-    const long cx = std::lrintf(k.x * inv), cy = std::lrintf(k.y * inv);
-    TOD_REQUIRE(cx >= tod::kDescBorder && cy >= tod::kDescBorder && cx < o->lw[k.octave] - tod::kDescBorder &&
-                    cy < o->lh[k.octave] - tod::kDescBorder,
-                "keypoint %d at (%g, %g) octave %d is closer than %d pixels to the border of its level (cv::ORB drops "
-                "such keypoints: edgeThreshold)", i, k.x, k.y, k.octave, tod::kDescBorder);
-    hx[size_t(i)] = k.x;
-    hy[size_t(i)] = k.y;
-    ho[size_t(i)] = k.octave;
-    ha[size_t(i)] = k.angle;
-  }
-  // ---- pyramid + smoothing ----------------------------------------------------------------------------------------
-  TOD_CUDA(cudaMemcpyAsync(o->d_img[0].ptr, image, size_t(width) * size_t(height), cudaMemcpyHostToDevice, st));
-  tod::Levels lv{};
-  for (int l = 0; l < L; ++l) {
+  TOD_CUDA(cudaMemcpyAsync(o->d_img[0].ptr, image, size_t(o->width) * size_t(o->height), cudaMemcpyHostToDevice, st));
+  for (int l = 0; l < o->p.n_levels; ++l) {
     const int w = o->lw[l], h = o->lh[l];
     dim3 grid((w + 255) / 256, h);
     if (l) {
@@ -334,19 +412,26 @@ int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t w
     tod::smooth_rows_kernel<<<grid, 256, 0, st>>>(o->d_img[l].as<uint8_t>(), w, h, o->d_rowf.as<float>());
     tod::smooth_cols_kernel<<<grid, 256, 0, st>>>(o->d_rowf.as<float>(), w, h, o->d_smooth[l].as<uint8_t>());
     tod::count_launch(2);
-    lv.l[l].img = o->d_img[l].as<uint8_t>();
-    lv.l[l].smooth = o->d_smooth[l].as<uint8_t>();
-    lv.l[l].w = w;
-    lv.l[l].h = h;
-    lv.l[l].inv_scale = 1.f / o->scale[l];
+    lv->l[l].img = o->d_img[l].as<uint8_t>();
+    lv->l[l].smooth = o->d_smooth[l].as<uint8_t>();
+    lv->l[l].w = w;
+    lv->l[l].h = h;
+    lv->l[l].inv_scale = 1.f / o->scale[l];
   }
   TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
+// Orientation (optional) + descriptors of n keypoints given as host arrays; angles come back in ha.
+int orb_describe_points(tod_orb *o, const tod::Levels &lv, const std::vector<float> &hx, const std::vector<float> &hy,
+                        const std::vector<int> &ho, std::vector<float> &ha, int n, bool compute_angles,
+                        uint8_t *descriptors, const void **d_descriptors) {
+  cudaStream_t st = o->stream;
   if (n == 0) {
     TOD_CUDA(cudaStreamSynchronize(st));
     if (d_descriptors) *d_descriptors = nullptr;
     return TOD_OK;
   }
-  // ---- orientation + descriptors -------------------------------------------------------------------------------------
   const size_t nn = size_t(n);
   TOD_CUDA(o->d_kx.reserve(nn * 4));
   TOD_CUDA(o->d_ky.reserve(nn * 4));
@@ -371,9 +456,175 @@ int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t w
   if (compute_angles) TOD_CUDA(cudaMemcpyAsync(ha.data(), o->d_angle.ptr, nn * 4, cudaMemcpyDeviceToHost, st));
   if (descriptors) TOD_CUDA(cudaMemcpyAsync(descriptors, o->d_desc.ptr, nn * 32, cudaMemcpyDeviceToHost, st));
   TOD_CUDA(cudaStreamSynchronize(st));
+  if (d_descriptors) *d_descriptors = o->d_desc.ptr;
+  return TOD_OK;
+}
+
+// KeyPointsFilter::retainBest: keep everything whose response reaches the n-th best one (ties are all kept).
+void retain_best(std::vector<int> &idx, const std::vector<float> &resp, size_t n) {
+  if (idx.size() <= n) return;
+  if (n == 0) {
+    idx.clear();
+    return;
+  }
+  std::vector<float> r;
+  r.reserve(idx.size());
+  for (int i : idx) r.push_back(resp[size_t(i)]);
+  std::nth_element(r.begin(), r.begin() + (n - 1), r.end(), std::greater<float>());
+  const float thr = r[n - 1];
+  std::vector<int> keep;
+  for (int i : idx)
+    if (resp[size_t(i)] >= thr) keep.push_back(i);
+  idx.swap(keep);
+}
+
+}  // namespace
+
+extern "C" {
+
+int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, tod_keypoint *keypoints,
+                     int32_t n, int32_t compute_angles, uint8_t *descriptors, const void **d_descriptors) {
+  TOD_REQUIRE(o && image && (keypoints || n == 0) && n >= 0, "bad argument");
+  TOD_CUDA(cudaSetDevice(o->p.device));
+  if (int rc = orb_prepare(o, height, width)) return rc;
+  const int L = o->p.n_levels;
+  // keypoints: level-0 coordinates and octave; every pattern / disc access must stay inside its level
+  std::vector<float> hx(static_cast<size_t>(n)), hy(static_cast<size_t>(n)), ha(static_cast<size_t>(n));
+  std::vector<int> ho(static_cast<size_t>(n));
+  for (int i = 0; i < n; ++i) {
+    const tod_keypoint &k = keypoints[i];
+    TOD_REQUIRE(k.octave >= 0 && k.octave < L, "keypoint %d: octave %d outside [0, %d)", i, k.octave, L);
+    const float inv = 1.f / o->scale[k.octave];
+    const long cx = std::lrintf(k.x * inv), cy = std::lrintf(k.y * inv);
+    TOD_REQUIRE(cx >= tod::kDescBorder && cy >= tod::kDescBorder && cx < o->lw[k.octave] - tod::kDescBorder &&
+                    cy < o->lh[k.octave] - tod::kDescBorder,
+                "keypoint %d at (%g, %g) octave %d is closer than %d pixels to the border of its level (cv::ORB drops "
+                "such keypoints: edgeThreshold)", i, k.x, k.y, k.octave, tod::kDescBorder);
+    hx[size_t(i)] = k.x;
+    hy[size_t(i)] = k.y;
+    ho[size_t(i)] = k.octave;
+    ha[size_t(i)] = k.angle;
+  }
+  tod::Levels lv{};
+  if (int rc = orb_build_pyramid(o, image, &lv)) return rc;
+  if (int rc = orb_describe_points(o, lv, hx, hy, ho, ha, n, compute_angles != 0, descriptors, d_descriptors)) return rc;
   if (compute_angles)
     for (int i = 0; i < n; ++i) keypoints[i].angle = ha[size_t(i)];
-  if (d_descriptors) *d_descriptors = o->d_desc.ptr;
+  return TOD_OK;
+}
+
+int tod_orb_detect_and_compute(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, int32_t n_features,
+                               tod_keypoint *keypoints, int32_t max_keypoints, int32_t *n_keypoints,
+                               uint8_t *descriptors, const void **d_descriptors) {
+  TOD_REQUIRE(o && image && keypoints && n_keypoints && n_features >= 0 && max_keypoints >= 0, "bad argument");
+  *n_keypoints = 0;
+  TOD_CUDA(cudaSetDevice(o->p.device));
+  if (int rc = orb_prepare(o, height, width)) return rc;
+  cudaStream_t st = o->stream;
+  const int L = o->p.n_levels;
+  const int kEdge = 31, kFastThreshold = 20;  // cv::ORB defaults: edgeThreshold, fastThreshold
+  tod::Levels lv{};
+  if (int rc = orb_build_pyramid(o, image, &lv)) return rc;
+  // features per level (ORB_Impl::computeKeyPoints): a geometric series over the levels, the last level takes the rest
+  std::vector<int> per_level(static_cast<size_t>(L), 0);
+  {
+    const float factor = float(1.0 / double(o->p.scale_factor));
+    float desired = float(n_features) * (1.f - factor) / (1.f - float(std::pow(double(factor), double(L))));  // float ops
+    int sum = 0;
+    for (int l = 0; l + 1 < L; ++l) {
+      per_level[size_t(l)] = int(std::lrintf(desired));
+      sum += per_level[size_t(l)];
+      desired *= factor;
+    }
+    per_level[size_t(L - 1)] = std::max(n_features - sum, 0);
+  }
+  // FAST + non-maximum suppression + border filter on every level -> one candidate list
+  const int capacity = std::max(1 << 16, (height * width) / 8);
+  TOD_CUDA(o->d_cand.reserve(size_t(capacity) * sizeof(int4)));
+  TOD_CUDA(o->d_count.reserve(sizeof(int)));
+  TOD_CUDA(cudaMemsetAsync(o->d_count.ptr, 0, sizeof(int), st));
+  for (int l = 0; l < L; ++l) {
+    const int w = o->lw[l], h = o->lh[l];
+    dim3 grid((w + 255) / 256, h);
+    tod::fast_score_kernel<<<grid, 256, 0, st>>>(o->d_img[l].as<uint8_t>(), w, h, kFastThreshold,
+                                                 o->d_score.as<uint8_t>());
+    tod::fast_nms_kernel<<<grid, 256, 0, st>>>(o->d_score.as<uint8_t>(), w, h, kEdge, l, capacity,
+                                               o->d_cand.as<int4>(), o->d_count.as<int>());
+    tod::count_launch(2);
+  }
+  TOD_CUDA(cudaGetLastError());
+  int n_cand = 0;
+  TOD_CUDA(cudaMemcpyAsync(&n_cand, o->d_count.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  if (n_cand > capacity) return fail(TOD_ERR_LIMIT, "%d FAST corners exceed the candidate capacity %d", n_cand, capacity);
+  std::vector<int4> cand(static_cast<size_t>(n_cand));
+  if (n_cand) TOD_CUDA(cudaMemcpy(cand.data(), o->d_cand.ptr, size_t(n_cand) * sizeof(int4), cudaMemcpyDeviceToHost));
+  // deterministic order (the append order on the device is not): by level, row, column
+  std::sort(cand.begin(), cand.end(), [](const int4 &a, const int4 &b) {
+    if (a.w != b.w) return a.w < b.w;
+    if (a.y != b.y) return a.y < b.y;
+    return a.x < b.x;
+  });
+  // per level: keep the 2 N best FAST scores (ties kept), Harris response, keep the N best (ties kept)
+  std::vector<int> first_cut;
+  {
+    std::vector<float> score(cand.size());
+    for (size_t i = 0; i < cand.size(); ++i) score[i] = float(cand[i].z);
+    size_t at = 0;
+    for (int l = 0; l < L; ++l) {
+      std::vector<int> idx;
+      while (at < cand.size() && cand[at].w == l) idx.push_back(int(at++));
+      retain_best(idx, score, size_t(2 * per_level[size_t(l)]));
+      first_cut.insert(first_cut.end(), idx.begin(), idx.end());
+    }
+  }
+  std::vector<int4> sel(first_cut.size());
+  for (size_t i = 0; i < first_cut.size(); ++i) sel[i] = cand[size_t(first_cut[i])];
+  std::vector<float> resp(sel.size());
+  if (!sel.empty()) {
+    TOD_CUDA(o->d_resp.reserve(sel.size() * sizeof(float)));
+    TOD_CUDA(cudaMemcpyAsync(o->d_cand.ptr, sel.data(), sel.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    tod::harris_kernel<<<unsigned((sel.size() + 127) / 128), 128, 0, st>>>(lv, o->d_cand.as<int4>(), int(sel.size()),
+                                                                             o->d_resp.as<float>());
+    tod::count_launch();
+    TOD_CUDA(cudaGetLastError());
+    TOD_CUDA(cudaMemcpyAsync(resp.data(), o->d_resp.ptr, sel.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    TOD_CUDA(cudaStreamSynchronize(st));
+  }
+  std::vector<int> final_idx;
+  {
+    size_t at = 0;
+    for (int l = 0; l < L; ++l) {
+      std::vector<int> idx;
+      while (at < sel.size() && sel[at].w == l) idx.push_back(int(at++));
+      retain_best(idx, resp, size_t(per_level[size_t(l)]));
+      final_idx.insert(final_idx.end(), idx.begin(), idx.end());
+    }
+  }
+  const int n = int(final_idx.size());
+  if (n > max_keypoints) return fail(TOD_ERR_LIMIT, "%d keypoints found but max_keypoints = %d", n, max_keypoints);
+  // level coordinates -> level-0 coordinates (pt *= scale), size = patchSize * scale
+  std::vector<float> hx(static_cast<size_t>(n)), hy(static_cast<size_t>(n)), ha(static_cast<size_t>(n), 0.f);
+  std::vector<int> ho(static_cast<size_t>(n));
+  for (int i = 0; i < n; ++i) {
+    const int4 c = sel[size_t(final_idx[size_t(i)])];
+    const float sc = o->scale[c.w];
+    hx[size_t(i)] = float(c.x) * sc;
+    hy[size_t(i)] = float(c.y) * sc;
+    ho[size_t(i)] = c.w;
+  }
+  if (int rc = orb_describe_points(o, lv, hx, hy, ho, ha, n, true, descriptors, d_descriptors)) return rc;
+  for (int i = 0; i < n; ++i) {
+    tod_keypoint &k = keypoints[i];
+    k.x = hx[size_t(i)];
+    k.y = hy[size_t(i)];
+    k.size = 31.f * o->scale[ho[size_t(i)]];
+    k.angle = ha[size_t(i)];
+    k.response = resp[size_t(final_idx[size_t(i)])];
+    k.octave = ho[size_t(i)];
+    k.class_id = -1;
+  }
+  *n_keypoints = n;
   return TOD_OK;
 }
 
