@@ -243,6 +243,10 @@ int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t w
 int tod_orb_detect_and_compute(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, int32_t n_features,
                                tod_keypoint *keypoints, int32_t max_keypoints, int32_t *n_keypoints,
                                uint8_t *descriptors, const void **d_descriptors);
+/* Reads back one pyramid level of the last processed frame (for stage-by-stage parity tests): kind 0 = the level as
+ * resized, 1 = smoothed, 2 = its FAST corner scores (0 = no corner).  out = height x width u8, may be NULL to query the
+ * level size only. */
+int tod_orb_read_level(tod_orb *o, int32_t level, int32_t kind, uint8_t *out, int32_t *height, int32_t *width);
 /* DepthTo3d: depth = height x width float32 metres (NaN = invalid) or, with depth_is_u16, uint16 millimetres (0 =
  * invalid); K = 3 x 3 row-major camera matrix (float); points3d = height x width x 3 f32 (host): x = (u - cx) z / fx,
  * y = (v - cy) z / fy, z — NaN where the depth is invalid: the `points3d` input of the GuessGenerator. */

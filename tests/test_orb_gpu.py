@@ -75,6 +75,20 @@ def test_live_cv2_orb_1280x960():
     assert (desc == des).all()
 
 
+def test_pyramid_smoothing_and_fast_scores_stage_by_stage():
+    """Every intermediate image of the feature stage, read back from the device, equals the oracle restatement byte for
+    byte: resized levels (INTER_LINEAR_EXACT), smoothed levels, FAST corner scores."""
+    img = synth.make_textured_image(333, 517, seed=12)
+    fd = FeatureDescriptor(n_features=1000)
+    fd.process(img)
+    levels = oo.pyramid(img, 3)
+    for l, lev in enumerate(levels):
+        assert (fd.read_level(l, 0) == lev).all()
+        assert (fd.read_level(l, 1) == oo.smooth(lev)).all()
+        assert (fd.read_level(l, 2) == oo.fast_scores(lev)).all()
+    fd.close()
+
+
 def as_records(kp):
     return {(int(k["octave"]), float(k["x"]), float(k["y"])): (float(k["angle"]), float(k["response"]), float(k["size"]))
             for k in kp}

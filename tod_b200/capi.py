@@ -96,6 +96,7 @@ SIGNATURES = [
     ("tod_orb_describe", ctypes.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _P, ctypes.POINTER(_P)]),
     ("tod_orb_detect_and_compute", ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, ctypes.POINTER(_I32), _P,
                                                   ctypes.POINTER(_P)]),
+    ("tod_orb_read_level", ctypes.c_int, [_P, _I32, _I32, _P, ctypes.POINTER(_I32), ctypes.POINTER(_I32)]),
     ("tod_depth_to_3d", ctypes.c_int, [_I32, _P, _I32, _I32, _I32, _P, _P]),
     ("tod_adjacency_row_words", _I32, [_I32]),
     ("tod_fill_adjacency", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _F, _P, _P, _P]),

@@ -389,6 +389,14 @@ class FeatureDescriptor:
         self.last_device_descriptors = dptr.value
         return kp[:n.value].copy(), desc[:n.value].copy()
 
+    def read_level(self, level, kind=0):
+        """One pyramid level of the last frame: kind 0 = resized, 1 = smoothed, 2 = FAST corner scores."""
+        h, w = ctypes.c_int32(0), ctypes.c_int32(0)
+        capi.check(self._lib.tod_orb_read_level(self._h, int(level), int(kind), None, ctypes.byref(h), ctypes.byref(w)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        capi.check(self._lib.tod_orb_read_level(self._h, int(level), int(kind), capi._ptr(out), None, None))
+        return out
+
     def describe(self, image, keypoints, compute_angles=True):
         """image: H x W u8; keypoints: KEYPOINT_DTYPE array (x, y, octave read; angle written when compute_angles).
         Returns (keypoints, descriptors[n, 32] u8)."""

@@ -206,15 +206,18 @@ fast_score_kernel(const uint8_t *__restrict__ img, int w, int h, int threshold, 
   if (x >= w || y >= h) return;
   int out = 0;
   if (x >= 3 && y >= 3 && x < w - 3 && y < h - 3) {
-    const int p = img[size_t(y) * w + x];
+    const uint8_t *pc = img + size_t(y) * w + x;
+    const int p = pc[0];
     int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = int(img[size_t(y + c_ring_dy[k]) * w + x + c_ring_dx[k]]) - p;
+    // NOTE: the loops stay rolled on purpose.  Fully unrolled, nvcc 12.9 for sm_100a produced wrong scores for this
+    // kernel (tools/fast_unroll_repro.cu reproduces it stand-alone); rolled, it equals cv2 and the host transliteration.
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) d[k] = int(pc[c_ring_dy[k] * w + c_ring_dx[k]]) - p;
     int best = -1000;
-#pragma unroll
+#pragma unroll 1
     for (int s0 = 0; s0 < 16; ++s0) {
       int mb = 1000, md = 1000;
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 9; ++j) {
         const int v = d[(s0 + j) & 15];
         mb = min(mb, v);
@@ -234,14 +237,15 @@ fast_nms_kernel(const uint8_t *__restrict__ score, int w, int h, int border, int
                 int4 *__restrict__ out, int *__restrict__ count) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x < border || y < border || x >= w - border || y >= h - border) return;
-  const int s = score[size_t(y) * w + x];
+  const uint8_t *pc = score + size_t(y) * w + x;
+  const int s = pc[0];
   if (s == 0) return;
   bool keep = true;
 #pragma unroll
   for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
     for (int dx = -1; dx <= 1; ++dx)
-      if (dx || dy) keep = keep && s > int(score[size_t(y + dy) * w + x + dx]);
+      if (dx || dy) keep = keep && s > int(pc[dy * w + dx]);
   if (!keep) return;
   const int slot = atomicAdd(count, 1);
   if (slot < capacity) out[slot] = make_int4(x, y, s, level);
@@ -625,6 +629,28 @@ int tod_orb_detect_and_compute(tod_orb *o, const uint8_t *image, int32_t height,
     k.class_id = -1;
   }
   *n_keypoints = n;
+  return TOD_OK;
+}
+
+int tod_orb_read_level(tod_orb *o, int32_t level, int32_t kind, uint8_t *out, int32_t *height, int32_t *width) {
+  TOD_REQUIRE(o && level >= 0 && level < o->p.n_levels && kind >= 0 && kind <= 2, "bad argument");
+  if (o->height == 0) return fail(TOD_ERR_STATE, "no frame has been processed yet");
+  TOD_CUDA(cudaSetDevice(o->p.device));
+  const int w = o->lw[level], h = o->lh[level];
+  if (height) *height = h;
+  if (width) *width = w;
+  if (!out) return TOD_OK;
+  const uint8_t *src = kind == 0 ? o->d_img[level].as<uint8_t>() : o->d_smooth[level].as<uint8_t>();
+  if (kind == 2) {  // FAST corner scores of the level, recomputed
+    dim3 grid((w + 255) / 256, h);
+    tod::fast_score_kernel<<<grid, 256, 0, o->stream>>>(o->d_img[level].as<uint8_t>(), w, h, 20,
+                                                        o->d_score.as<uint8_t>());
+    tod::count_launch();
+    TOD_CUDA(cudaGetLastError());
+    src = o->d_score.as<uint8_t>();
+  }
+  TOD_CUDA(cudaMemcpyAsync(out, src, size_t(w) * size_t(h), cudaMemcpyDeviceToHost, o->stream));
+  TOD_CUDA(cudaStreamSynchronize(o->stream));
   return TOD_OK;
 }
 
