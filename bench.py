@@ -397,6 +397,53 @@ def pipeline_leg(args, descs, points, hbm_peak, hbm_src):
     return e2e, stages
 
 
+def feature_leg(args):
+    """The stage in front of the hot path (SURVEY.md §8f rank 2): cv::ORB(5000, 1.2, 3) on one synthetic 1280 x 960
+    frame and DepthTo3d, on the GPU through the C-ABI with host buffers, beside cv2.ORB on the host cores, with the
+    parity of this very frame (keypoint set and descriptors)."""
+    from tod_b200 import FeatureDescriptor, depth_to_3d, synth
+    h, w, nf = 960, 1280, 5000
+    img = synth.make_textured_image(h, w, seed=synth.BASE_SEED + 41, n_shapes=1500)
+    zf, _ = synth.make_depth_image(h, w, seed=synth.BASE_SEED + 42)
+    K = np.array([[1050.0, 0, 639.5], [0, 1050.0, 479.5], [0, 0, 1]], np.float32)
+    fd = FeatureDescriptor(n_features=nf)
+    t_orb, t_d3 = [], []
+    for _ in range(6):
+        t0 = time.perf_counter()
+        kp, desc = fd.process(img)
+        t1 = time.perf_counter()
+        depth_to_3d(zf, K)
+        t2 = time.perf_counter()
+        t_orb.append(t1 - t0)
+        t_d3.append(t2 - t1)
+    fd.close()
+    out = {"workload": "one %dx%d frame, ORB n_features %d, n_levels 3, scale_factor 1.2 (conf/detection.ork:23-31)" % (w, h, nf),
+           "orb_ms_per_frame": 1e3 * float(np.median(t_orb[1:])), "keypoints": int(kp.shape[0]),
+           "depth_to_3d_ms_per_frame": 1e3 * float(np.median(t_d3[1:])),
+           "scope": "tod_orb_detect_and_compute / tod_depth_to_3d with host buffers (H2D of the frame, D2H of keypoints, "
+                    "descriptors and the point image inside)"}
+    try:
+        import cv2
+        orb = cv2.ORB_create(nf, 1.2, 3)
+        tt = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            kps, des = orb.detectAndCompute(img, None)
+            tt.append(time.perf_counter() - t0)
+        ref = {(k.octave, float(k.pt[0]), float(k.pt[1])): i for i, k in enumerate(kps)}
+        mine = [(int(k["octave"]), float(k["x"]), float(k["y"])) for k in kp]
+        same_set = set(mine) == set(ref)
+        bad = -1
+        if same_set:
+            bad = int((desc != des[[ref[m] for m in mine]]).any(axis=1).sum())
+        out["cpu_baseline"] = {"value": 1e3 * float(np.median(tt[1:])), "unit": "ms/frame", "kind": "reference",
+                               "cores": cv2.getNumThreads(), "what": "cv2 %s ORB_create(5000, 1.2, 3).detectAndCompute" % cv2.__version__}
+        out["parity"] = {"keypoints_cv2": len(kps), "same_keypoint_set": bool(same_set), "descriptor_rows_differing": bad}
+    except ImportError:
+        out["cpu_baseline"] = None
+    return out
+
+
 def c5_leg(args, hbm_peak, hbm_src):
     """BASELINE config C5 (RANSAC stress): 100 objects x 2000 correspondences, 90 % outlier matches injected at the
     GuessGenerator boundary, 4096 iterations per object."""
@@ -715,6 +762,7 @@ def run_ours(args):
         line["stages"] = stages
         if args.c5_objects > 0:
             line["stages_c5"] = c5_leg(args, hbm_peak, hbm_src)
+        line["feature_stage"] = feature_leg(args)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
