@@ -243,15 +243,56 @@ int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t w
 int tod_orb_detect_and_compute(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, int32_t n_features,
                                tod_keypoint *keypoints, int32_t max_keypoints, int32_t *n_keypoints,
                                uint8_t *descriptors, const void **d_descriptors);
+/* The same with a detection mask (u8, height x width; keypoints on zero pixels are dropped level by level on ORB's mask
+ * pyramid — cv::ORB::detectAndCompute(image, mask, ...)) and with grey (channels = 1) or BGR (channels = 3: converted
+ * like cv::cvtColor(BGR2GRAY)) frames.  mask may be NULL. */
+int tod_orb_detect_and_compute_masked(tod_orb *o, const uint8_t *image, int32_t channels, int32_t height,
+                                      int32_t width, const uint8_t *mask, int32_t n_features, tod_keypoint *keypoints,
+                                      int32_t max_keypoints, int32_t *n_keypoints, uint8_t *descriptors,
+                                      const void **d_descriptors);
 /* Reads back one pyramid level of the last processed frame (for stage-by-stage parity tests): kind 0 = the level as
  * resized, 1 = smoothed, 2 = its FAST corner scores (0 = no corner).  out = height x width u8, may be NULL to query the
  * level size only. */
 int tod_orb_read_level(tod_orb *o, int32_t level, int32_t kind, uint8_t *out, int32_t *height, int32_t *width);
 /* DepthTo3d: depth = height x width float32 metres (NaN = invalid) or, with depth_is_u16, uint16 millimetres (0 =
- * invalid); K = 3 x 3 row-major camera matrix (float); points3d = height x width x 3 f32 (host): x = (u - cx) z / fx,
- * y = (v - cy) z / fy, z — NaN where the depth is invalid: the `points3d` input of the GuessGenerator. */
+ * invalid); K = 3 x 3 row-major camera matrix (float); points3d = height x width x 3 f32 (host):
+ * x = ((u - cx) (1 / fx)) z, y = ((v - cy) (1 / fy)) z, z — NaN where the depth is invalid: the `points3d` input of the
+ * GuessGenerator. */
 int tod_depth_to_3d(int32_t device, const void *depth, int32_t depth_is_u16, int32_t height, int32_t width,
                     const float *K, float *points3d);
+
+/* ================================================================================================================
+ * Offline training path: the Trainer cell (src/training/Trainer.cpp:121-187) with its helpers
+ * (training.cpp:57-195) — per observation of an object: ORB features on the masked image, depth rescaled to the image,
+ * keypoints validated against the eroded mask and the depth, back-projection, camera -> object frame, and the views
+ * stacked into the model the DescriptorMatcher loads (descriptors N x 32 u8, points N x 3 f32: ModelFiller.cpp:23-24).
+ * The DB view iteration (Trainer.cpp:124-133) is the caller's loop.  Keypoints come out ordered by (octave, row,
+ * column), so the model holds the reference's (descriptor, point) pairs in a different row order.
+ * ============================================================================================================== */
+
+typedef struct tod_trainer tod_trainer;
+typedef struct tod_trainer_params {
+  int32_t n_features;   /* 500: Trainer.cpp:142-150 builds cv::ORB without parameters (its TODO), so OpenCV's defaults */
+  int32_t n_levels;     /* 8 */
+  float scale_factor;   /* 1.2 */
+  int32_t device;
+} tod_trainer_params;
+
+void tod_trainer_default_params(tod_trainer_params *p);
+int tod_trainer_create(const tod_trainer_params *p, tod_trainer **out);
+void tod_trainer_destroy(tod_trainer *t);
+/* One observation (the body of the loop, Trainer.cpp:134-171): image = height x width x channels u8 (1 grey, 3 BGR),
+ * mask = height x width u8 (object pixels non-zero), depth = depth_height x depth_width float32 metres or uint16
+ * millimetres (rescaled to the image like rescale_depth, :63-81), K = 3 x 3 camera matrix, R (3 x 3) and T (3) = the
+ * observation's pose (cameraToWorld computes (p - T) * R, training.cpp:175-195).  *n_added = points appended. */
+int tod_trainer_add_observation(tod_trainer *t, const uint8_t *image, int32_t channels, int32_t height, int32_t width,
+                                const uint8_t *mask, const void *depth, int32_t depth_is_u16, int32_t depth_height,
+                                int32_t depth_width, const float *K, const float *R, const float *T,
+                                int32_t *n_added);
+/* mergePoints (training.cpp:147-173): the stacked model so far; pointers stay valid until the next add / clear. */
+int tod_trainer_model(const tod_trainer *t, const uint8_t **descriptors, const float **points, int64_t *n);
+int64_t tod_trainer_num_points(const tod_trainer *t);
+int tod_trainer_clear(tod_trainer *t);
 
 /* ================================================================================================================
  * Geometry stages (adjacency_ransac.cpp, sac_model_registration_graph.h) — exposed for parity tests and reuse

@@ -21,9 +21,9 @@ tests/golden/orb_*.npz (made by tests/golden/make_orb_golden.py):
   descriptor  steered BRIEF: 256 comparisons of the smoothed level image at pattern points rotated by the angle
               (cosf / sinf of angle * pi/180 in float, products and differences in float, cvRound = half to even);
               pattern = oracle/orb_pattern.npy (recovered from cv2, tools/recover_orb_pattern.py).
-  depth -> 3D x = (u - cx) z / fx, y = (v - cy) z / fy, z = depth (metres; uint16 = millimetres, 0 = invalid -> NaN):
-              the published formula of cv::rgbd::depthTo3d, which this image's cv2 does not ship — parity unpinned for
-              this one function (checked against a float64 evaluation only).
+  depth -> 3D x = ((u - cx) (1 / fx)) z, y = ((v - cy) (1 / fy)) z, z = depth (metres; uint16 = millimetres, 0 = invalid
+              -> NaN): the published formula of cv::rgbd::depthTo3d, which this image's cv2 does not ship — parity
+              unpinned for this one function (checked against a float64 evaluation only).
 """
 import ctypes
 import math
@@ -261,15 +261,31 @@ def features_per_level(n_features, n_levels, scale_factor=1.2):
     return out
 
 
-def detect(img, n_features=5000, n_levels=3, scale_factor=1.2):
+def mask_pyramid(mask, n_levels=3, scale_factor=1.2):
+    """ORB's mask pyramid: every level is the previous one resized (INTER_LINEAR_EXACT), then values below 255 -> 0
+    (cv::threshold(254, THRESH_TOZERO))."""
+    levels = [np.ascontiguousarray(mask, np.uint8)]
+    for l, (h, w) in enumerate(level_sizes(mask.shape[0], mask.shape[1], n_levels, scale_factor)):
+        if l:
+            m = resize_linear_exact(levels[-1], h, w)
+            levels.append(np.where(m > 254, m, 0).astype(np.uint8))
+    return levels
+
+
+def detect(img, n_features=5000, n_levels=3, scale_factor=1.2, mask=None):
     """Keypoints of cv::ORB::detect as a list of (octave, x_level, y_level, harris_response), ordered by level, row,
-    column (cv2's own order is an artefact of nth_element)."""
+    column (cv2's own order is an artefact of nth_element).  mask: u8 image, keypoints on zero pixels are dropped
+    (KeyPointsFilter::runByPixelsMask on every level's resized mask)."""
     levels = pyramid(img, n_levels, scale_factor)
+    masks = mask_pyramid(mask, n_levels, scale_factor) if mask is not None else None
     per_level = features_per_level(n_features, n_levels, scale_factor)
     out = []
     for l, lev in enumerate(levels):
         s = fast_scores(lev)
-        ys, xs = np.nonzero(non_max_suppression(s))
+        keep = non_max_suppression(s)
+        if masks is not None:
+            keep &= masks[l] != 0
+        ys, xs = np.nonzero(keep)
         h, w = lev.shape
         inside = (xs >= 31) & (xs < w - 31) & (ys >= 31) & (ys < h - 31)
         xs, ys = xs[inside], ys[inside]
@@ -294,8 +310,11 @@ def depth_to_3d(depth, K):
     h, w = z.shape
     u = np.arange(w, dtype=F32)[None, :]
     v = np.arange(h, dtype=F32)[:, None]
-    x = ((u - cx).astype(F32) * z).astype(F32) / fx
-    y = ((v - cy).astype(F32) * z).astype(F32) / fy
+    # cv::rgbd::depthTo3d (dense, no mask) caches (u - cx) * (1 / fx) per column and (v - cy) * (1 / fy) per row, then
+    # multiplies by z — restated from the published source, which this image does not hold
+    inv_fx, inv_fy = F32(1.0) / fx, F32(1.0) / fy
+    x = ((u - cx).astype(F32) * inv_fx).astype(F32) * z
+    y = ((v - cy).astype(F32) * inv_fy).astype(F32) * z
     out = np.stack([x.astype(F32), y.astype(F32), z], axis=2)
     out[np.isnan(z)] = np.nan
     return out

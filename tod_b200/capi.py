@@ -40,6 +40,11 @@ class OrbParams(ctypes.Structure):
                 ("reserved", ctypes.c_int32)]
 
 
+class TrainerParams(ctypes.Structure):
+    _fields_ = [("n_features", ctypes.c_int32), ("n_levels", ctypes.c_int32), ("scale_factor", ctypes.c_float),
+                ("device", ctypes.c_int32)]
+
+
 class TodError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("tod_b200 error %d: %s" % (code, msg))
@@ -96,6 +101,16 @@ SIGNATURES = [
     ("tod_orb_describe", ctypes.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _P, ctypes.POINTER(_P)]),
     ("tod_orb_detect_and_compute", ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, ctypes.POINTER(_I32), _P,
                                                   ctypes.POINTER(_P)]),
+    ("tod_orb_detect_and_compute_masked", ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, _P, _I32,
+                                                         ctypes.POINTER(_I32), _P, ctypes.POINTER(_P)]),
+    ("tod_trainer_default_params", None, [ctypes.POINTER(TrainerParams)]),
+    ("tod_trainer_create", ctypes.c_int, [ctypes.POINTER(TrainerParams), ctypes.POINTER(_P)]),
+    ("tod_trainer_destroy", None, [_P]),
+    ("tod_trainer_add_observation", ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P,
+                                                   ctypes.POINTER(_I32)]),
+    ("tod_trainer_model", ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_I64)]),
+    ("tod_trainer_num_points", _I64, [_P]),
+    ("tod_trainer_clear", ctypes.c_int, [_P]),
     ("tod_orb_read_level", ctypes.c_int, [_P, _I32, _I32, _P, ctypes.POINTER(_I32), ctypes.POINTER(_I32)]),
     ("tod_depth_to_3d", ctypes.c_int, [_I32, _P, _I32, _I32, _I32, _P, _P]),
     ("tod_adjacency_row_words", _I32, [_I32]),

@@ -389,6 +389,22 @@ class FeatureDescriptor:
         self.last_device_descriptors = dptr.value
         return kp[:n.value].copy(), desc[:n.value].copy()
 
+    def process_masked(self, image, mask):
+        """cv::ORB::detectAndCompute(image, mask): image H x W (grey) or H x W x 3 (BGR) u8, mask H x W u8 or None."""
+        img = np.ascontiguousarray(image, np.uint8)
+        ch = 1 if img.ndim == 2 else int(img.shape[2])
+        mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        cap = 2 * self.n_features + 1024
+        kp = np.zeros(cap, capi.KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = ctypes.c_int32(0)
+        dptr = ctypes.c_void_p()
+        capi.check(self._lib.tod_orb_detect_and_compute_masked(self._h, capi._ptr(img), ch, img.shape[0], img.shape[1],
+                                                               capi._ptr(mk), self.n_features, capi._ptr(kp), cap,
+                                                               ctypes.byref(n), capi._ptr(desc), ctypes.byref(dptr)))
+        self.last_device_descriptors = dptr.value
+        return kp[:n.value].copy(), desc[:n.value].copy()
+
     def read_level(self, level, kind=0):
         """One pyramid level of the last frame: kind 0 = resized, 1 = smoothed, 2 = FAST corner scores."""
         h, w = ctypes.c_int32(0), ctypes.c_int32(0)
@@ -410,6 +426,58 @@ class FeatureDescriptor:
                                               ctypes.byref(dptr)))
         self.last_device_descriptors = dptr.value
         return kp, desc
+
+
+class Trainer:
+    """Mirror of the reference's Trainer cell (src/training/Trainer.cpp:83-187): observations of one object in, the
+    stacked `descriptors` (N x 32 u8) and `points` (N x 3 f32, object frame) out — what ModelFiller stores
+    (ModelFiller.cpp:23-24) and DescriptorMatcher.add_object / dbio.write_snapshot take."""
+
+    def __init__(self, n_features=500, n_levels=8, scale_factor=1.2, device=0):
+        lib = capi.load()
+        p = capi.TrainerParams()
+        lib.tod_trainer_default_params(ctypes.byref(p))
+        p.n_features, p.n_levels, p.scale_factor, p.device = int(n_features), int(n_levels), float(scale_factor), int(device)
+        self._h = ctypes.c_void_p()
+        capi.check(lib.tod_trainer_create(ctypes.byref(p), ctypes.byref(self._h)))
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tod_trainer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def add_observation(self, image, mask, depth, K, R, T):
+        """One observation (obs.image, obs.mask, obs.depth, obs.K, obs.R, obs.T).  Returns the number of points added."""
+        img = np.ascontiguousarray(image, np.uint8)
+        ch = 1 if img.ndim == 2 else int(img.shape[2])
+        mk = np.ascontiguousarray(mask, np.uint8)
+        d = np.ascontiguousarray(depth)
+        assert d.dtype in (np.float32, np.uint16) and mk.shape == img.shape[:2]
+        k = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
+        r = np.ascontiguousarray(np.asarray(R, np.float32).reshape(9))
+        t = np.ascontiguousarray(np.asarray(T, np.float32).reshape(3))
+        n = ctypes.c_int32(0)
+        capi.check(self._lib.tod_trainer_add_observation(self._h, capi._ptr(img), ch, img.shape[0], img.shape[1],
+                                                         capi._ptr(mk), capi._ptr(d), 1 if d.dtype == np.uint16 else 0,
+                                                         d.shape[0], d.shape[1], capi._ptr(k), capi._ptr(r),
+                                                         capi._ptr(t), ctypes.byref(n)))
+        return n.value
+
+    def model(self):
+        """(descriptors N x 32 u8, points N x 3 f32): mergePoints over the observations added so far."""
+        dp, pp, n = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64(0)
+        capi.check(self._lib.tod_trainer_model(self._h, ctypes.byref(dp), ctypes.byref(pp), ctypes.byref(n)))
+        if n.value == 0:
+            return np.zeros((0, 32), np.uint8), np.zeros((0, 3), np.float32)
+        d = np.ctypeslib.as_array(ctypes.cast(dp, ctypes.POINTER(ctypes.c_uint8)), (n.value, 32)).copy()
+        p = np.ctypeslib.as_array(ctypes.cast(pp, ctypes.POINTER(ctypes.c_float)), (n.value, 3)).copy()
+        return d, p
+
+    def clear(self):
+        capi.check(self._lib.tod_trainer_clear(self._h))
 
 
 def depth_to_3d(depth, K, device=0):

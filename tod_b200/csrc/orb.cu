@@ -188,8 +188,9 @@ depth_to_3d_kernel(const T *__restrict__ depth, int w, int h, float fx, float fy
     o[0] = o[1] = o[2] = __int_as_float(0x7fc00000);
     return;
   }
-  o[0] = __fdiv_rn(__fmul_rn(__fsub_rn(float(x), cx), z), fx);
-  o[1] = __fdiv_rn(__fmul_rn(__fsub_rn(float(y), cy), z), fy);
+  // cv::rgbd::depthTo3d caches (u - cx) * (1 / fx) per column, (v - cy) * (1 / fy) per row, then multiplies by z
+  o[0] = __fmul_rn(__fmul_rn(__fsub_rn(float(x), cx), __fdiv_rn(1.f, fx)), z);
+  o[1] = __fmul_rn(__fmul_rn(__fsub_rn(float(y), cy), __fdiv_rn(1.f, fy)), z);
   o[2] = z;
 }
 
@@ -234,9 +235,10 @@ fast_score_kernel(const uint8_t *__restrict__ img, int w, int h, int threshold, 
 // (KeyPointsFilter::runByImageBorder with ORB's edgeThreshold); candidates are appended in arbitrary order.
 __global__ void __launch_bounds__(256)
 fast_nms_kernel(const uint8_t *__restrict__ score, int w, int h, int border, int level, int capacity,
-                int4 *__restrict__ out, int *__restrict__ count) {
+                int4 *__restrict__ out, int *__restrict__ count, const uint8_t *__restrict__ mask) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x < border || y < border || x >= w - border || y >= h - border) return;
+  if (mask && mask[size_t(y) * w + x] == 0) return;  // KeyPointsFilter::runByPixelsMask on this level's mask
   const uint8_t *pc = score + size_t(y) * w + x;
   const int s = pc[0];
   if (s == 0) return;
@@ -249,6 +251,107 @@ fast_nms_kernel(const uint8_t *__restrict__ score, int w, int h, int border, int
   if (!keep) return;
   const int slot = atomicAdd(count, 1);
   if (slot < capacity) out[slot] = make_int4(x, y, s, level);
+}
+
+// cv::threshold(mask, mask, 254, 0, THRESH_TOZERO): the resized mask levels keep only fully covered pixels
+__global__ void __launch_bounds__(256) threshold_tozero_kernel(uint8_t *__restrict__ m, size_t n) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && m[i] <= 254) m[i] = 0;
+}
+
+// cv::cvtColor(COLOR_BGR2GRAY), 8-bit: (B 3735 + G 19235 + R 9798 + 2^14) >> 15
+__global__ void __launch_bounds__(256)
+bgr_to_gray_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ gray, size_t n) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
+  gray[i] = uint8_t((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15);
+}
+
+// one pass of cv::erode with the default 3 x 3 rectangle; pixels outside the image do not erode
+__global__ void __launch_bounds__(256)
+erode3x3_kernel(const uint8_t *__restrict__ src, int w, int h, uint8_t *__restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  int m = 255;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = x + dx, yy = y + dy;
+      if (xx >= 0 && yy >= 0 && xx < w && yy < h) m = min(m, int(src[size_t(yy) * w + xx]));
+    }
+  dst[size_t(y) * w + x] = uint8_t(m);
+}
+
+// rescale_depth (Trainer.cpp:63-81): depth -> float32 metres (uint16 millimetres, 0 -> NaN) on an image-sized canvas;
+// when the depth image is smaller, nearest-neighbour resize into the top sub_h rows, NaN below
+template <typename T>
+__global__ void __launch_bounds__(256)
+rescale_depth_kernel(const T *__restrict__ depth, int dw, int dh, int iw, int ih, int sub_h, float *__restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= iw || y >= ih) return;
+  float z = __int_as_float(0x7fc00000);
+  if (y < sub_h) {
+    const int sy = (dh == ih && dw == iw) ? y : min(int(floor(double(y) * (double(dh) / double(sub_h)))), dh - 1);
+    const int sx = (dh == ih && dw == iw) ? x : min(int(floor(double(x) * (double(dw) / double(iw)))), dw - 1);
+    if (sizeof(T) == 2) {
+      const unsigned d = unsigned(depth[size_t(sy) * dw + sx]);
+      if (d != 0) z = __fmul_rn(float(d), 0.001f);
+    } else {
+      z = float(depth[size_t(sy) * dw + sx]);
+    }
+  }
+  out[size_t(y) * iw + x] = z;
+}
+
+struct TrainView {
+  float fx, fy, cx, cy;
+  float R[9], T[3];
+};
+
+// validateKeyPoints (training.cpp:57-145) + depthTo3dSparse + cameraToWorld (training.cpp:175-195), one thread per
+// keypoint: keep[i] = 1 and world[i] = ((p - T) * R) when the keypoint (or the nearest masked pixel of its 5 x 5
+// neighbourhood) lies in the eroded mask and the depth there is valid.
+__global__ void __launch_bounds__(128)
+train_validate_kernel(const float *__restrict__ kx, const float *__restrict__ ky, int n,
+                      const uint8_t *__restrict__ mask, const float *__restrict__ depth, int w, int h, TrainView v,
+                      uint8_t *__restrict__ keep, float *__restrict__ world) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float fx = kx[i], fy = ky[i];
+  int x = min(max(__float2int_rn(fx), 0), w), y = min(max(__float2int_rn(fy), 0), h);
+  auto in_mask = [&](int yy, int xx) { return xx >= 0 && yy >= 0 && xx < w && yy < h && mask[size_t(yy) * w + xx] != 0; };
+  bool good = in_mask(y, x);
+  if (!good) {
+    float best = __int_as_float(0x7f800000);
+    const int x0 = x, y0 = y;
+    for (int ii = max(x0 - 2, 0); ii <= min(x0 + 2, w); ++ii)
+      for (int jj = max(y0 - 2, 0); jj <= min(y0 + 2, h); ++jj)
+        if (in_mask(jj, ii)) {
+          const float dx = __fsub_rn(float(ii), fx), dy = __fsub_rn(float(jj), fy);
+          const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+          if (d2 < best) {
+            best = d2;
+            x = ii;
+            y = jj;
+            good = true;
+          }
+        }
+  }
+  float z = 0.f;
+  if (good) {
+    z = depth[size_t(y) * w + x];
+    good = !isnan(z);
+  }
+  keep[i] = good ? 1 : 0;
+  if (!good) return;
+  // depthTo3dSparse: ((u - cx) / fx) z ; cameraToWorld: (p - T) * R in float, products added left to right
+  const float px = __fmul_rn(__fdiv_rn(__fsub_rn(float(x), v.cx), v.fx), z);
+  const float py = __fmul_rn(__fdiv_rn(__fsub_rn(float(y), v.cy), v.fy), z);
+  const float a0 = __fsub_rn(px, v.T[0]), a1 = __fsub_rn(py, v.T[1]), a2 = __fsub_rn(z, v.T[2]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    world[size_t(i) * 3 + j] =
+        __fadd_rn(__fadd_rn(__fmul_rn(a0, v.R[j]), __fmul_rn(a1, v.R[3 + j])), __fmul_rn(a2, v.R[6 + j]));
 }
 
 // cv::ORB's HarrisResponses (blockSize 7, k = 0.04) on the unsmoothed level: integer sums of the Sobel products over the
@@ -311,6 +414,7 @@ struct tod_orb {
   DeviceBuffer d_img[tod::kMaxLevels], d_smooth[tod::kMaxLevels], d_rowf, d_tables[tod::kMaxLevels];
   DeviceBuffer d_kx, d_ky, d_oct, d_angle, d_desc;
   DeviceBuffer d_score, d_cand, d_count, d_resp;  // detection: FAST score image, candidate list, counter, Harris
+  DeviceBuffer d_mask[tod::kMaxLevels], d_bgr;    // optional detection mask pyramid; staging of a BGR frame
   bool pattern_uploaded = false;
 };
 
@@ -351,7 +455,9 @@ void tod_orb_destroy(tod_orb *o) {
     o->d_img[l].release();
     o->d_smooth[l].release();
     o->d_tables[l].release();
+    o->d_mask[l].release();
   }
+  o->d_bgr.release();
   for (DeviceBuffer *b : {&o->d_rowf, &o->d_kx, &o->d_ky, &o->d_oct, &o->d_angle, &o->d_desc, &o->d_score, &o->d_cand,
                           &o->d_count, &o->d_resp})
     b->release();
@@ -396,13 +502,22 @@ int orb_prepare(tod_orb *o, int height, int width) {
 }
 
 // Upload the frame, build the pyramid (unsmoothed + smoothed levels) on the handle's stream.
-int orb_build_pyramid(tod_orb *o, const uint8_t *image, tod::Levels *lv) {
+int orb_build_pyramid(tod_orb *o, const uint8_t *image, tod::Levels *lv, int channels = 1) {
   cudaStream_t st = o->stream;
   if (!o->pattern_uploaded) {
     TOD_CUDA(cudaMemcpyToSymbol(tod::c_pattern, tod::kOrbPattern, sizeof(tod::kOrbPattern)));
     o->pattern_uploaded = true;
   }
-  TOD_CUDA(cudaMemcpyAsync(o->d_img[0].ptr, image, size_t(o->width) * size_t(o->height), cudaMemcpyHostToDevice, st));
+  const size_t px0 = size_t(o->width) * size_t(o->height);
+  if (channels == 3) {  // cv::ORB converts a colour frame itself: cvtColor(BGR2GRAY)
+    TOD_CUDA(o->d_bgr.reserve(px0 * 3));
+    TOD_CUDA(cudaMemcpyAsync(o->d_bgr.ptr, image, px0 * 3, cudaMemcpyHostToDevice, st));
+    tod::bgr_to_gray_kernel<<<unsigned((px0 + 255) / 256), 256, 0, st>>>(o->d_bgr.as<uint8_t>(),
+                                                                          o->d_img[0].as<uint8_t>(), px0);
+    tod::count_launch();
+  } else {
+    TOD_CUDA(cudaMemcpyAsync(o->d_img[0].ptr, image, px0, cudaMemcpyHostToDevice, st));
+  }
   for (int l = 0; l < o->p.n_levels; ++l) {
     const int w = o->lw[l], h = o->lh[l];
     dim3 grid((w + 255) / 256, h);
@@ -520,7 +635,16 @@ int tod_orb_describe(tod_orb *o, const uint8_t *image, int32_t height, int32_t w
 int tod_orb_detect_and_compute(tod_orb *o, const uint8_t *image, int32_t height, int32_t width, int32_t n_features,
                                tod_keypoint *keypoints, int32_t max_keypoints, int32_t *n_keypoints,
                                uint8_t *descriptors, const void **d_descriptors) {
+  return tod_orb_detect_and_compute_masked(o, image, 1, height, width, nullptr, n_features, keypoints, max_keypoints,
+                                           n_keypoints, descriptors, d_descriptors);
+}
+
+int tod_orb_detect_and_compute_masked(tod_orb *o, const uint8_t *image, int32_t channels, int32_t height,
+                                      int32_t width, const uint8_t *mask, int32_t n_features, tod_keypoint *keypoints,
+                                      int32_t max_keypoints, int32_t *n_keypoints, uint8_t *descriptors,
+                                      const void **d_descriptors) {
   TOD_REQUIRE(o && image && keypoints && n_keypoints && n_features >= 0 && max_keypoints >= 0, "bad argument");
+  TOD_REQUIRE(channels == 1 || channels == 3, "image must have 1 (grey) or 3 (BGR) channels");
   *n_keypoints = 0;
   TOD_CUDA(cudaSetDevice(o->p.device));
   if (int rc = orb_prepare(o, height, width)) return rc;
@@ -528,7 +652,26 @@ int tod_orb_detect_and_compute(tod_orb *o, const uint8_t *image, int32_t height,
   const int L = o->p.n_levels;
   const int kEdge = 31, kFastThreshold = 20;  // cv::ORB defaults: edgeThreshold, fastThreshold
   tod::Levels lv{};
-  if (int rc = orb_build_pyramid(o, image, &lv)) return rc;
+  if (int rc = orb_build_pyramid(o, image, &lv, channels)) return rc;
+  if (mask) {
+    // ORB's mask pyramid: level l = resize(level l-1, INTER_LINEAR_EXACT), then everything below 255 -> 0
+    for (int l = 0; l < L; ++l) {
+      const size_t px = size_t(o->lw[l]) * size_t(o->lh[l]);
+      TOD_CUDA(o->d_mask[l].reserve(px));
+      if (l == 0) {
+        TOD_CUDA(cudaMemcpyAsync(o->d_mask[0].ptr, mask, px, cudaMemcpyHostToDevice, st));
+      } else {
+        const int w = o->lw[l], h = o->lh[l];
+        const int *t = o->d_tables[l].as<int>();
+        dim3 grid((w + 255) / 256, h);
+        tod::resize_exact_kernel<<<grid, 256, 0, st>>>(o->d_mask[l - 1].as<uint8_t>(), o->lw[l - 1],
+                                                       o->d_mask[l].as<uint8_t>(), w, h, t, t + w, t + 2 * w,
+                                                       t + 3 * w, t + 3 * w + h, t + 3 * w + 2 * h);
+        tod::threshold_tozero_kernel<<<unsigned((px + 255) / 256), 256, 0, st>>>(o->d_mask[l].as<uint8_t>(), px);
+        tod::count_launch(2);
+      }
+    }
+  }
   // features per level (ORB_Impl::computeKeyPoints): a geometric series over the levels, the last level takes the rest
   std::vector<int> per_level(static_cast<size_t>(L), 0);
   {
@@ -553,7 +696,8 @@ int tod_orb_detect_and_compute(tod_orb *o, const uint8_t *image, int32_t height,
     tod::fast_score_kernel<<<grid, 256, 0, st>>>(o->d_img[l].as<uint8_t>(), w, h, kFastThreshold,
                                                  o->d_score.as<uint8_t>());
     tod::fast_nms_kernel<<<grid, 256, 0, st>>>(o->d_score.as<uint8_t>(), w, h, kEdge, l, capacity,
-                                               o->d_cand.as<int4>(), o->d_count.as<int>());
+                                               o->d_cand.as<int4>(), o->d_count.as<int>(),
+                                               mask ? o->d_mask[l].as<uint8_t>() : nullptr);
     tod::count_launch(2);
   }
   TOD_CUDA(cudaGetLastError());
@@ -629,6 +773,156 @@ int tod_orb_detect_and_compute(tod_orb *o, const uint8_t *image, int32_t height,
     k.class_id = -1;
   }
   *n_keypoints = n;
+  return TOD_OK;
+}
+
+}  // extern "C"
+
+// ---- the offline training path (Trainer.cpp:121-187, training.cpp) ---------------------------------------------------
+struct tod_trainer {
+  tod_trainer_params p{};
+  tod_orb *orb = nullptr;
+  DeviceBuffer d_mask_a, d_mask_b, d_depth_in, d_depth, d_kx, d_ky, d_keep, d_world;
+  std::vector<uint8_t> desc;   // merged model: n x 32
+  std::vector<float> points;   // n x 3, object frame
+};
+
+extern "C" {
+
+void tod_trainer_default_params(tod_trainer_params *p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->n_features = 500;     // cv::ORB's own defaults: Trainer.cpp:142-150 builds the extractor without parameters
+  p->n_levels = 8;
+  p->scale_factor = 1.2f;
+  p->device = 0;
+}
+
+int tod_trainer_create(const tod_trainer_params *p, tod_trainer **out) {
+  TOD_REQUIRE(p && out && p->n_features >= 0, "bad argument");
+  tod_orb_params op;
+  tod_orb_default_params(&op);
+  op.n_levels = p->n_levels;
+  op.scale_factor = p->scale_factor;
+  op.device = p->device;
+  tod_orb *orb = nullptr;
+  if (int rc = tod_orb_create(&op, &orb)) return rc;
+  tod_trainer *t = new tod_trainer();
+  t->p = *p;
+  t->orb = orb;
+  *out = t;
+  return TOD_OK;
+}
+
+void tod_trainer_destroy(tod_trainer *t) {
+  if (!t) return;
+  cudaSetDevice(t->p.device);
+  for (DeviceBuffer *b : {&t->d_mask_a, &t->d_mask_b, &t->d_depth_in, &t->d_depth, &t->d_kx, &t->d_ky, &t->d_keep,
+                          &t->d_world})
+    b->release();
+  tod_orb_destroy(t->orb);
+  delete t;
+}
+
+int tod_trainer_clear(tod_trainer *t) {
+  TOD_REQUIRE(t, "null argument");
+  t->desc.clear();
+  t->points.clear();
+  return TOD_OK;
+}
+
+int64_t tod_trainer_num_points(const tod_trainer *t) { return t ? int64_t(t->desc.size() / 32) : 0; }
+
+int tod_trainer_model(const tod_trainer *t, const uint8_t **descriptors, const float **points, int64_t *n) {
+  TOD_REQUIRE(t, "null argument");
+  if (descriptors) *descriptors = t->desc.data();
+  if (points) *points = t->points.data();
+  if (n) *n = int64_t(t->desc.size() / 32);
+  return TOD_OK;
+}
+
+int tod_trainer_add_observation(tod_trainer *t, const uint8_t *image, int32_t channels, int32_t height, int32_t width,
+                                const uint8_t *mask, const void *depth, int32_t depth_is_u16, int32_t depth_height,
+                                int32_t depth_width, const float *K, const float *R, const float *T,
+                                int32_t *n_added) {
+  TOD_REQUIRE(t && image && mask && depth && K && R && T, "null argument");
+  TOD_REQUIRE(depth_height > 0 && depth_width > 0, "bad depth size");
+  if (n_added) *n_added = 0;
+  TOD_CUDA(cudaSetDevice(t->p.device));
+  // features on the masked image (Trainer.cpp:142-150)
+  const int cap = 2 * t->p.n_features + 1024;
+  std::vector<tod_keypoint> kp(static_cast<size_t>(cap));
+  std::vector<uint8_t> desc(size_t(cap) * 32);
+  int32_t n = 0;
+  if (int rc = tod_orb_detect_and_compute_masked(t->orb, image, channels, height, width, mask, t->p.n_features,
+                                                 kp.data(), cap, &n, desc.data(), nullptr))
+    return rc;
+  if (n == 0) return TOD_OK;
+  cudaStream_t st = t->orb->stream;
+  const size_t px = size_t(height) * size_t(width);
+  // mask eroded 4 times (training.cpp:66-70)
+  TOD_CUDA(t->d_mask_a.reserve(px));
+  TOD_CUDA(t->d_mask_b.reserve(px));
+  TOD_CUDA(cudaMemcpyAsync(t->d_mask_a.ptr, mask, px, cudaMemcpyHostToDevice, st));
+  dim3 grid((width + 255) / 256, height);
+  uint8_t *ma = t->d_mask_a.as<uint8_t>(), *mb = t->d_mask_b.as<uint8_t>();
+  for (int it = 0; it < 4; ++it) {
+    tod::erode3x3_kernel<<<grid, 256, 0, st>>>(ma, width, height, mb);
+    std::swap(ma, mb);
+  }
+  tod::count_launch(4);
+  // depth rescaled to the image (Trainer.cpp:63-81, :154)
+  const size_t dpx = size_t(depth_height) * size_t(depth_width), dbytes = dpx * (depth_is_u16 ? 2 : 4);
+  TOD_CUDA(t->d_depth_in.reserve(dbytes));
+  TOD_CUDA(t->d_depth.reserve(px * 4));
+  TOD_CUDA(cudaMemcpyAsync(t->d_depth_in.ptr, depth, dbytes, cudaMemcpyHostToDevice, st));
+  const bool same = depth_height == height && depth_width == width;
+  const int sub_h = same ? height : std::min(height, int(float(depth_height) * (float(width) / float(depth_width))));
+  if (depth_is_u16)
+    tod::rescale_depth_kernel<uint16_t><<<grid, 256, 0, st>>>(t->d_depth_in.as<uint16_t>(), depth_width, depth_height,
+                                                              width, height, sub_h, t->d_depth.as<float>());
+  else
+    tod::rescale_depth_kernel<float><<<grid, 256, 0, st>>>(t->d_depth_in.as<float>(), depth_width, depth_height, width,
+                                                           height, sub_h, t->d_depth.as<float>());
+  tod::count_launch();
+  // validateKeyPoints + depthTo3dSparse + cameraToWorld (Trainer.cpp:157-171)
+  std::vector<float> hx(static_cast<size_t>(n)), hy(static_cast<size_t>(n));
+  for (int i = 0; i < n; ++i) {
+    hx[size_t(i)] = kp[size_t(i)].x;
+    hy[size_t(i)] = kp[size_t(i)].y;
+  }
+  TOD_CUDA(t->d_kx.reserve(size_t(n) * 4));
+  TOD_CUDA(t->d_ky.reserve(size_t(n) * 4));
+  TOD_CUDA(t->d_keep.reserve(size_t(n)));
+  TOD_CUDA(t->d_world.reserve(size_t(n) * 12));
+  TOD_CUDA(cudaMemcpyAsync(t->d_kx.ptr, hx.data(), size_t(n) * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(t->d_ky.ptr, hy.data(), size_t(n) * 4, cudaMemcpyHostToDevice, st));
+  tod::TrainView v{};
+  v.fx = K[0];
+  v.fy = K[4];
+  v.cx = K[2];
+  v.cy = K[5];
+  for (int i = 0; i < 9; ++i) v.R[i] = R[i];
+  for (int i = 0; i < 3; ++i) v.T[i] = T[i];
+  tod::train_validate_kernel<<<(n + 127) / 128, 128, 0, st>>>(t->d_kx.as<float>(), t->d_ky.as<float>(), n, ma,
+                                                              t->d_depth.as<float>(), width, height, v,
+                                                              t->d_keep.as<uint8_t>(), t->d_world.as<float>());
+  tod::count_launch();
+  TOD_CUDA(cudaGetLastError());
+  std::vector<uint8_t> keep(static_cast<size_t>(n));
+  std::vector<float> world(size_t(n) * 3);
+  TOD_CUDA(cudaMemcpyAsync(keep.data(), t->d_keep.ptr, size_t(n), cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaMemcpyAsync(world.data(), t->d_world.ptr, size_t(n) * 12, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  // mergePoints (training.cpp:147-173): kept keypoints appended in order
+  int added = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!keep[size_t(i)]) continue;
+    t->desc.insert(t->desc.end(), desc.begin() + size_t(i) * 32, desc.begin() + size_t(i + 1) * 32);
+    t->points.insert(t->points.end(), world.begin() + size_t(i) * 3, world.begin() + size_t(i + 1) * 3);
+    ++added;
+  }
+  if (n_added) *n_added = added;
   return TOD_OK;
 }
 

@@ -205,3 +205,29 @@ def make_depth_image(height=480, width=640, seed=BASE_SEED + 7, invalid_fraction
     zf[hole] = np.nan
     mm = np.where(hole, 0, np.rint(z * 1000.0)).astype(np.uint16)
     return zf, mm
+
+
+def make_training_views(n_views=3, height=480, width=640, seed=BASE_SEED + 8, depth_scale=1, bgr=True):
+    """Synthetic observations of one object for the training path (Trainer.cpp:134-171): per view a textured BGR (or
+    grey) image, an object mask (a disc with a hole), a depth image (float32 metres with NaN holes; optionally at
+    1/depth_scale of the image resolution), the camera matrix and a pose (R, T).  numpy only."""
+    rng = np.random.default_rng(seed)
+    views = []
+    for v in range(n_views):
+        g = make_textured_image(height, width, seed=seed + 10 * v + 1)
+        if bgr:
+            img = np.stack([g, np.roll(g, 3, axis=1), np.roll(g, -2, axis=0)], axis=2).astype(np.uint8)
+        else:
+            img = g
+        yy, xx = np.mgrid[0:height, 0:width]
+        cx, cy = width // 2 + int(rng.integers(-40, 40)), height // 2 + int(rng.integers(-30, 30))
+        mask = (((xx - cx) ** 2 + (yy - cy) ** 2) < (min(height, width) * 0.38) ** 2).astype(np.uint8) * 255
+        mask[cy - 20:cy + 25, cx - 60:cx - 20] = 0
+        dh, dw = height // depth_scale, width // depth_scale
+        zf, _ = make_depth_image(dh, dw, seed=seed + 10 * v + 2, invalid_fraction=0.05)
+        f = 525.0 * width / 640.0
+        K = np.array([[f, 0, (width - 1) / 2.0], [0, f, (height - 1) / 2.0], [0, 0, 1]], np.float32)
+        R = random_rotation(rng).astype(np.float32)
+        T = np.array([rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1), rng.uniform(0.6, 0.9)], np.float32)
+        views.append({"image": img, "mask": mask, "depth": zf, "K": K, "R": R, "T": T})
+    return views
