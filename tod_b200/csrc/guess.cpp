@@ -57,6 +57,7 @@ struct Cluster {
   std::vector<uint32_t> deg7;      // W words: valid vertices with >= 7 valid sample-neighbours this round (gate :209-213);
                                    // computed by sample_degree_mask_kernel on the GPU, or by host_degree_mask
   std::vector<uint32_t> finite;    // W words: all six coordinates finite
+  std::vector<uint32_t> vpre;      // sampler: prefix popcounts of `valid` per 64-bit word, rebuilt when a round starts
   int n_valid = 0;
   int64_t point_offset = 0, matrix_offset = 0, valid_offset = 0;
   const uint32_t *P = nullptr, *S = nullptr;  // host copies of the bit-matrices (n x W)
@@ -75,74 +76,131 @@ struct Cluster {
   int batch_begin = 0;         // offset of this cluster's hypotheses in the frame-wide batch
 };
 
-// index of the r-th set bit (ascending) of a W-word mask
-inline uint32_t select_bit(const uint32_t *m, int W, uint32_t r) {
-  for (int w = 0; w < W; ++w) {
-    const uint32_t c = uint32_t(popc32(m[w]));
-    if (r < c) {
-      uint32_t x = m[w];
-      for (uint32_t i = 0; i < r; ++i) x &= x - 1;
-      return uint32_t(w) * 32u + uint32_t(__builtin_ctz(x));
-    }
-    r -= c;
-  }
-  return 0xFFFFFFFFu;
-}
-
 inline int mask_count(const uint32_t *m, int W) {
   int c = 0;
   for (int w = 0; w < W; ++w) c += popc32(m[w]);
   return c;
 }
 
-// Per-thread scratch of the sampler: one candidate mask per recursion level (no allocation per hypothesis).
+#if defined(__x86_64__)
+inline bool have_bmi2() {
+  static const bool yes = [] {
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("bmi2") != 0;
+  }();
+  return yes;
+}
+// position of the r-th set bit: deposit a single bit at the r-th set position of x
+__attribute__((target("bmi2"))) inline int bit_select_bmi2(uint64_t x, uint32_t r) {
+  return __builtin_ctzll(_pdep_u64(1ull << r, x));
+}
+#endif
+
+// Per-thread scratch of the sampler: one candidate mask per level (64-bit words, no allocation per hypothesis).
 struct SamplerScratch {
-  std::vector<uint32_t> level[3];
-  void fit(int W) {
+  std::vector<uint64_t> level[3];
+  void fit(int W64) {
     for (auto &v : level)
-      if (int(v.size()) < W) v.resize(size_t(W));
+      if (int(v.size()) < W64) v.resize(size_t(W64));
   }
 };
 
-// drawIndexSampleHelper (sac_model_registration_graph.h:102-132) on bit masks.  `cur` (level `depth`'s mask) is
-// consumed.  out[] receives the samples deepest-first, like samples_.push_back in the reference.
-bool draw_samples(const Cluster &c, SamplerScratch &sc, int depth, int count, int n_samples, uint64_t &rng,
-                  uint32_t *out, int &n_out) {
-  if (n_samples == 0) return true;
-  if (count == 0) return false;
-  const int W = c.W;
-  uint32_t *cur = sc.level[depth].data();
-  while (true) {
-    const uint32_t r = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count));
-    const uint32_t s = select_bit(cur, W, r);
-    if (n_samples == 1) {  // the recursion below would return true at once (n_samples - 1 == 0)
-      out[n_out++] = s;
-      return true;
-    }
-    const uint32_t *row = c.S + size_t(s) * W;
-    uint32_t *next = sc.level[depth + 1].data();
-    int nc = 0;
-    for (int w = 0; w < W; ++w) {
-      next[w] = cur[w] & row[w];
-      nc += popc32(next[w]);
-    }
-    if (draw_samples(c, sc, depth + 1, nc, n_samples - 1, rng, out, n_out)) {
-      out[n_out++] = s;
-      return true;
-    }
-    cur[s >> 5] &= ~(1u << (s & 31));
-    if (--count == 0) return false;
-  }
+inline int popc64(uint64_t x) { return __builtin_popcountll(x); }
+
+// position of the r-th (0-based) set bit of x; x has more than r bits set
+inline int select_in_word(uint64_t x, uint32_t r) {
+#if defined(__x86_64__)
+  if (have_bmi2()) return bit_select_bmi2(x, r);
+#endif
+  for (uint32_t i = 0; i < r; ++i) x &= x - 1;
+  return __builtin_ctzll(x);
 }
 
-// getSamples (:141-168).  Returns false when the valid set holds no triangle of the sample graph (every one of the
-// reference's 1000 retries would then fail identically, so one exhaustive attempt decides).
+// index of the r-th set bit (ascending) of a W64-word mask
+inline uint32_t select_bit64(const uint64_t *m, int W64, uint32_t r) {
+  for (int w = 0; w < W64; ++w) {
+    const uint32_t c = uint32_t(popc64(m[w]));
+    if (r < c) return uint32_t(w) * 64u + uint32_t(select_in_word(m[w], r));
+    r -= c;
+  }
+  return 0xFFFFFFFFu;
+}
+
+// the same on the round's valid mask through its prefix popcounts (vpre[w] = set bits in words < w)
+inline uint32_t select_valid(const Cluster &c, int W64, uint32_t r) {
+  const uint64_t *m = reinterpret_cast<const uint64_t *>(c.valid.data());
+  int lo = 0, hi = W64;  // largest w with vpre[w] <= r
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (c.vpre[size_t(mid)] <= r) lo = mid; else hi = mid;
+  }
+  return uint32_t(lo) * 64u + uint32_t(select_in_word(m[lo], r - c.vpre[size_t(lo)]));
+}
+
+// Called when a round starts (the valid mask is fixed during a round).
+void prepare_sampler(Cluster &c) {
+  const int W64 = c.W / 2;
+  const uint64_t *m = reinterpret_cast<const uint64_t *>(c.valid.data());
+  c.vpre.resize(size_t(W64) + 1);
+  uint32_t acc = 0;
+  for (int w = 0; w < W64; ++w) {
+    c.vpre[size_t(w)] = acc;
+    acc += uint32_t(popc64(m[w]));
+  }
+  c.vpre[size_t(W64)] = acc;
+}
+
+// getSamples (sac_model_registration_graph.h:141-168) with drawIndexSampleHelper (:102-132) unrolled for 3 samples, on
+// 64-bit mask words: s = valid[rand() % size]; valid' = valid & sample_adj.neighbors(s); recurse; on failure remove s
+// and retry.  The samples come out deepest-first (s3, s2, s1) like samples_.push_back in the reference.  Returns false
+// when the valid set holds no triangle of the sample graph (every one of the reference's 1000 retries would then fail
+// identically, so one exhaustive attempt decides).  The level-0 mask is the round's valid mask itself until a retry
+// has to remove a vertex from it.
 bool get_samples(const Cluster &c, SamplerScratch &sc, uint64_t &rng, uint32_t triple[3]) {
   if (c.n_valid < 3) return false;
-  sc.fit(c.W);
-  std::copy(c.valid.begin(), c.valid.end(), sc.level[0].begin());
-  int n_out = 0;
-  return draw_samples(c, sc, 0, c.n_valid, 3, rng, triple, n_out);
+  const int W64 = c.W / 2;
+  sc.fit(W64);
+  const uint64_t *S = reinterpret_cast<const uint64_t *>(c.S);
+  const uint64_t *cur0 = reinterpret_cast<const uint64_t *>(c.valid.data());
+  uint64_t *own0 = sc.level[0].data(), *l1 = sc.level[1].data(), *l2 = sc.level[2].data();
+  bool copied = false;
+  int count0 = c.n_valid;
+  for (;;) {
+    const uint32_t r0 = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count0));
+    const uint32_t s0 = copied ? select_bit64(cur0, W64, r0) : select_valid(c, W64, r0);
+    const uint64_t *row0 = S + size_t(s0) * W64;
+    int count1 = 0;
+    for (int w = 0; w < W64; ++w) {
+      l1[w] = cur0[w] & row0[w];
+      count1 += popc64(l1[w]);
+    }
+    while (count1 > 0) {
+      const uint32_t r1 = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count1));
+      const uint32_t s1 = select_bit64(l1, W64, r1);
+      const uint64_t *row1 = S + size_t(s1) * W64;
+      int count2 = 0;
+      for (int w = 0; w < W64; ++w) {
+        l2[w] = l1[w] & row1[w];
+        count2 += popc64(l2[w]);
+      }
+      if (count2 > 0) {
+        const uint32_t r2 = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count2));
+        triple[0] = select_bit64(l2, W64, r2);
+        triple[1] = s1;
+        triple[2] = s0;
+        return true;
+      }
+      l1[s1 >> 6] &= ~(1ull << (s1 & 63));
+      --count1;
+    }
+    if (!copied) {
+      std::copy(cur0, cur0 + W64, own0);
+      cur0 = own0;
+      copied = true;
+    }
+    own0[s0 >> 6] &= ~(1ull << (s0 & 63));
+    if (--count0 == 0) return false;
+  }
 }
 
 // Small persistent pool: the per-cluster host work of a round (sampler, replay + gate, refinement + invalidation) is
@@ -352,13 +410,6 @@ __attribute__((target("bmi2"))) inline void compress_row_bmi2(const uint32_t *ro
     if (v >> 32) out[(b >> 5) + 1] |= uint32_t(v >> 32);
   }
 }
-inline bool have_bmi2() {
-  static const bool yes = [] {
-    __builtin_cpu_init();
-    return __builtin_cpu_supports("bmi2") != 0;
-  }();
-  return yes;
-}
 #endif
 
 // The clique gate of selectWithinDistance (:203-268) on an inlier list of size > 7.  Returns true if the list stands.
@@ -489,6 +540,7 @@ int32_t tod_sample_triples(int32_t n, const uint32_t *sample_bits, const uint32_
   c.S = sample_bits;
   c.valid.assign(valid_bits, valid_bits + c.W);
   c.n_valid = mask_count(c.valid.data(), c.W);
+  prepare_sampler(c);
   SamplerScratch sc;
   int32_t made = 0;
   for (; made < n_hyp; ++made)
@@ -844,6 +896,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         continue;
       }
       c->rng = tod_rng_seed(g->p.seed, uint32_t(c->object), c->round);
+      prepare_sampler(*c);
       c->iterations = 0;
       c->n_best = -INT_MAX;
       c->k = 1.0;
