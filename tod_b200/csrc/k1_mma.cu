@@ -33,7 +33,10 @@
 //                     list of the same query [non-strict]) — the latter through one u32 per query in global memory
 //                     (atomicMin on publish, one relaxed load per tile).  Exact: a candidate farther than some list's
 //                     k-th best can never be in the global top-k; equal distances are kept for the tie-break.
-// Grid: 1-D, query group fastest (see the kernel); cluster (2,1,1) in pair mode.
+// Grid: 1-D, two phases (k1_mma_plan): first the query groups that fill whole rounds of the machine, one CTA each
+// over the WHOLE shard (one cold start of the top-k lists per query, all CTAs sweeping the db in step so a row fetched
+// from HBM serves every SM out of L2); then the left-over groups, split into db chunks (query group fastest) so that
+// the last round is balanced too.  Cluster (2,1,1) in pair mode.
 #include <cuda.h>
 
 #include <algorithm>
@@ -75,6 +78,9 @@ constexpr uint32_t kSpinLimit = 1u << 26;  // bounded waits: a protocol bug trap
 // b_full [4] epilogue cycles waiting acc_full (sum over warps) [5] CTA lifetime cycles [6] epilogue groups (warp
 // level) [7] epilogue busy cycles (sum over warps, excludes acc_full waits) [8] CTAs [9] producer cycles waiting b_empty
 __device__ unsigned long long g_k1_stats[16];
+// per tile index inside a CTA's sweep (63 = all later tiles): [0] MMA issuer cycles waiting for acc_empty, [1] slow
+// calls (warp level), [2] cycles inside slow calls, [3] MMA issuer cycles waiting for b_full
+__device__ unsigned long long g_k1_tile[4][64];
 #define STAT_T0(var) const long long var = clock64()
 #define STAT_ADD(acc, var) acc += (unsigned long long)(clock64() - var)
 #else
@@ -335,8 +341,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsMma, 1)
 __global__ void __launch_bounds__(kThreadsMma, 1)
 #endif
 k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, int nq,
-              int shard_rows, uint32_t global_row_base, int rows_per_chunk, int n_chunks, uint32_t thr_init, int K,
-              uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, const uint32_t *__restrict__ popq
+              int shard_rows, uint32_t global_row_base, int rows_per_chunk, int n_chunks, int full_units,
+              int n_sources, uint32_t thr_init, int K, uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, const uint32_t *__restrict__ popq
 #if TOD_K1_STATS
               , int debug_mode   // ablation knobs of the instrumented build only (tools/k1_stats.py)
 #endif
@@ -365,16 +371,20 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   unsigned long long st_a = 0, st_b = 0, st_c = 0, st_d = 0, st_e = 0;
 #endif
   const uint32_t rank = cluster_ctarank();                  // 0 = leader
-  // 1-D grid, query group fastest: the CTAs of db chunk c + 1 start after (most of) chunk c has been scanned for the
-  // same queries, so all but the first chunk's CTAs begin with tight bounds in gthr.  A pair handles query groups
-  // 2p and 2p + 1.  (debug_mode & 32: chunk fastest, for the ablation in profiles/r1_k1_stats.md.)
+  // 1-D grid.  Units (CTA pairs) [0, full_units) take one query group each over the whole shard.  The remaining units
+  // are (chunk, query group) items, query group fastest: the CTAs of db chunk c + 1 start after (most of) chunk c has
+  // been scanned for the same queries, so all but the first chunk's CTAs begin with tight bounds in gthr.  A pair
+  // handles query groups 2p and 2p + 1.  (debug_mode & 32: chunk fastest, for the ablation in profiles/r1_k1_stats.md.)
   const int unit = int(blockIdx.x) / kCtas;
-  const int n_units_q = int(gridDim.x) / kCtas / n_chunks;
-  const int chunk = (debug_mode & 32) ? unit % n_chunks : unit / n_units_q;
-  const int q_group = ((debug_mode & 32) ? unit / n_chunks : unit % n_units_q) * kCtas + int(blockIdx.x) % kCtas;
+  const bool full_sweep = unit < full_units;
+  const int unit2 = unit - full_units;
+  const int n_units_q = full_sweep ? 1 : (int(gridDim.x) / kCtas - full_units) / n_chunks;
+  const int chunk = full_sweep ? 0 : ((debug_mode & 32) ? unit2 % n_chunks : unit2 / n_units_q);
+  const int q_unit = full_sweep ? unit : full_units + ((debug_mode & 32) ? unit2 / n_chunks : unit2 % n_units_q);
+  const int q_group = q_unit * kCtas + int(blockIdx.x) % kCtas;
   const int q_row0 = q_group * (kQT * kBlockM);
-  const int row0 = chunk * rows_per_chunk;
-  const int row1 = min(shard_rows, row0 + rows_per_chunk);
+  const int row0 = full_sweep ? 0 : chunk * rows_per_chunk;
+  const int row1 = full_sweep ? shard_rows : min(shard_rows, row0 + rows_per_chunk);
   const int n_tiles = (row1 - row0 + kBlockN - 1) / kBlockN;
 
   if (threadIdx.x == 0) {
@@ -448,6 +458,9 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           STAT_T0(t0);
           if (!((debug_mode & 2) && t >= kBStages)) mbar_wait_bounded(&b_full[s], (t / kBStages) & 1);
           STAT_ADD(st_b, t0);
+#if TOD_K1_STATS
+          atomicAdd(&g_k1_tile[3][min(t, 63)], (unsigned long long)(clock64() - t0));
+#endif
         }
         tc_fence_after();
         for (int j = 0; j < kQT; ++j, ++acc_iter) {
@@ -456,6 +469,9 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             STAT_T0(t0);
             mbar_wait_bounded(&acc_empty[as], ((acc_iter / kAccStages) & 1) ^ 1);
             STAT_ADD(st_a, t0);
+#if TOD_K1_STATS
+            atomicAdd(&g_k1_tile[0][min(t, 63)], (unsigned long long)(clock64() - t0));
+#endif
           }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * kBlockN;
@@ -537,14 +553,33 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
       uint32_t flags = 0;
       if (!(debug_mode & 4)) {
-        flags |= (max32p(va, 0) > thr_dot) ? 1u : 0u;
-        flags |= (max32p(va, 16) > thr_dot) ? 2u : 0u;
-        flags |= (max32p(vb, 0) > thr_dot) ? 4u : 0u;
-        flags |= (max32p(vb, 16) > thr_dot) ? 8u : 0u;
-        flags |= (max32p(vc, 0) > thr_dot) ? 16u : 0u;
-        flags |= (max32p(vc, 16) > thr_dot) ? 32u : 0u;
-        flags |= (max32p(vd, 0) > thr_dot) ? 64u : 0u;
-        flags |= (max32p(vd, 16) > thr_dot) ? 128u : 0u;
+        const int m0 = max32p(va, 0), m1 = max32p(va, 16), m2 = max32p(vb, 0), m3 = max32p(vb, 16);
+        const int m4 = max32p(vc, 0), m5 = max32p(vc, 16), m6 = max32p(vd, 0), m7 = max32p(vd, 16);
+        if (t == 0 && cols_valid == kBlockN) {
+          // Cold list: without a bound every one of the 256 columns is a candidate and the slow path walks them all
+          // (24 000 cycles per CTA measured, tools/k1_stats.py).  The K-th largest of the eight sub-group maxima is
+          // reached by K distinct rows of this tile, so no row below it can be among the K nearest: start from there.
+          int a0 = m0, a1 = m1, a2 = m2, a3 = m3, a4 = m4, a5 = m5, a6 = m6, a7 = m7;
+#define TOD_CSWAP(x, y) { const int lo_ = min(x, y); x = max(x, y); y = lo_; }   // descending
+          TOD_CSWAP(a0, a1) TOD_CSWAP(a2, a3) TOD_CSWAP(a4, a5) TOD_CSWAP(a6, a7)
+          TOD_CSWAP(a0, a2) TOD_CSWAP(a1, a3) TOD_CSWAP(a4, a6) TOD_CSWAP(a5, a7)
+          TOD_CSWAP(a1, a2) TOD_CSWAP(a5, a6) TOD_CSWAP(a0, a4) TOD_CSWAP(a3, a7)
+          TOD_CSWAP(a1, a5) TOD_CSWAP(a2, a6)
+          TOD_CSWAP(a1, a4) TOD_CSWAP(a3, a6)
+          TOD_CSWAP(a2, a4) TOD_CSWAP(a3, a5)
+          TOD_CSWAP(a3, a4)
+#undef TOD_CSWAP
+          const int kth = K == 1 ? a0 : K == 2 ? a1 : K == 3 ? a2 : K == 4 ? a3 : K == 5 ? a4 : K == 6 ? a5 : K == 7 ? a6 : a7;
+          thr_dot = max(thr_dot, kth - 1);               // keep dot >= kth
+        }
+        flags |= (m0 > thr_dot) ? 1u : 0u;
+        flags |= (m1 > thr_dot) ? 2u : 0u;
+        flags |= (m2 > thr_dot) ? 4u : 0u;
+        flags |= (m3 > thr_dot) ? 8u : 0u;
+        flags |= (m4 > thr_dot) ? 16u : 0u;
+        flags |= (m5 > thr_dot) ? 32u : 0u;
+        flags |= (m6 > thr_dot) ? 64u : 0u;
+        flags |= (m7 > thr_dot) ? 128u : 0u;
         if (cols_valid < kBlockN) flags &= (1u << ((cols_valid + 31) >> 5)) - 1u;
       } else {
         thr_dot = max(thr_dot, int(va[0] ^ vb[7] ^ vc[3] ^ vd[9]) == 0x7fffffff ? 1 : 0);
@@ -564,6 +599,10 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         STAT_ADD(st_b, t0);
 #if TOD_K1_STATS
         st_a += (unsigned long long)__popc(flags);
+        if (lane == 0) {
+          atomicAdd(&g_k1_tile[1][min(t, 63)], (unsigned long long)__popc(flags));
+          atomicAdd(&g_k1_tile[2][min(t, 63)], (unsigned long long)(clock64() - t0));
+        }
 #endif
       }
       STAT_ADD(st_d, t_busy);
@@ -581,6 +620,9 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     if (qi < nq) {
       uint32_t *o = partial + (size_t(chunk) * nq + qi) * K;  // one candidate list per (chunk, query): a merge source
       for (int i = 0; i < K; ++i) o[i] = lds_u32(my_list + uint32_t(i) * 4u * kBlockM);
+      if (full_sweep)  // the only list of this query: the other merge sources are empty
+        for (int c = 1; c < n_sources; ++c)
+          for (int i = 0; i < K; ++i) partial[(size_t(c) * nq + qi) * K + i] = kKeyEmpty;
     }
   }
 
@@ -663,24 +705,37 @@ K1Plan k1_mma_plan(int nq, int64_t shard_rows, int sm_count) {
   constexpr double kStartupTiles = 28.0;
   const int64_t tiles_total = max_chunks;
   const int64_t c_hi = std::min<int64_t>(max_chunks, 64);
-  int64_t best_c = 1;
+  // Whole rounds of the machine run unsplit (one start-up per round); only the left-over query groups are chunked.
+  // full = 0 is the plain chunked plan; both are modelled and the cheaper one wins.
+  const int64_t slots = std::max(kCtas, sm_count / kCtas * kCtas);
+  int64_t best_c = 1, best_full = 0;
   double best_t = 1e300;
-  for (int64_t c = 1; c <= std::max<int64_t>(1, c_hi); ++c) {
-    const int64_t ctas = c * p.n_qtiles;
-    const int64_t waves = (ctas + sm_count - 1) / sm_count;
-    const double t = double(waves) * (kStartupTiles + double((tiles_total + c - 1) / c));
-    if (t < best_t * (1.0 - 1e-9)) {
-      best_t = t;
-      best_c = c;
+#ifndef TOD_K1_TWO_PHASE
+#define TOD_K1_TWO_PHASE 1            // 0: variant build with the round-1 plan (every query group chunked), for A/B runs
+#endif
+  for (int64_t full : {int64_t(0), TOD_K1_TWO_PHASE ? int64_t(p.n_qtiles) / slots * slots : int64_t(0)}) {
+    const int64_t rest = p.n_qtiles - full;
+    const double t_full = double(full / slots) * (kStartupTiles + double(tiles_total));
+    if (rest == 0) {
+      if (t_full < best_t * (1.0 - 1e-9)) best_t = t_full, best_c = 1, best_full = full;
+      continue;
+    }
+    for (int64_t c = 1; c <= std::max<int64_t>(1, c_hi); ++c) {
+      const int64_t waves = (c * rest + sm_count - 1) / sm_count;
+      const double t = t_full + double(waves) * (kStartupTiles + double((tiles_total + c - 1) / c));
+      if (t < best_t * (1.0 - 1e-9)) best_t = t, best_c = c, best_full = full;
     }
   }
 #if TOD_K1_STATS
   if (const char *e = getenv("TOD_K1_CHUNKS")) best_c = std::min<int64_t>(max_chunks, std::max(1, atoi(e)));  // experiments
+  if (const char *e = getenv("TOD_K1_FULL")) best_full = std::min<int64_t>(p.n_qtiles, std::max(0, atoi(e)) / kCtas * kCtas);
 #endif
+  p.full_qtiles = int(best_full);
   int64_t rpc = (shard_rows + best_c - 1) / best_c;
   rpc = std::max<int64_t>(kBlockN, (rpc + kBlockN - 1) / kBlockN * kBlockN);
   p.rows_per_chunk = int(rpc);
   p.n_chunks = int(std::max<int64_t>(1, (shard_rows + rpc - 1) / rpc));
+  if (p.full_qtiles == p.n_qtiles) p.n_chunks = 1;
   p.n_sources = p.n_chunks;
   return p;
 }
@@ -729,6 +784,14 @@ extern "C" void tod_debug_k1_stats(unsigned long long *out16, int reset) {
     cudaMemcpyToSymbol(tod::g_k1_stats, z, sizeof(z));
   }
 }
+extern "C" void tod_debug_k1_tile_stats(unsigned long long *out256, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out256, tod::g_k1_tile, sizeof(unsigned long long) * 256);
+  if (reset) {
+    static unsigned long long z[256] = {0};
+    cudaMemcpyToSymbol(tod::g_k1_tile, z, sizeof(z));
+  }
+}
 namespace tod {
 #endif
 
@@ -751,10 +814,12 @@ cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map
     return e ? atoi(e) : 0;
   }();
 #endif
-  dim3 grid(unsigned(plan.n_qtiles) * unsigned(plan.n_chunks));  // n_qtiles is even in pair mode (cluster (2,1,1))
+  // n_qtiles and full_qtiles are even in pair mode (cluster (2,1,1))
+  dim3 grid(unsigned(plan.full_qtiles) + unsigned(plan.n_qtiles - plan.full_qtiles) * unsigned(plan.n_chunks));
   k1_mma_kernel<<<grid, kThreadsMma, kSmemMma, stream>>>(*static_cast<const CUtensorMap *>(map_q),
                                                          *static_cast<const CUtensorMap *>(map_db), nq, int(shard_rows),
-                                                         global_row_base, plan.rows_per_chunk, plan.n_chunks, thr_init, k, d_partial,
+                                                         global_row_base, plan.rows_per_chunk, plan.n_chunks,
+                                                         plan.full_qtiles / kCtas, plan.n_sources, thr_init, k, d_partial,
                                                          d_gthr, d_popq
 #if TOD_K1_STATS
                                                          , debug_mode

@@ -97,6 +97,8 @@ struct K1Plan {
   int rows_per_chunk;  // multiple of the smem tile
   int n_chunks;
   int n_sources;       // candidate lists per query written to `partial` (merge fan-in)
+  int full_qtiles;     // k1_mma: the first full_qtiles query groups sweep the whole shard in one CTA (one cold start);
+                       // only the remaining n_qtiles - full_qtiles groups are split into n_chunks db chunks
 };
 K1Plan k1_popc_plan(int nq, int64_t shard_rows, int sm_count);
 

@@ -34,13 +34,16 @@ def main():
         q_dev = torch.from_numpy(q).to(dev)
         keys = torch.empty((q.shape[0], k), dtype=torch.int32, device=dev)
         out = (ctypes.c_ulonglong * 16)()
+        tile = (ctypes.c_ulonglong * 256)()
         for it in range(3):
             m.knn_keys_device(q_dev.data_ptr(), q.shape[0], keys.data_ptr(), None)
             torch.cuda.synchronize()
             if it == 1:
                 lib.tod_debug_k1_stats(out, 1)      # drop the warm-up counts
+                lib.tod_debug_k1_tile_stats(tile, 1)
         ms = m.last_k1_ms
         lib.tod_debug_k1_stats(out, 1)
+        lib.tod_debug_k1_tile_stats(tile, 1)
         s = dict(zip(names, [int(x) for x in out]))
         ctas = max(s["ctas"], 1)
         per_cta = s["cta_cycles"] / ctas
@@ -60,6 +63,12 @@ def main():
              "slow_events_per_call": s["slow_events"] / max(s["slow_calls"], 1),
              "epi_hold_cycles_per_tile": s["epi_hold_cycles"] * 8.0 / max(s["epi_groups"], 1),
              "epi_busy_cycles_per_group": s["epi_busy_cycles"] / max(s["epi_groups"], 1), "raw": s}
+        # per tile index of a CTA's sweep (last bucket = tiles >= 63), per CTA: where the start-up goes
+        tl = [int(x) for x in tile]
+        d["by_tile"] = {"mma_wait_acc_empty_cycles_per_cta": [round(x / ctas * 2, 0) for x in tl[0:64]],
+                        "slow_calls_per_cta": [round(x / ctas, 2) for x in tl[64:128]],
+                        "slow_cycles_per_call": [round(tl[128 + i] / max(tl[64 + i], 1), 0) for i in range(64)],
+                        "mma_wait_b_full_cycles_per_cta": [round(x / ctas * 2, 0) for x in tl[192:256]]}
         print(json.dumps(d))
         sys.stdout.flush()
 
