@@ -337,6 +337,13 @@ float tod_last_stage_ms(void);
  *                    sac_model_registration_graph.h:304-347): R (9, row-major) and T (3) map query -> training. */
 int32_t tod_clique_find(int32_t n_vertices, const int32_t *edges, int32_t n_edges, uint32_t minimal_size,
                         int32_t *out_vertices, int32_t *finds_more);
+/*   tod_clique_gate_small  the fixed-capacity form of the same search that K5 runs on the GPU for induced sample
+ *                    sub-graphs of at most 128 vertices (tod_b200/csrc/clique_small.h, one source for host and
+ *                    device): the gate's question at minimal size 7 (sac_model_registration_graph.h:258-265).
+ *                    Returns 1 (more than 7 vertices would be returned), 0 (not), -1 (step_cap reached: the caller
+ *                    falls back to tod_clique_find), -2 on bad input; *steps (may be NULL) = search steps taken. */
+int32_t tod_clique_gate_small(int32_t n_vertices, const int32_t *edges, int32_t n_edges, int32_t step_cap,
+                              int32_t *steps);
 int tod_rigid_fit(const float *query_pts, const float *train_pts, const uint32_t *indices, int32_t m, float *R, float *T);
 /*   tod_sample_triples  getSamples (sac_model_registration_graph.h:141-168): n_hyp sample triples from the sample
  *                    graph (n x tod_adjacency_row_words(n) bit-matrix) restricted to the valid mask, consuming the
@@ -410,6 +417,10 @@ void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_
  * settled with a K4 "fails" verdict, [22] hypotheses K4 left undecided that the replay sent to the host search,
  * [23] device time of the K4 launches in microseconds. */
 void tod_guess_last_gate_stats(const tod_guess *g, int64_t *out24);
+/* K5 (the reference's bounded clique search stepped exactly on the GPU for induced sub-graphs of <= 128 vertices) in
+ * the last process call: [0] hypotheses the replay settled with a K5 "passes" verdict, [1] with a K5 "fails" verdict,
+ * [2] hypotheses left to the host search (larger graphs, full queue, step cap), [3] reserved. */
+void tod_guess_last_k5_stats(const tod_guess *g, int64_t *out4);
 /* Algorithmic bytes (SURVEY.md §8d units) moved by the K2 launch (32 n in + two n x W bit-matrices out, summed over
  * the clusters) and by all K3 launches ((3 rows + 2 masks) x W x 4 + 140 per hypothesis) of the last process call,
  * with the number of (frame, object) clusters and correspondences: bench.py divides them by k2_ms / k3_ms. */

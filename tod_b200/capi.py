@@ -118,6 +118,7 @@ SIGNATURES = [
     ("tod_score_hypotheses", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P, _I32, _P, _D, _P, _P, _P]),
     ("tod_last_stage_ms", _F, []),
     ("tod_clique_find", _I32, [_I32, _P, _I32, _U32, _P, ctypes.POINTER(_I32)]),
+    ("tod_clique_gate_small", _I32, [_I32, _P, _I32, _I32, ctypes.POINTER(_I32)]),
     ("tod_rigid_fit", ctypes.c_int, [_P, _P, _P, _I32, _P, _P]),
     ("tod_sample_triples", _I32, [_I32, _P, _P, ctypes.POINTER(_U64), _I32, _P]),
     ("tod_select_inliers", _I32, [_I32, _P, _P, _P, _P, _P]),
@@ -131,6 +132,7 @@ SIGNATURES = [
     ("tod_rng_seed", _U64, [_U64, _U32, _U32]),
     ("tod_rng_next", _I32, [ctypes.POINTER(_U64)]),
     ("tod_guess_last_gate_stats", None, [_P, ctypes.POINTER(_I64)]),
+    ("tod_guess_last_k5_stats", None, [_P, ctypes.POINTER(_I64)]),
     ("tod_guess_last_traffic", None, [_P, ctypes.POINTER(_D), ctypes.POINTER(_D), ctypes.POINTER(_I64),
                                       ctypes.POINTER(_I64)]),
     ("tod_guess_last_profile", None, [_P, ctypes.POINTER(_D)]),

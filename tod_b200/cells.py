@@ -339,10 +339,13 @@ class GuessGenerator:
         gh = (ctypes.c_int64 * 24)()
         self._lib.tod_guess_last_gate_stats(self._h, gh)
         gh = [int(x) for x in gh]
+        k5 = (ctypes.c_int64 * 4)()
+        self._lib.tod_guess_last_k5_stats(self._h, k5)
         return {"gate_shape": {"by_graph_size": gh[0:8], "by_core_size": gh[8:16], "core_too_small": gh[16],
                                "colour_bound": gh[17], "searches": gh[18], "search_passes": gh[19],
                                "search_steps": gh[20], "k4_fails_used": gh[21], "k4_undecided_used": gh[22],
-                               "k4_kernel_ms": gh[23] / 1000.0},
+                               "k4_kernel_ms": gh[23] / 1000.0, "k5_passes_used": int(k5[0]),
+                               "k5_fails_used": int(k5[1])},
                 "k2_ms": k2.value, "k3_ms": k3.value, "k2_bytes": b2.value, "k3_bytes": b3.value,
                 "n_clusters": ncl.value, "n_correspondences": ncor.value, "n_hypotheses": nh.value, "n_rounds": nr.value,
                 "host_ms": {"cluster_k2": prof[0], "sampler": prof[1], "k3_launch_sync": prof[2],

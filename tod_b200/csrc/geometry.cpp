@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "clique.h"
+#include "clique_small.h"
 #include "host_geometry.h"
 #include "tod_internal.h"
 
@@ -83,6 +84,41 @@ int32_t tod_clique_find(int32_t n_vertices, const int32_t *edges, int32_t n_edge
     *finds_more = again.finds_more_than(minimal_size) ? 1 : 0;
   }
   return int32_t(best.size());
+}
+
+int32_t tod_clique_gate_small(int32_t n_vertices, const int32_t *edges, int32_t n_edges, int32_t step_cap,
+                              int32_t *steps) {
+  if (n_vertices < 0 || n_vertices > tod::kSmallGraphMax || n_edges < 0 || (n_edges > 0 && !edges) || step_cap < 1) {
+    tod::set_error("bad graph (at most %d vertices)", tod::kSmallGraphMax);
+    return -2;
+  }
+  std::vector<tod::Bits128> adj(size_t(std::max(n_vertices, 1)), tod::Bits128{0ull, 0ull});
+  for (int32_t e = 0; e < n_edges; ++e) {
+    const int32_t a = edges[2 * e], b = edges[2 * e + 1];
+    if (a < 0 || a >= n_vertices || b < 0 || b >= n_vertices) {
+      tod::set_error("edge endpoint out of range");
+      return -2;
+    }
+    if (a == b) continue;
+    tod::small_clique::set_bit(adj[size_t(a)], b);
+    tod::small_clique::set_bit(adj[size_t(b)], a);
+  }
+  int st = 0;
+  int r;
+  if (n_vertices <= 64) {  // the one-word rows K5 uses for graphs of at most 64 vertices
+    std::vector<tod::Bits64> adj64(adj.size());
+    for (size_t i = 0; i < adj.size(); ++i) adj64[i].lo = adj[i].lo;
+    r = tod::small_gate_search(adj64.data(), n_vertices, step_cap, &st);
+    int st2 = 0;
+    if (tod::small_gate_search(adj.data(), n_vertices, step_cap, &st2) != r || st2 != st) {
+      tod::set_error("the 64-bit and 128-bit forms of the search disagree");
+      return -2;
+    }
+  } else {
+    r = tod::small_gate_search(adj.data(), n_vertices, step_cap, &st);
+  }
+  if (steps) *steps = st;
+  return r;
 }
 
 int tod_rigid_fit(const float *query_pts, const float *train_pts, const uint32_t *indices, int32_t m, float *R, float *T) {

@@ -511,6 +511,8 @@ struct tod_guess {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_k2 = nullptr, ev_S = nullptr, ev_P = nullptr;
   DeviceBuffer d_off, d_mo, d_q, d_t, d_px, d_sp, d_P, d_S, d_desc, d_valid, d_finite, d_hyps, d_counts, d_R, d_T;
   DeviceBuffer d_deg, d_active, d_floor, d_verdict;  // K4: degree masks, active-cluster list, per-cluster best, verdicts
+  DeviceBuffer d_jobs;                               // K5: queue of packed induced sub-graphs (<= 128 vertices each)
+  int64_t k5_stats[4] = {0, 0, 0, 0};
   tod::PinnedBuffer h_P, h_S;  // host copies of the bit-matrices (read by the sampler and the gate)
   float k2_ms = 0, k3_ms = 0;
   double k2_bytes = 0, k3_bytes = 0;  // algorithmic bytes of the last call's K2 / K3 launches (SURVEY.md §8d units)
@@ -624,7 +626,7 @@ void tod_guess_destroy(tod_guess *g) {
   cudaSetDevice(g->p.device);
   for (DeviceBuffer *b : {&g->d_off, &g->d_mo, &g->d_q, &g->d_t, &g->d_px, &g->d_sp, &g->d_P, &g->d_S, &g->d_desc,
                           &g->d_valid, &g->d_finite, &g->d_hyps, &g->d_counts, &g->d_R, &g->d_T, &g->d_deg,
-                          &g->d_active, &g->d_floor, &g->d_verdict})
+                          &g->d_active, &g->d_floor, &g->d_verdict, &g->d_jobs})
     b->release();
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -649,6 +651,11 @@ void tod_guess_last_profile(const tod_guess *g, double *ms12) {
 void tod_guess_last_gate_stats(const tod_guess *g, int64_t *out24) {
   if (!out24) return;
   for (int i = 0; i < 24; ++i) out24[i] = g ? g->gate_hist[i] : 0;
+}
+
+void tod_guess_last_k5_stats(const tod_guess *g, int64_t *out4) {
+  if (!out4) return;
+  for (int i = 0; i < 4; ++i) out4[i] = g ? g->k5_stats[i] : 0;
 }
 
 void tod_guess_last_traffic(const tod_guess *g, double *k2_bytes, double *k3_bytes, int64_t *n_clusters,
@@ -825,7 +832,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   std::vector<uint8_t> batch_verdict;
   int max_W = 0;
   for (const Cluster *c : clusters) max_W = std::max(max_W, c->W);
-  long k4_fails_used = 0, k4_host_used = 0;
+  long k4_fails_used = 0, k4_host_used = 0, k5_pass_used = 0, k5_fail_used = 0;
   float k4_ms = 0.f;
   TOD_CUDA(cudaMemcpyAsync(g->d_off.ptr, offsets.data(), offsets.size() * 4, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(g->d_mo.ptr, mo.data(), mo.size() * 8, cudaMemcpyHostToDevice, st));
@@ -876,7 +883,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     SamplerScratch sampler;
     std::vector<uint32_t> inliers;
     std::string error;
-    long k4_fails = 0, k4_host = 0;
+    long k4_fails = 0, k4_host = 0, k5_pass = 0, k5_fail = 0;
   };
   std::vector<ThreadScratch> ts(static_cast<size_t>(n_thr));
   std::vector<std::vector<Found>> found_by_cluster(clusters.size());
@@ -983,6 +990,9 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
           }
           batch_verdict.resize(size_t(H));
           TOD_CUDA(g->d_verdict.reserve(size_t(H)));
+          // K5 queue: room for every hypothesis of the launch at the largest graph K5 takes (2 KB), capped at 1 GiB
+          const size_t pool_bytes = std::min<size_t>(size_t(H) * 2048, size_t(1) << 30);
+          TOD_CUDA(g->d_jobs.reserve(tod::gate_job_bytes(H, pool_bytes)));
           TOD_CUDA(cudaMemcpyAsync(g->d_floor.ptr, floor_by_cluster.data(), floor_by_cluster.size() * 4,
                                    cudaMemcpyHostToDevice, st));
           TOD_CUDA(cudaEventRecord(g->ev2, st));
@@ -990,7 +1000,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
                                               g->d_valid.as<uint32_t>(), g->d_finite.as<uint32_t>(),
                                               g->d_deg.as<uint32_t>(), H, g->d_hyps.as<uint32_t>(),
                                               g->d_counts.as<int32_t>(), g->d_floor.as<int32_t>(), max_W,
-                                              g->d_verdict.as<uint8_t>(), st));
+                                              g->d_verdict.as<uint8_t>(), g->d_jobs.ptr, pool_bytes, st));
           TOD_CUDA(cudaEventRecord(g->ev3, st));
           TOD_CUDA(cudaMemcpyAsync(batch_verdict.data(), g->d_verdict.ptr, size_t(H), cudaMemcpyDeviceToHost, st));
         }
@@ -1037,10 +1047,19 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         if (inf_thr && pre > 7) {
           const uint8_t v = batch_verdict[size_t(c->batch_begin + h)];
           proofs_done = c->W <= 128;  // K4 evaluates clusters of up to 4096 correspondences
-          if (v == tod::kGateFails) {  // K4 proved that the gate clears this list
+          if (v == tod::kGateFails || v == tod::kGateFailsSearch) {  // K4 proved / K5 found that the gate clears this list
             sc.inliers.clear();
-            ++sc.k4_fails;
+            ++(v == tod::kGateFails ? sc.k4_fails : sc.k5_fail);
             return 0;
+          }
+          if (v == tod::kGatePasses) {  // K5 ran the reference's search to its end: the candidate list stands
+            ++sc.k5_pass;
+            hypothesis_inliers(*c, c->hyps.data() + size_t(h) * 3, inf_thr, thr2, nullptr, nullptr, sc.inliers);
+            if (int(sc.inliers.size()) != pre) {
+              sc.error = "K3 count disagrees with the host candidate list";
+              return -1;
+            }
+            return pre;
           }
           if (v == tod::kGateNeedsHost) ++sc.k4_host;
           else {
@@ -1294,7 +1313,12 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     for (int i = 0; i < 24; ++i) g->gate_hist[i] += sc.gate.hist[i];
     k4_fails_used += sc.k4_fails;
     k4_host_used += sc.k4_host;
+    k5_pass_used += sc.k5_pass;
+    k5_fail_used += sc.k5_fail;
   }
+  g->k5_stats[0] = k5_pass_used;
+  g->k5_stats[1] = k5_fail_used;
+  g->k5_stats[2] = k4_host_used;
   g->gate_hist[21] = k4_fails_used;
   g->gate_hist[22] = k4_host_used;
   g->gate_hist[23] = int64_t(k4_ms * 1000.f);

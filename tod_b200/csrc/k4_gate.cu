@@ -8,13 +8,17 @@
 //   * its 7-core (iterated removal of vertices with fewer than 7 live neighbours) has fewer than 8 vertices;
 //   * a greedy colouring of the core needs fewer than 8 colours;
 //   * (cores of at most 128 vertices) an exhaustive depth-first search over 128-bit candidate sets finds no 8-clique.
-// Only hypotheses whose sub-graph DOES hold an 8-clique — where the reference's exact stepping decides between "found
-// 8" and "stopped at an exact 7"  — go back to the host search.  The gate can only keep or zero a
-// count, so a certain "fails" is all the host replay needs.
+// Hypotheses whose sub-graph DOES hold an 8-clique — where the reference's exact stepping decides between "found 8" and
+// "stopped at an exact 7"  — are settled by K5 (k5_search_kernel below) when the filtered graph
+// has at most 128 vertices: the reference's bounded search itself, stepped exactly (clique_small.h, one source for the
+// host and the device), one thread per hypothesis on the packed induced sub-graph K4 leaves in a job queue.  Larger
+// graphs, and searches that exceed K5's step cap, go back to the host search.  The gate can only keep or zero a
+// count, so "fails" / "passes" is all the host replay needs.
 //
 // One warp per hypothesis.  Bit-rows of the sample graph are read straight from K2's output; masks live in shared
 // memory (W words per warp).  Reference-faithful (+inf threshold) mode only: the candidate set is
 // P[s0] & P[s1] & P[s2] & valid & finite, plus the three samples.
+#include "clique_small.h"
 #include "tod_internal.h"
 
 namespace tod {
@@ -24,6 +28,8 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kSmallCore = 128;   // exhaustive search limit (two 64-bit words per set)
 constexpr int kMaxSweeps = 64;
 constexpr int kDfsBudget = 6000;  // node expansions per lane before giving the hypothesis back to the host
+constexpr int kK5Threads = 64;
+constexpr int kK5StepCap = 512;   // searches of the gate take tens of steps; longer ones are left to the host
 
 __global__ void __launch_bounds__(256)
 sample_degree_mask_kernel(const K3Cluster *__restrict__ clusters, const int32_t *__restrict__ active,
@@ -53,9 +59,7 @@ sample_degree_mask_kernel(const K3Cluster *__restrict__ clusters, const int32_t 
   }
 }
 
-struct U128 {
-  unsigned long long lo, hi;
-};
+using U128 = Bits128;
 __device__ __forceinline__ int popc128(U128 a) { return __popcll(a.lo) + __popcll(a.hi); }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -63,18 +67,21 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
                const uint32_t *__restrict__ sample, const uint32_t *__restrict__ valid,
                const uint32_t *__restrict__ finite, const uint32_t *__restrict__ deg_mask, int n_hyp,
                const uint4 *__restrict__ hyps, const int32_t *__restrict__ counts, const int32_t *__restrict__ floor_,
-               int max_words, uint8_t *__restrict__ verdict) {
+               int max_words, uint8_t *__restrict__ verdict, int4 *__restrict__ job_hdr,
+               unsigned long long *__restrict__ job_pool, unsigned long long *__restrict__ job_ctl,
+               unsigned long long pool_words) {
   extern __shared__ uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int h = blockIdx.x * kWarpsPerCta + warp;
   if (h >= n_hyp) return;
-  // per warp: alive[max_words] | work[max_words] | ids[128] (u16) | adj[128] (U128)
-  const int per_warp = 2 * max_words + kSmallCore / 2 + kSmallCore * 4;
-  uint32_t *alive = smem + size_t(warp) * per_warp;
+  // per warp: adj[128] (U128) | alive[max_words] | work[max_words] | filt[max_words] | ids[128] (u16)
+  const int per_warp = kSmallCore * 4 + 3 * max_words + kSmallCore / 2;
+  U128 *adj = reinterpret_cast<U128 *>(smem + size_t(warp) * per_warp);
+  uint32_t *alive = smem + size_t(warp) * per_warp + kSmallCore * 4;
   uint32_t *work = alive + max_words;
-  uint16_t *ids = reinterpret_cast<uint16_t *>(work + max_words);
-  U128 *adj = reinterpret_cast<U128 *>(work + max_words + kSmallCore / 2);
+  uint32_t *filt = work + max_words;   // the filtered set before the core peeling: the graph the reference searches
+  uint16_t *ids = reinterpret_cast<uint16_t *>(filt + max_words);
 
   const int cnt = __ldg(counts + h);
   const uint4 hy = __ldg(hyps + h);
@@ -101,6 +108,7 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
     if (int(hy.z >> 5) == w) m |= 1u << (hy.z & 31);
     m &= __ldg(D + w);
     alive[w] = m;
+    filt[w] = m;
     nf += __popc(m);
   }
   nf = __reduce_add_sync(0xffffffffu, nf);
@@ -205,14 +213,18 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
     __syncwarp();
   }
   if (!undecided) return finish(kGateFails);
-  if (n_alive > kSmallCore) return finish(kGateNeedsHost);
+  // K5 job: the filtered graph (NOT its core — the reference's search order depends on every vertex) when it is small
+  const bool to_search = job_hdr != nullptr && nf <= kSmallCore;
+  if (!to_search && n_alive > kSmallCore) return finish(kGateNeedsHost);
+  const uint32_t *members = to_search ? filt : alive;
+  const int nn = to_search ? nf : n_alive;
 
-  // ---- small core: exhaustive search for an 8-clique over 128-bit sets ------------------------------------------------
+  // ---- pack the induced sub-graph: vertex a = a-th smallest member (the renumbering of :241-255) ---------------------
   __syncwarp();
   if (lane == 0) {
     int k = 0;
     for (int w = 0; w < W; ++w) {
-      uint32_t m = alive[w];
+      uint32_t m = members[w];
       while (m) {
         ids[k++] = uint16_t(w * 32 + __ffs(m) - 1);
         m &= m - 1;
@@ -220,10 +232,10 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
     }
   }
   __syncwarp();
-  for (int i = lane; i < n_alive; i += 32) {
+  for (int i = lane; i < nn; i += 32) {
     const uint32_t *row = S + size_t(ids[i]) * W;
     U128 a{0ull, 0ull};
-    for (int j = 0; j < n_alive; ++j) {
+    for (int j = 0; j < nn; ++j) {
       const uint32_t u = ids[j];
       const unsigned long long bit = (__ldg(row + (u >> 5)) >> (u & 31)) & 1u;
       if (j < 64) a.lo |= bit << j;
@@ -232,6 +244,38 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
     adj[i] = a;
   }
   __syncwarp();
+  if (to_search) {
+    // queue: headers of graphs of <= 64 vertices (one-word rows) grow from the front, the others from the back, so
+    // that the warps of K5 run one row width each; rows are bump-allocated in the pool
+    const bool narrow = nn <= 64;
+    const unsigned long long words = narrow ? (unsigned long long)nn : 2ull * (unsigned long long)nn;
+    unsigned long long slot = 0, off = 0;
+    if (lane == 0) {
+      slot = atomicAdd(job_ctl + (narrow ? 0 : 1), 1ull);
+      off = atomicAdd(job_ctl + 2, words);
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    const bool fits = off + words <= pool_words;
+    if (fits) {
+      unsigned long long *dst = job_pool + off;
+      if (narrow) {
+        for (int i = lane; i < nn; i += 32) dst[i] = adj[i].lo;
+      } else {
+        for (int i = lane; i < nn; i += 32) {
+          dst[2 * i] = adj[i].lo;
+          dst[2 * i + 1] = adj[i].hi;
+        }
+      }
+    }
+    // (at most one job per hypothesis, so the n_hyp header slots cannot overflow)
+    if (lane == 0)
+      job_hdr[narrow ? slot : (unsigned long long)(n_hyp - 1) - slot] =
+          make_int4(h, fits ? nn : 0, int(off & 0xffffffffull), int(off >> 32));
+    return finish(kGateNeedsHost);  // K5 overwrites the verdict unless the pool was full or its step cap is reached
+  }
+
+  // ---- small core of a larger graph: exhaustive search for an 8-clique over 128-bit sets -----------------------------
   bool found = false, overflow = false;
   for (int root = lane; root < n_alive && !found && !overflow; root += 32) {
     // cliques are enumerated with increasing core indices: candidates of level 1 = neighbours of root above root
@@ -282,7 +326,29 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
   finish((any_found || any_overflow) ? kGateNeedsHost : kGateFails);
 }
 
+// K5: the reference's bounded clique search, stepped exactly, one thread per queued hypothesis.
+__global__ void __launch_bounds__(kK5Threads)
+k5_search_kernel(const int4 *__restrict__ job_hdr, const unsigned long long *__restrict__ job_pool,
+                 const unsigned long long *__restrict__ job_ctl, int n_hyp, int step_cap,
+                 uint8_t *__restrict__ verdict) {
+  const long long j = (long long)blockIdx.x * kK5Threads + threadIdx.x;
+  const long long n_narrow = (long long)job_ctl[0], n_wide = (long long)job_ctl[1];
+  if (j >= n_hyp || (j >= n_narrow && j < (long long)n_hyp - n_wide)) return;
+  const int4 hd = job_hdr[j];
+  if (hd.y <= 0) return;  // the pool was full: the verdict stays "host"
+  const unsigned long long *rows = job_pool + ((unsigned long long)(unsigned)hd.z | ((unsigned long long)(unsigned)hd.w << 32));
+  const int r = hd.y <= 64 ? small_gate_search(reinterpret_cast<const Bits64 *>(rows), hd.y, step_cap, nullptr)
+                           : small_gate_search(reinterpret_cast<const Bits128 *>(rows), hd.y, step_cap, nullptr);
+  if (r == 1) verdict[hd.x] = uint8_t(kGatePasses);
+  else if (r == 0) verdict[hd.x] = uint8_t(kGateFailsSearch);
+}
+
 }  // namespace
+
+// job queue layout: [3 x u64 control: narrow jobs, wide jobs, pool words used | pad to 256 B] [n_hyp headers] [pool]
+size_t gate_job_bytes(int n_hyp, size_t pool_bytes) {
+  return 256 + ((size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)) + pool_bytes;
+}
 
 cudaError_t launch_sample_degree_mask(const void *d_clusters, const int32_t *d_active, int n_active, int max_n,
                                       const uint32_t *d_sample, const uint32_t *d_valid, uint32_t *d_deg_mask,
@@ -303,18 +369,35 @@ cudaError_t launch_sample_degree_mask(const void *d_clusters, const int32_t *d_a
 cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_physical, const uint32_t *d_sample,
                                   const uint32_t *d_valid, const uint32_t *d_finite, const uint32_t *d_deg_mask,
                                   int n_hyp, const uint32_t *d_hyps, const int32_t *d_counts, const int32_t *d_floor,
-                                  int max_words, uint8_t *d_verdict, cudaStream_t stream) {
+                                  int max_words, uint8_t *d_verdict, void *d_jobs, size_t pool_bytes,
+                                  cudaStream_t stream) {
   if (n_hyp <= 0) return cudaSuccess;
   max_words = std::min(max_words, 128);  // clusters of more than 4096 correspondences go to the host search
   max_words = std::max(max_words, 4);
-  const size_t smem = size_t(kWarpsPerCta) * (2 * size_t(max_words) + kSmallCore / 2 + kSmallCore * 4) * sizeof(uint32_t);
+  const size_t smem = size_t(kWarpsPerCta) * (3 * size_t(max_words) + kSmallCore / 2 + kSmallCore * 4) * sizeof(uint32_t);
   cudaError_t e = cudaFuncSetAttribute(k4_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
+  unsigned long long *job_ctl = nullptr, *job_pool = nullptr;
+  int4 *job_hdr = nullptr;
+  if (d_jobs && pool_bytes >= 2048) {
+    job_ctl = static_cast<unsigned long long *>(d_jobs);
+    job_hdr = reinterpret_cast<int4 *>(static_cast<char *>(d_jobs) + 256);
+    job_pool = reinterpret_cast<unsigned long long *>(static_cast<char *>(d_jobs) + 256 +
+                                                      ((size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)));
+    e = cudaMemsetAsync(job_ctl, 0, 3 * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+  }
   const int blocks = (n_hyp + kWarpsPerCta - 1) / kWarpsPerCta;
   k4_gate_kernel<<<blocks, kWarpsPerCta * 32, smem, stream>>>(
       static_cast<const K3Cluster *>(d_clusters), d_physical, d_sample, d_valid, d_finite, d_deg_mask, n_hyp,
-      reinterpret_cast<const uint4 *>(d_hyps), d_counts, d_floor, max_words, d_verdict);
+      reinterpret_cast<const uint4 *>(d_hyps), d_counts, d_floor, max_words, d_verdict, job_hdr, job_pool, job_ctl,
+      (unsigned long long)(pool_bytes / 8));
   count_launch();
+  if (job_hdr) {
+    k5_search_kernel<<<(n_hyp + kK5Threads - 1) / kK5Threads, kK5Threads, 0, stream>>>(job_hdr, job_pool, job_ctl, n_hyp,
+                                                                                      kK5StepCap, d_verdict);
+    count_launch();
+  }
   return cudaGetLastError();
 }
 
