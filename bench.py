@@ -569,9 +569,11 @@ def run_ours(args):
         ev[s][0].record(stream)
         step()
         ev[s][1].record(stream)
-        k1_ms.append(m.last_k1_ms)   # CUDA events recorded by the library around the K1 launch, on the launch stream
     barrier()
     wall = time.perf_counter() - wall0
+    # CUDA events recorded by the library around every K1 launch of the timed region, on the launch stream; read after
+    # the loop (reading them inside it would park the host on each step and let the ranks drift apart)
+    k1_ms = [x for x in m.k1_ms_history(min(args.steps, 64)) if x >= 0]
     clocks = sampler.stop() if rank == 0 else None
     launches = lib.tod_kernel_launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)

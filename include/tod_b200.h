@@ -183,6 +183,9 @@ int tod_matcher_merge_device(tod_matcher *m, const uint32_t *d_keys_all, int32_t
                              tod_match *d_matches, int32_t *d_counts, float *d_points3d, void *stream);
 /* Device time (ms, CUDA events on the launch stream) of the K1 kernel alone in the last knn call; <0 if unknown. */
 float tod_matcher_last_k1_ms(const tod_matcher *m);
+/* The same for the call made `calls_ago` calls before the last one (0 = the last; the library keeps 64 event pairs):
+ * a streaming caller reads the K1 time of every step after its loop instead of synchronising inside it. */
+float tod_matcher_k1_ms_ago(const tod_matcher *m, int32_t calls_ago);
 /* Name of the K1 formulation actually used by the last call ("popc" | "mma"). */
 const char *tod_matcher_last_kernel(const tod_matcher *m);
 
@@ -338,7 +341,7 @@ float tod_last_stage_ms(void);
 int32_t tod_clique_find(int32_t n_vertices, const int32_t *edges, int32_t n_edges, uint32_t minimal_size,
                         int32_t *out_vertices, int32_t *finds_more);
 /*   tod_clique_gate_small  the fixed-capacity form of the same search that K5 runs on the GPU for induced sample
- *                    sub-graphs of at most 128 vertices (tod_b200/csrc/clique_small.h, one source for host and
+ *                    sub-graphs of at most 256 vertices (tod_b200/csrc/clique_small.h, one source for host and
  *                    device): the gate's question at minimal size 7 (sac_model_registration_graph.h:258-265).
  *                    Returns 1 (more than 7 vertices would be returned), 0 (not), -1 (step_cap reached: the caller
  *                    falls back to tod_clique_find), -2 on bad input; *steps (may be NULL) = search steps taken. */
@@ -417,9 +420,10 @@ void tod_guess_last_stats(const tod_guess *g, float *k2_ms, float *k3_ms, int64_
  * settled with a K4 "fails" verdict, [22] hypotheses K4 left undecided that the replay sent to the host search,
  * [23] device time of the K4 launches in microseconds. */
 void tod_guess_last_gate_stats(const tod_guess *g, int64_t *out24);
-/* K5 (the reference's bounded clique search stepped exactly on the GPU for induced sub-graphs of <= 128 vertices) in
+/* K5 (the reference's bounded clique search stepped exactly on the GPU for induced sub-graphs of <= 256 vertices) in
  * the last process call: [0] hypotheses the replay settled with a K5 "passes" verdict, [1] with a K5 "fails" verdict,
- * [2] hypotheses left to the host search (larger graphs, full queue, step cap), [3] reserved. */
+ * [2] hypotheses left to the host search (larger graphs, full queue, step cap), [3] device time of the K5 launches in
+ * microseconds (included in counter [23] of tod_guess_last_gate_stats). */
 void tod_guess_last_k5_stats(const tod_guess *g, int64_t *out4);
 /* Algorithmic bytes (SURVEY.md §8d units) moved by the K2 launch (32 n in + two n x W bit-matrices out, summed over
  * the clusters) and by all K3 launches ((3 rows + 2 masks) x W x 4 + 140 per hypothesis) of the last process call,

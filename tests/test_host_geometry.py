@@ -160,11 +160,12 @@ def clique_gate_small(n, edges, cap=100000):
 
 def test_small_gate_search_equals_the_host_clique_finder():
     """clique_small.h (the search K5 runs on the GPU, compiled here for the host) answers the gate's question exactly
-    like CliqueFinder::finds_more_than(7) on graphs of 1..128 vertices: dense graphs with a low-degree fringe (the
-    gate's regime) and the densities where the clique number sits around 7-8 and the search has to step."""
+    like CliqueFinder::finds_more_than(7) on graphs of 1..256 vertices: dense graphs with a low-degree fringe (the
+    gate's regime) and the densities where the clique number sits around 7-8 and the search has to step.  The entry
+    point also runs the 64- and 128-bit instantiations where the graph fits and fails if they disagree."""
     rng = np.random.default_rng(5)
     for trial in range(1500):
-        n = int(rng.integers(1, 129))
+        n = int(rng.integers(1, 257)) if trial % 3 else int(rng.integers(1, 129))
         if trial % 2:
             p = rng.choice([0.15, 0.4, 0.6, 0.7, 0.8, 0.85, 0.9, 0.97])
             a = np.triu(rng.random((n, n)) < p, 1)
@@ -184,7 +185,7 @@ def test_small_gate_search_equals_the_host_clique_finder():
 def test_small_gate_search_equals_compiled_reference():
     rng = np.random.default_rng(6)
     for trial in range(150):
-        n = int(rng.integers(8, 129))
+        n = int(rng.integers(8, 257))
         a = np.triu(rng.random((n, n)) < rng.uniform(0.2, 0.9), 1)
         edges = np.argwhere(a)
         exp = ref.find_clique(n, [tuple(x) for x in edges], 7, sorted_insert=True)
@@ -197,7 +198,7 @@ def test_small_gate_search_limits():
     edges = np.argwhere(np.triu(rng.random((100, 100)) < 0.45, 1))
     assert clique_gate_small(100, edges, cap=5)[0] == -1            # step cap reached: the caller falls back
     assert clique_gate_small(0, np.zeros((0, 2), np.int32))[0] == 0
-    assert clique_gate_small(129, np.zeros((0, 2), np.int32))[0] == -2
+    assert clique_gate_small(257, np.zeros((0, 2), np.int32))[0] == -2
     full = [(i, j) for i in range(8) for j in range(i + 1, 8)]
     assert clique_gate_small(8, full)[0] == 1                       # K8
     assert clique_gate_small(7, [(i, j) for i in range(7) for j in range(i + 1, 7)])[0] == 0   # K7: exactly 7

@@ -86,6 +86,7 @@ SIGNATURES = [
     ("tod_matcher_knn_keys_device", ctypes.c_int, [_P, _P, _I32, _P, _P]),
     ("tod_matcher_merge_device", ctypes.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P]),
     ("tod_matcher_last_k1_ms", _F, [_P]),
+    ("tod_matcher_k1_ms_ago", ctypes.c_float, [_P, _I32]),
     ("tod_matcher_last_kernel", ctypes.c_char_p, [_P]),
     ("tod_snapshot_write", ctypes.c_int, [ctypes.c_char_p, _I32, _P, _P, _P, _P]),
     ("tod_snapshot_open", ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_P)]),

@@ -153,6 +153,10 @@ class DescriptorMatcher:
     def last_k1_ms(self):
         return float(self._lib.tod_matcher_last_k1_ms(self._h))
 
+    def k1_ms_history(self, n):
+        """K1 kernel times (ms) of the last n calls, oldest first (the library keeps 64 event pairs)."""
+        return [float(self._lib.tod_matcher_k1_ms_ago(self._h, i)) for i in range(int(n) - 1, -1, -1)]
+
     def set_stage_timing(self, on):
         self._lib.tod_matcher_set_stage_timing(self._h, 1 if on else 0)
 
@@ -345,7 +349,7 @@ class GuessGenerator:
                                "colour_bound": gh[17], "searches": gh[18], "search_passes": gh[19],
                                "search_steps": gh[20], "k4_fails_used": gh[21], "k4_undecided_used": gh[22],
                                "k4_kernel_ms": gh[23] / 1000.0, "k5_passes_used": int(k5[0]),
-                               "k5_fails_used": int(k5[1])},
+                               "k5_fails_used": int(k5[1]), "k5_kernel_ms": int(k5[3]) / 1000.0},
                 "k2_ms": k2.value, "k3_ms": k3.value, "k2_bytes": b2.value, "k3_bytes": b3.value,
                 "n_clusters": ncl.value, "n_correspondences": ncor.value, "n_hypotheses": nh.value, "n_rounds": nr.value,
                 "host_ms": {"cluster_k2": prof[0], "sampler": prof[1], "k3_launch_sync": prof[2],

@@ -1,11 +1,12 @@
-// The clique gate's bounded search for graphs of at most 128 vertices, written once for the host and the device.
+// The clique gate's bounded search for graphs of at most 256 vertices, written once for the host and the device.
 //
 // Same contract as CliqueFinder::finds_more_than(7) (clique.h), i.e. "would tod::maximum_clique::Graph::FindClique
 // (src/common/maximum_clique.cpp:343-369 of the reference) called with minimal_size = 7 return MORE than 7 vertices?"
 // (sac_model_registration_graph.h:258-265), stepping exactly like the reference: DegreeSort (:263-284), ColorSort
 // (:219-261) with its shared colour vector, the 0.025 re-sort rule (:313), early exit at the first clique of 7
 // (:290, :325).  Only the SIZES of the incumbent and of the current clique are tracked — that is all the gate asks.
-// Fixed-capacity state (no allocation): vertex sets are 128-bit masks, the per-level candidate lists are byte arrays.
+// Fixed-capacity state (no allocation): vertex sets are masks of 64, 128 or 256 bits (one instantiation each), the
+// per-level candidate lists are byte arrays.
 // The 100000-step budget of the reference is replaced by a caller-given cap far below it: a search that reaches the
 // cap returns -1 and is decided by the host's CliqueFinder instead.
 #ifndef TOD_CLIQUE_SMALL_H_
@@ -21,14 +22,16 @@
 
 namespace tod {
 
-struct Bits128 {
-  unsigned long long lo, hi;
+// A vertex set of up to 64 * NW vertices.
+template <int NW>
+struct BitsN {
+  unsigned long long w[NW];
 };
-struct Bits64 {
-  unsigned long long lo;
-};
+typedef BitsN<1> Bits64;
+typedef BitsN<2> Bits128;
+typedef BitsN<4> Bits256;
 
-constexpr int kSmallGraphMax = 128;
+constexpr int kSmallGraphMax = 256;
 constexpr int kSmallGateMinimal = 7;  // std::min(best_inlier_number_, 7) with best_inlier_number_ >= 8 (:85, :203)
 
 namespace small_clique {
@@ -48,57 +51,69 @@ TOD_HD int clz64(unsigned long long x) {
 #endif
 }
 
-// set operations of the two row widths
-TOD_HD Bits128 empty_set(const Bits128 *) { return Bits128{0ull, 0ull}; }
-TOD_HD Bits64 empty_set(const Bits64 *) { return Bits64{0ull}; }
-TOD_HD bool test_bit(const Bits128 &s, int v) { return ((v < 64 ? s.lo >> v : s.hi >> (v - 64)) & 1ull) != 0; }
-TOD_HD bool test_bit(const Bits64 &s, int v) { return ((s.lo >> v) & 1ull) != 0; }
-TOD_HD void set_bit(Bits128 &s, int v) {
-  if (v < 64) s.lo |= 1ull << v;
-  else s.hi |= 1ull << (v - 64);
+template <int NW>
+TOD_HD BitsN<NW> empty_set() {
+  BitsN<NW> s;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) s.w[i] = 0ull;
+  return s;
 }
-TOD_HD void set_bit(Bits64 &s, int v) { s.lo |= 1ull << v; }
-TOD_HD int and_popc(const Bits128 &a, const Bits128 &b) { return popc64(a.lo & b.lo) + popc64(a.hi & b.hi); }
-TOD_HD int and_popc(const Bits64 &a, const Bits64 &b) { return popc64(a.lo & b.lo); }
-TOD_HD bool intersects(const Bits128 &a, const Bits128 &b) { return ((a.lo & b.lo) | (a.hi & b.hi)) != 0ull; }
-TOD_HD bool intersects(const Bits64 &a, const Bits64 &b) { return (a.lo & b.lo) != 0ull; }
+template <int NW>
+TOD_HD bool test_bit(const BitsN<NW> &s, int v) {
+  if (NW == 1) return ((s.w[0] >> v) & 1ull) != 0;
+  return ((s.w[v >> 6] >> (v & 63)) & 1ull) != 0;
+}
+template <int NW>
+TOD_HD void set_bit(BitsN<NW> &s, int v) {
+  if (NW == 1) s.w[0] |= 1ull << v;
+  else s.w[v >> 6] |= 1ull << (v & 63);
+}
+template <int NW>
+TOD_HD int and_popc(const BitsN<NW> &a, const BitsN<NW> &b) {
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) c += popc64(a.w[i] & b.w[i]);
+  return c;
+}
+template <int NW>
+TOD_HD bool intersects(const BitsN<NW> &a, const BitsN<NW> &b) {
+  unsigned long long x = 0ull;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) x |= a.w[i] & b.w[i];
+  return x != 0ull;
+}
 // highest member, removed from the set (-1 when empty)
-TOD_HD int pop_highest(Bits128 &s) {
-  if (s.hi) {
-    const int b = 63 - clz64(s.hi);
-    s.hi &= ~(1ull << b);
-    return 64 + b;
-  }
-  if (s.lo) {
-    const int b = 63 - clz64(s.lo);
-    s.lo &= ~(1ull << b);
-    return b;
-  }
+template <int NW>
+TOD_HD int pop_highest(BitsN<NW> &s) {
+#pragma unroll
+  for (int i = NW - 1; i >= 0; --i)
+    if (s.w[i]) {
+      const int b = 63 - clz64(s.w[i]);
+      s.w[i] &= ~(1ull << b);
+      return 64 * i + b;
+    }
   return -1;
 }
-TOD_HD int pop_highest(Bits64 &s) {
-  if (!s.lo) return -1;
-  const int b = 63 - clz64(s.lo);
-  s.lo &= ~(1ull << b);
-  return b;
-}
 
-template <typename Set, int kMaxN>
+// Idx: unsigned char up to 128 vertices, unsigned short above (positions and class numbers reach the vertex count)
+template <int NW, typename Idx>
 struct State {
-  unsigned char lists[kSmallGateMinimal + 2][kMaxN];  // candidate list of every recursion level (1-based)
-  unsigned char colour[kMaxN];                        // the colour vector shared by all levels
-  unsigned char snapshot[kMaxN], cls[kMaxN];
-  unsigned char count[kMaxN + 2];
-  Set class_mask[kMaxN + 1];
+  static constexpr int kMaxN = 64 * NW;
+  unsigned char lists[kSmallGateMinimal + 2][kMaxN];  // candidate list of every recursion level (1-based); ids < 256
+  Idx colour[kMaxN];                                  // the colour vector shared by all levels
+  unsigned char snapshot[kMaxN];
+  Idx cls[kMaxN];
+  Idx count[kMaxN + 2];
+  BitsN<NW> class_mask[kMaxN + 1];
   int size[kSmallGateMinimal + 2];
   unsigned level_steps[kSmallGateMinimal + 3], level_steps_old[kSmallGateMinimal + 3];
 };
 
 // DegreeSort: descending by (degree inside the list, vertex id) — std::sort of (degree, vertex) pairs read backwards.
 // Returns the largest degree.
-template <typename Set>
-TOD_HD int sort_by_degree(const Set *adj, unsigned char *r, int m, unsigned char *count) {
-  Set mask = empty_set(adj);
+template <int NW, typename Idx>
+TOD_HD int sort_by_degree(const BitsN<NW> *adj, unsigned char *r, int m, Idx *count) {
+  BitsN<NW> mask = empty_set<NW>();
   for (int i = 0; i < m; ++i) set_bit(mask, r[i]);
   for (int d = 0; d <= m; ++d) count[d] = 0;
   int top = 0;
@@ -111,68 +126,68 @@ TOD_HD int sort_by_degree(const Set *adj, unsigned char *r, int m, unsigned char
   int pos = 0;
   for (int d = top; d >= 0; --d) {
     const int c = count[d];
-    count[d] = (unsigned char)pos;
+    count[d] = (Idx)pos;
     pos += c;
   }
   // vertices by descending id; equal degrees keep that order
-  Set walk = mask;
+  BitsN<NW> walk = mask;
   for (int v = pop_highest(walk); v >= 0; v = pop_highest(walk)) r[count[and_popc(adj[v], mask)]++] = (unsigned char)v;
   return top;
 }
 
 // ColorSort with min_k == 1: every vertex, in list order, joins the first class that holds none of its neighbours;
 // the list is rewritten class by class and colour[position] = class number.
-template <typename Set, int kMaxN>
-TOD_HD void colour_sort(const Set *adj, State<Set, kMaxN> &s, unsigned char *r, int m) {
+template <int NW, typename Idx>
+TOD_HD void colour_sort(const BitsN<NW> *adj, State<NW, Idx> &s, unsigned char *r, int m) {
   int n_classes = 0;
   for (int i = 0; i < m; ++i) {
     const int p = r[i];
     s.snapshot[i] = (unsigned char)p;
-    const Set a = adj[p];
+    const BitsN<NW> a = adj[p];
     int k = 1;
     while (k <= n_classes && intersects(a, s.class_mask[k])) ++k;
     if (k > n_classes) {
       n_classes = k;
-      s.class_mask[k] = empty_set(adj);
+      s.class_mask[k] = empty_set<NW>();
       s.count[k] = 0;
     }
     set_bit(s.class_mask[k], p);
-    s.cls[i] = (unsigned char)k;
+    s.cls[i] = (Idx)k;
     ++s.count[k];
   }
   int pos = 0;
   for (int k = 1; k <= n_classes; ++k) {
     const int c = s.count[k];
-    s.count[k] = (unsigned char)pos;
+    s.count[k] = (Idx)pos;
     pos += c;
   }
   for (int i = 0; i < m; ++i) {
     const int k = s.cls[i];
     const int at = s.count[k]++;
     r[at] = s.snapshot[i];
-    s.colour[at] = (unsigned char)k;
+    s.colour[at] = (Idx)k;
   }
 }
 
 }  // namespace small_clique
 
-// adj: n rows, bit j of row i <=> vertices i and j are adjacent (symmetric, no self-loops); n <= 64 for Bits64 rows,
-// n <= 128 for Bits128 rows.
+// adj: n rows of NW 64-bit words, bit j of row i <=> vertices i and j are adjacent (symmetric, no self-loops),
+// n <= 64 * NW.
 // Returns 1 (the search returns more than 7 vertices: the gate passes), 0 (it does not), -1 (step cap reached).
-template <typename Set, int kMaxN>
-TOD_HD int small_gate_search_t(const Set *adj, int n, int step_cap, int *steps_out) {
+template <int NW, typename Idx>
+TOD_HD int small_gate_search_t(const BitsN<NW> *adj, int n, int step_cap, int *steps_out) {
   using namespace small_clique;
   constexpr int kMinimal = kSmallGateMinimal;
   if (steps_out) *steps_out = 0;
   if (n <= 0) return 0;
-  State<Set, kMaxN> s;
+  State<NW, Idx> s;
   for (int i = 0; i < kMinimal + 3; ++i) s.level_steps[i] = s.level_steps_old[i] = 0u;
   int steps = 1;
   int best = 0, cur = 0;
   unsigned char *order = s.lists[1];
   for (int i = 0; i < n; ++i) order[i] = (unsigned char)i;
   const int top = sort_by_degree(adj, order, n, s.count);
-  for (int i = 0; i < n; ++i) s.colour[i] = (unsigned char)(i < top ? i + 1 : top + 1);
+  for (int i = 0; i < n; ++i) s.colour[i] = (Idx)(i < top ? i + 1 : top + 1);
   long colour_size = n;
   // word in front of the colour array on a glibc heap (read by the reference when the shared vector underflows)
   unsigned long chunk = (4ul * (unsigned long)n + 8ul + 15ul) & ~15ul;
@@ -196,7 +211,7 @@ TOD_HD int small_gate_search_t(const Set *adj, int n, int step_cap, int *steps_o
           goto done;
         }
         unsigned char *next = s.lists[level + 1];
-        const Set a = adj[p];
+        const BitsN<NW> a = adj[p];
         int mn = 0;
         for (int i = 0; i < m; ++i) {
           const int v = r[i];
@@ -246,11 +261,14 @@ done:
   return result;
 }
 
-TOD_HD int small_gate_search(const Bits128 *adj, int n, int step_cap, int *steps_out) {
-  return small_gate_search_t<Bits128, 128>(adj, n, step_cap, steps_out);
-}
 TOD_HD int small_gate_search(const Bits64 *adj, int n, int step_cap, int *steps_out) {
-  return small_gate_search_t<Bits64, 64>(adj, n, step_cap, steps_out);
+  return small_gate_search_t<1, unsigned char>(adj, n, step_cap, steps_out);
+}
+TOD_HD int small_gate_search(const Bits128 *adj, int n, int step_cap, int *steps_out) {
+  return small_gate_search_t<2, unsigned char>(adj, n, step_cap, steps_out);
+}
+TOD_HD int small_gate_search(const Bits256 *adj, int n, int step_cap, int *steps_out) {
+  return small_gate_search_t<4, unsigned short>(adj, n, step_cap, steps_out);
 }
 
 }  // namespace tod

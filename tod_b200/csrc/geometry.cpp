@@ -92,7 +92,8 @@ int32_t tod_clique_gate_small(int32_t n_vertices, const int32_t *edges, int32_t 
     tod::set_error("bad graph (at most %d vertices)", tod::kSmallGraphMax);
     return -2;
   }
-  std::vector<tod::Bits128> adj(size_t(std::max(n_vertices, 1)), tod::Bits128{0ull, 0ull});
+  // widest form first; the narrower forms K5 uses for small graphs must agree with it
+  std::vector<tod::Bits256> adj(size_t(std::max(n_vertices, 1)), tod::small_clique::empty_set<4>());
   for (int32_t e = 0; e < n_edges; ++e) {
     const int32_t a = edges[2 * e], b = edges[2 * e + 1];
     if (a < 0 || a >= n_vertices || b < 0 || b >= n_vertices) {
@@ -104,18 +105,24 @@ int32_t tod_clique_gate_small(int32_t n_vertices, const int32_t *edges, int32_t 
     tod::small_clique::set_bit(adj[size_t(b)], a);
   }
   int st = 0;
-  int r;
-  if (n_vertices <= 64) {  // the one-word rows K5 uses for graphs of at most 64 vertices
-    std::vector<tod::Bits64> adj64(adj.size());
-    for (size_t i = 0; i < adj.size(); ++i) adj64[i].lo = adj[i].lo;
-    r = tod::small_gate_search(adj64.data(), n_vertices, step_cap, &st);
+  const int r = tod::small_gate_search(adj.data(), n_vertices, step_cap, &st);
+  if (n_vertices <= 128) {
+    std::vector<tod::Bits128> a2(adj.size());
+    for (size_t i = 0; i < adj.size(); ++i) a2[i].w[0] = adj[i].w[0], a2[i].w[1] = adj[i].w[1];
     int st2 = 0;
-    if (tod::small_gate_search(adj.data(), n_vertices, step_cap, &st2) != r || st2 != st) {
-      tod::set_error("the 64-bit and 128-bit forms of the search disagree");
+    if (tod::small_gate_search(a2.data(), n_vertices, step_cap, &st2) != r || st2 != st) {
+      tod::set_error("the 128-bit and 256-bit forms of the search disagree");
       return -2;
     }
-  } else {
-    r = tod::small_gate_search(adj.data(), n_vertices, step_cap, &st);
+  }
+  if (n_vertices <= 64) {
+    std::vector<tod::Bits64> a1(adj.size());
+    for (size_t i = 0; i < adj.size(); ++i) a1[i].w[0] = adj[i].w[0];
+    int st1 = 0;
+    if (tod::small_gate_search(a1.data(), n_vertices, step_cap, &st1) != r || st1 != st) {
+      tod::set_error("the 64-bit and 256-bit forms of the search disagree");
+      return -2;
+    }
   }
   if (steps) *steps = st;
   return r;

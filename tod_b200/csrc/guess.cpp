@@ -470,11 +470,11 @@ bool clique_gate(const Cluster &c, const std::vector<uint32_t> &inliers, GateScr
   const Clock::time_point t1 = Clock::now();
   g.ms_setup += std::chrono::duration<double, std::milli>(t1 - t0).count();
   // (when K4 has already run the proofs on the GPU and could not settle the hypothesis, they are not repeated)
-  const bool none = proofs_done ? false : proves_no_clique(g, nv, words, int(minimal) + 1);
+  const bool none = (proofs_done && nv <= tod::kGateProofMax) ? false : proves_no_clique(g, nv, words, int(minimal) + 1);
   const Clock::time_point t2 = Clock::now();
   g.ms_proof += std::chrono::duration<double, std::milli>(t2 - t1).count();
   ++g.hist[size_bucket(nv)];
-  if (!proofs_done) ++g.hist[8 + size_bucket(g.last_core)];
+  if (!(proofs_done && nv <= tod::kGateProofMax)) ++g.hist[8 + size_bucket(g.last_core)];
   if (none) {
     ++g.proved_empty;
     ++g.hist[g.last_core < int(minimal) + 1 ? 16 : 17];
@@ -508,7 +508,8 @@ void host_degree_mask(Cluster &c) {
 struct tod_guess {
   tod_guess_params p{};
   cudaStream_t stream = nullptr, copy_stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_k2 = nullptr, ev_S = nullptr, ev_P = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev_k2 = nullptr, ev_S = nullptr,
+              ev_P = nullptr;
   DeviceBuffer d_off, d_mo, d_q, d_t, d_px, d_sp, d_P, d_S, d_desc, d_valid, d_finite, d_hyps, d_counts, d_R, d_T;
   DeviceBuffer d_deg, d_active, d_floor, d_verdict;  // K4: degree masks, active-cluster list, per-cluster best, verdicts
   DeviceBuffer d_jobs;                               // K5: queue of packed induced sub-graphs (<= 128 vertices each)
@@ -613,6 +614,7 @@ int tod_guess_create(const tod_guess_params *p, tod_guess **out) {
   if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev1);
   if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev2);
   if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev3);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&g->ev4);
   if (ce != cudaSuccess) {
     tod_guess_destroy(g);
     return fail(TOD_ERR_CUDA, "creating the guess generator's stream/events failed: %s", cudaGetErrorString(ce));
@@ -632,6 +634,7 @@ void tod_guess_destroy(tod_guess *g) {
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->ev2) cudaEventDestroy(g->ev2);
   if (g->ev3) cudaEventDestroy(g->ev3);
+  if (g->ev4) cudaEventDestroy(g->ev4);
   if (g->ev_k2) cudaEventDestroy(g->ev_k2);
   if (g->ev_S) cudaEventDestroy(g->ev_S);
   if (g->ev_P) cudaEventDestroy(g->ev_P);
@@ -833,7 +836,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   int max_W = 0;
   for (const Cluster *c : clusters) max_W = std::max(max_W, c->W);
   long k4_fails_used = 0, k4_host_used = 0, k5_pass_used = 0, k5_fail_used = 0;
-  float k4_ms = 0.f;
+  float k4_ms = 0.f, k5_ms = 0.f;  // K4 + K5 together / K5 alone
   TOD_CUDA(cudaMemcpyAsync(g->d_off.ptr, offsets.data(), offsets.size() * 4, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(g->d_mo.ptr, mo.data(), mo.size() * 8, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(g->d_q.ptr, all_q.data(), all_q.size() * 4, cudaMemcpyHostToDevice, st));
@@ -990,8 +993,9 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
           }
           batch_verdict.resize(size_t(H));
           TOD_CUDA(g->d_verdict.reserve(size_t(H)));
-          // K5 queue: room for every hypothesis of the launch at the largest graph K5 takes (2 KB), capped at 1 GiB
-          const size_t pool_bytes = std::min<size_t>(size_t(H) * 2048, size_t(1) << 30);
+          // K5 queue: room for every hypothesis of the launch at 2 KB (128 vertices; the rare graphs of up to 256
+          // take 8 KB, most take 0.5 KB), capped at 1 GiB; a hypothesis that finds the pool full goes to the host
+          const size_t pool_bytes = std::min<size_t>(std::max<size_t>(size_t(H) * 2048, 65536), size_t(1) << 30);
           TOD_CUDA(g->d_jobs.reserve(tod::gate_job_bytes(H, pool_bytes)));
           TOD_CUDA(cudaMemcpyAsync(g->d_floor.ptr, floor_by_cluster.data(), floor_by_cluster.size() * 4,
                                    cudaMemcpyHostToDevice, st));
@@ -1000,7 +1004,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
                                               g->d_valid.as<uint32_t>(), g->d_finite.as<uint32_t>(),
                                               g->d_deg.as<uint32_t>(), H, g->d_hyps.as<uint32_t>(),
                                               g->d_counts.as<int32_t>(), g->d_floor.as<int32_t>(), max_W,
-                                              g->d_verdict.as<uint8_t>(), g->d_jobs.ptr, pool_bytes, st));
+                                              g->d_verdict.as<uint8_t>(), g->d_jobs.ptr, pool_bytes, st, g->ev4));
           TOD_CUDA(cudaEventRecord(g->ev3, st));
           TOD_CUDA(cudaMemcpyAsync(batch_verdict.data(), g->d_verdict.ptr, size_t(H), cudaMemcpyDeviceToHost, st));
         }
@@ -1015,6 +1019,8 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         if (inf_thr) {
           TOD_CUDA(cudaEventElapsedTime(&ms, g->ev2, g->ev3));
           k4_ms += ms;
+          TOD_CUDA(cudaEventElapsedTime(&ms, g->ev4, g->ev3));
+          k5_ms += ms;
         }
         if (!deg_on_host) {  // the round's degree masks arrived with this synchronisation
           for (int ci : active_idx) {
@@ -1319,6 +1325,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   g->k5_stats[0] = k5_pass_used;
   g->k5_stats[1] = k5_fail_used;
   g->k5_stats[2] = k4_host_used;
+  g->k5_stats[3] = int64_t(k5_ms * 1000.f);
   g->gate_hist[21] = k4_fails_used;
   g->gate_hist[22] = k4_host_used;
   g->gate_hist[23] = int64_t(k4_ms * 1000.f);

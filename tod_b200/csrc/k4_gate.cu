@@ -26,6 +26,8 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kSmallCore = 128;   // exhaustive search limit (two 64-bit words per set)
+constexpr int kProofMax = tod::kGateProofMax;  // larger filtered graphs skip the proofs (host search)
+constexpr int kSearchMax = 256;   // largest filtered graph K5 takes (four 64-bit words per row)
 constexpr int kMaxSweeps = 64;
 constexpr int kDfsBudget = 6000;  // node expansions per lane before giving the hypothesis back to the host
 constexpr int kK5Threads = 64;
@@ -59,7 +61,9 @@ sample_degree_mask_kernel(const K3Cluster *__restrict__ clusters, const int32_t 
   }
 }
 
-using U128 = Bits128;
+struct U128 {
+  unsigned long long lo, hi;
+};
 __device__ __forceinline__ int popc128(U128 a) { return __popcll(a.lo) + __popcll(a.hi); }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -75,8 +79,8 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
   const int warp = threadIdx.x >> 5;
   const int h = blockIdx.x * kWarpsPerCta + warp;
   if (h >= n_hyp) return;
-  // per warp: adj[128] (U128) | alive[max_words] | work[max_words] | filt[max_words] | ids[128] (u16)
-  const int per_warp = kSmallCore * 4 + 3 * max_words + kSmallCore / 2;
+  // per warp: adj[128] (U128) | alive[max_words] | work[max_words] | filt[max_words] | ids[256] (u16)
+  const int per_warp = kSmallCore * 4 + 3 * max_words + kSearchMax / 2;
   U128 *adj = reinterpret_cast<U128 *>(smem + size_t(warp) * per_warp);
   uint32_t *alive = smem + size_t(warp) * per_warp + kSmallCore * 4;
   uint32_t *work = alive + max_words;
@@ -113,6 +117,9 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
   }
   nf = __reduce_add_sync(0xffffffffu, nf);
   if (nf <= 7) return finish(kGateFails);  // :214-218
+  // A filtered graph of thousands of vertices (one object filling the frame) is too large for K5 and its proofs cost
+  // milliseconds per warp (2 ms of C1's 4.8 ms frame) while they rarely succeed there: straight to the host search.
+  if (nf > kProofMax) return finish(kGateNeedsHost);
   __syncwarp();
 
   // ---- neighbourhood test (:222-238) and 7-core: Jacobi sweeps of "degree inside the live set" ------------------------
@@ -214,12 +221,12 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
   }
   if (!undecided) return finish(kGateFails);
   // K5 job: the filtered graph (NOT its core — the reference's search order depends on every vertex) when it is small
-  const bool to_search = job_hdr != nullptr && nf <= kSmallCore;
+  const bool to_search = job_hdr != nullptr && nf <= kSearchMax;
   if (!to_search && n_alive > kSmallCore) return finish(kGateNeedsHost);
   const uint32_t *members = to_search ? filt : alive;
   const int nn = to_search ? nf : n_alive;
 
-  // ---- pack the induced sub-graph: vertex a = a-th smallest member (the renumbering of :241-255) ---------------------
+  // ---- the induced sub-graph's vertices: vertex a = a-th smallest member (the renumbering of :241-255) -------------
   __syncwarp();
   if (lane == 0) {
     int k = 0;
@@ -232,6 +239,43 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
     }
   }
   __syncwarp();
+  if (to_search) {
+    // queue: rows of 1, 2 or 4 words (<= 64, 128, 256 vertices), bump-allocated in the pool; the headers of each width
+    // are kept together so that the warps of K5 run one instantiation of the search each
+    const int nw = nn <= 64 ? 1 : (nn <= 128 ? 2 : 4);
+    const unsigned long long words = (unsigned long long)nw * (unsigned long long)nn;
+    unsigned long long slot = 0, off = 0;
+    if (lane == 0) {
+      slot = atomicAdd(job_ctl + (nw == 1 ? 0 : (nw == 2 ? 1 : 3)), 1ull);
+      off = atomicAdd(job_ctl + 2, words);
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    const bool fits = off + words <= pool_words;
+    if (fits) {
+      unsigned long long *dst = job_pool + off;
+      for (int i = lane; i < nn; i += 32) {
+        const uint32_t *row = S + size_t(ids[i]) * W;
+        unsigned long long a[4] = {0ull, 0ull, 0ull, 0ull};
+        for (int j = 0; j < nn; ++j) {
+          const uint32_t u = ids[j];
+          const unsigned long long bit = (__ldg(row + (u >> 5)) >> (u & 31)) & 1u;
+          a[j >> 6] |= bit << (j & 63);
+        }
+        for (int x = 0; x < nw; ++x) dst[size_t(i) * nw + x] = a[x];
+      }
+    }
+    // header slots: [0, n1) one-word jobs | [n_hyp - n2, n_hyp) two-word jobs | four-word jobs in a second array of
+    // n_hyp slots behind the first (a hypothesis takes at most one slot, so none of them can overflow)
+    if (lane == 0) {
+      const unsigned long long at = nw == 1 ? slot : (nw == 2 ? (unsigned long long)(n_hyp - 1) - slot
+                                                              : (unsigned long long)n_hyp + slot);
+      job_hdr[at] = make_int4(h, fits ? nn : 0, int(off & 0xffffffffull), int(off >> 32));
+    }
+    return finish(kGateNeedsHost);  // K5 overwrites the verdict unless the pool was full or its step cap is reached
+  }
+
+  // ---- pack the core into shared memory ------------------------------------------------------------------------------
   for (int i = lane; i < nn; i += 32) {
     const uint32_t *row = S + size_t(ids[i]) * W;
     U128 a{0ull, 0ull};
@@ -244,36 +288,6 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
     adj[i] = a;
   }
   __syncwarp();
-  if (to_search) {
-    // queue: headers of graphs of <= 64 vertices (one-word rows) grow from the front, the others from the back, so
-    // that the warps of K5 run one row width each; rows are bump-allocated in the pool
-    const bool narrow = nn <= 64;
-    const unsigned long long words = narrow ? (unsigned long long)nn : 2ull * (unsigned long long)nn;
-    unsigned long long slot = 0, off = 0;
-    if (lane == 0) {
-      slot = atomicAdd(job_ctl + (narrow ? 0 : 1), 1ull);
-      off = atomicAdd(job_ctl + 2, words);
-    }
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    off = __shfl_sync(0xffffffffu, off, 0);
-    const bool fits = off + words <= pool_words;
-    if (fits) {
-      unsigned long long *dst = job_pool + off;
-      if (narrow) {
-        for (int i = lane; i < nn; i += 32) dst[i] = adj[i].lo;
-      } else {
-        for (int i = lane; i < nn; i += 32) {
-          dst[2 * i] = adj[i].lo;
-          dst[2 * i + 1] = adj[i].hi;
-        }
-      }
-    }
-    // (at most one job per hypothesis, so the n_hyp header slots cannot overflow)
-    if (lane == 0)
-      job_hdr[narrow ? slot : (unsigned long long)(n_hyp - 1) - slot] =
-          make_int4(h, fits ? nn : 0, int(off & 0xffffffffull), int(off >> 32));
-    return finish(kGateNeedsHost);  // K5 overwrites the verdict unless the pool was full or its step cap is reached
-  }
 
   // ---- small core of a larger graph: exhaustive search for an 8-clique over 128-bit sets -----------------------------
   bool found = false, overflow = false;
@@ -331,23 +345,27 @@ __global__ void __launch_bounds__(kK5Threads)
 k5_search_kernel(const int4 *__restrict__ job_hdr, const unsigned long long *__restrict__ job_pool,
                  const unsigned long long *__restrict__ job_ctl, int n_hyp, int step_cap,
                  uint8_t *__restrict__ verdict) {
-  const long long j = (long long)blockIdx.x * kK5Threads + threadIdx.x;
-  const long long n_narrow = (long long)job_ctl[0], n_wide = (long long)job_ctl[1];
-  if (j >= n_hyp || (j >= n_narrow && j < (long long)n_hyp - n_wide)) return;
+  const long long j = (long long)blockIdx.x * kK5Threads + threadIdx.x;  // header slot, 2 * n_hyp of them
+  const long long n1 = (long long)job_ctl[0], n2 = (long long)job_ctl[1], n4 = (long long)job_ctl[3];
+  const bool mine = j < n1 || (j >= (long long)n_hyp - n2 && j < n_hyp) || (j >= n_hyp && j < (long long)n_hyp + n4);
+  if (!mine) return;
   const int4 hd = job_hdr[j];
   if (hd.y <= 0) return;  // the pool was full: the verdict stays "host"
   const unsigned long long *rows = job_pool + ((unsigned long long)(unsigned)hd.z | ((unsigned long long)(unsigned)hd.w << 32));
-  const int r = hd.y <= 64 ? small_gate_search(reinterpret_cast<const Bits64 *>(rows), hd.y, step_cap, nullptr)
-                           : small_gate_search(reinterpret_cast<const Bits128 *>(rows), hd.y, step_cap, nullptr);
+  int r;
+  if (hd.y <= 64) r = small_gate_search(reinterpret_cast<const Bits64 *>(rows), hd.y, step_cap, nullptr);
+  else if (hd.y <= 128) r = small_gate_search(reinterpret_cast<const Bits128 *>(rows), hd.y, step_cap, nullptr);
+  else r = small_gate_search(reinterpret_cast<const Bits256 *>(rows), hd.y, step_cap, nullptr);
   if (r == 1) verdict[hd.x] = uint8_t(kGatePasses);
   else if (r == 0) verdict[hd.x] = uint8_t(kGateFailsSearch);
 }
 
 }  // namespace
 
-// job queue layout: [3 x u64 control: narrow jobs, wide jobs, pool words used | pad to 256 B] [n_hyp headers] [pool]
+// job queue layout: [4 x u64 control: 1-word jobs, 2-word jobs, pool words used, 4-word jobs | pad to 256 B]
+// [2 * n_hyp headers] [pool]
 size_t gate_job_bytes(int n_hyp, size_t pool_bytes) {
-  return 256 + ((size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)) + pool_bytes;
+  return 256 + ((2 * size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)) + pool_bytes;
 }
 
 cudaError_t launch_sample_degree_mask(const void *d_clusters, const int32_t *d_active, int n_active, int max_n,
@@ -370,11 +388,11 @@ cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_phys
                                   const uint32_t *d_valid, const uint32_t *d_finite, const uint32_t *d_deg_mask,
                                   int n_hyp, const uint32_t *d_hyps, const int32_t *d_counts, const int32_t *d_floor,
                                   int max_words, uint8_t *d_verdict, void *d_jobs, size_t pool_bytes,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, cudaEvent_t ev_between) {
   if (n_hyp <= 0) return cudaSuccess;
   max_words = std::min(max_words, 128);  // clusters of more than 4096 correspondences go to the host search
   max_words = std::max(max_words, 4);
-  const size_t smem = size_t(kWarpsPerCta) * (3 * size_t(max_words) + kSmallCore / 2 + kSmallCore * 4) * sizeof(uint32_t);
+  const size_t smem = size_t(kWarpsPerCta) * (3 * size_t(max_words) + kSearchMax / 2 + kSmallCore * 4) * sizeof(uint32_t);
   cudaError_t e = cudaFuncSetAttribute(k4_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   unsigned long long *job_ctl = nullptr, *job_pool = nullptr;
@@ -383,8 +401,8 @@ cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_phys
     job_ctl = static_cast<unsigned long long *>(d_jobs);
     job_hdr = reinterpret_cast<int4 *>(static_cast<char *>(d_jobs) + 256);
     job_pool = reinterpret_cast<unsigned long long *>(static_cast<char *>(d_jobs) + 256 +
-                                                      ((size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)));
-    e = cudaMemsetAsync(job_ctl, 0, 3 * sizeof(unsigned long long), stream);
+                                                      ((2 * size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)));
+    e = cudaMemsetAsync(job_ctl, 0, 4 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
   }
   const int blocks = (n_hyp + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -393,9 +411,13 @@ cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_phys
       reinterpret_cast<const uint4 *>(d_hyps), d_counts, d_floor, max_words, d_verdict, job_hdr, job_pool, job_ctl,
       (unsigned long long)(pool_bytes / 8));
   count_launch();
+  if (ev_between) {
+    e = cudaEventRecord(ev_between, stream);
+    if (e != cudaSuccess) return e;
+  }
   if (job_hdr) {
-    k5_search_kernel<<<(n_hyp + kK5Threads - 1) / kK5Threads, kK5Threads, 0, stream>>>(job_hdr, job_pool, job_ctl, n_hyp,
-                                                                                      kK5StepCap, d_verdict);
+    k5_search_kernel<<<(2 * n_hyp + kK5Threads - 1) / kK5Threads, kK5Threads, 0, stream>>>(job_hdr, job_pool, job_ctl,
+                                                                                          n_hyp, kK5StepCap, d_verdict);
     count_launch();
   }
   return cudaGetLastError();

@@ -26,8 +26,11 @@ struct tod_matcher {
   bool trained = false;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool ev_valid = false;
+  // K1 is bracketed by a ring of event pairs, one pair per call: a caller that streams many steps can read every
+  // step's kernel time afterwards (tod_matcher_k1_ms_ago) without synchronising inside its loop
+  static constexpr int kEvRing = 64;
+  cudaEvent_t ev0[kEvRing] = {nullptr}, ev1[kEvRing] = {nullptr};
+  uint64_t k1_calls = 0;
   int64_t shard_begin = 0, shard_rows = 0;
   DeviceBuffer d_db, d_pts, d_offsets, d_query, d_partial, d_matches, d_counts, d_pts3d;
   // tensor-core formulation: int8 copies (db 0/1, queries +-1; 256 B / descriptor) and their TMA tensor maps
@@ -79,23 +82,25 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
     TOD_CUDA(m->d_popq.reserve(size_t(nq) * sizeof(uint32_t)));
     TOD_CUDA(tod::launch_expand_queries(d_query, m->d_q8.ptr, nq, m->d_popq.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
                                         st));
-    TOD_CUDA(cudaEventRecord(m->ev0, st));
+    const int er = int(m->k1_calls % tod_matcher::kEvRing);
+    TOD_CUDA(cudaEventRecord(m->ev0[er], st));
     TOD_CUDA(tod::launch_k1_mma(plan, m->map_q, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
                                 m->p.radius, m->d_partial.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
                                 m->d_popq.as<uint32_t>(), st));
-    TOD_CUDA(cudaEventRecord(m->ev1, st));
-    m->ev_valid = true;
+    TOD_CUDA(cudaEventRecord(m->ev1[er], st));
+    ++m->k1_calls;
     m->last_kernel = "mma";
     *plan_out = plan;
     return TOD_OK;
   }
   tod::K1Plan plan = tod::k1_popc_plan(nq, m->shard_rows, m->sm_count);
   TOD_CUDA(m->d_partial.reserve(size_t(plan.n_sources) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
-  TOD_CUDA(cudaEventRecord(m->ev0, st));
+  const int er = int(m->k1_calls % tod_matcher::kEvRing);
+  TOD_CUDA(cudaEventRecord(m->ev0[er], st));
   TOD_CUDA(tod::launch_k1_popc(plan, d_query, nq, m->d_db.ptr, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
                                m->p.radius, m->d_partial.as<uint32_t>(), st));
-  TOD_CUDA(cudaEventRecord(m->ev1, st));
-  m->ev_valid = true;
+  TOD_CUDA(cudaEventRecord(m->ev1[er], st));
+  ++m->k1_calls;
   m->last_kernel = "popc";
   *plan_out = plan;
   return TOD_OK;
@@ -254,8 +259,10 @@ int tod_matcher_create(const tod_matcher_params *p, tod_matcher **out) {
   m->p = *p;
   cudaError_t ce = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, p->device);
   if (ce == cudaSuccess) ce = cudaStreamCreate(&m->stream);
-  if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev0);
-  if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev1);
+  for (int i = 0; i < tod_matcher::kEvRing && ce == cudaSuccess; ++i) {
+    ce = cudaEventCreate(&m->ev0[i]);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev1[i]);
+  }
   if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev_x0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev_x1);
   if (ce != cudaSuccess) {
@@ -275,8 +282,10 @@ void tod_matcher_destroy(tod_matcher *m) {
                           &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8, &m->d_gthr, &m->d_popq, &m->d_rows,
                           &m->d_hkeys, &m->d_hvals, &m->d_keys_local, &m->d_keys_all})
     b->release();
-  if (m->ev0) cudaEventDestroy(m->ev0);
-  if (m->ev1) cudaEventDestroy(m->ev1);
+  for (int i = 0; i < tod_matcher::kEvRing; ++i) {
+    if (m->ev0[i]) cudaEventDestroy(m->ev0[i]);
+    if (m->ev1[i]) cudaEventDestroy(m->ev1[i]);
+  }
   if (m->ev_x0) cudaEventDestroy(m->ev_x0);
   if (m->ev_x1) cudaEventDestroy(m->ev_x1);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -505,13 +514,16 @@ int tod_matcher_merge_device(tod_matcher *m, const uint32_t *d_keys_all, int32_t
   return finalize(m, d_keys_all, n_src, nq, d_matches, d_counts, d_points3d, st);
 }
 
-float tod_matcher_last_k1_ms(const tod_matcher *m) {
-  if (!m || !m->ev_valid) return -1.f;
-  if (cudaEventSynchronize(m->ev1) != cudaSuccess) return -1.f;
+float tod_matcher_k1_ms_ago(const tod_matcher *m, int32_t calls_ago) {
+  if (!m || calls_ago < 0 || calls_ago >= tod_matcher::kEvRing || uint64_t(calls_ago) >= m->k1_calls) return -1.f;
+  const int er = int((m->k1_calls - 1 - uint64_t(calls_ago)) % tod_matcher::kEvRing);
+  if (cudaEventSynchronize(m->ev1[er]) != cudaSuccess) return -1.f;
   float ms = -1.f;
-  if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, m->ev0[er], m->ev1[er]) != cudaSuccess) return -1.f;
   return ms;
 }
+
+float tod_matcher_last_k1_ms(const tod_matcher *m) { return tod_matcher_k1_ms_ago(m, 0); }
 
 const char *tod_matcher_last_kernel(const tod_matcher *m) { return m ? m->last_kernel : "none"; }
 

@@ -180,13 +180,14 @@ cudaError_t launch_sample_degree_mask(const void *d_clusters, const int32_t *d_a
 // K5 (same launch call): hypotheses K4 cannot settle whose filtered graph has at most 128 vertices are queued in
 // d_jobs (gate_job_bytes(n_hyp, pool_bytes) bytes, may be null = no K5) and decided by the reference's bounded search
 // stepped exactly on the GPU: verdict 3 = the gate PASSES, 4 = it fails (decided by the search, not by a proof).
+constexpr int kGateProofMax = 1024;  // K4 runs its proofs on filtered graphs of at most this many vertices
 enum { kGateNotEvaluated = 0, kGateFails = 1, kGateNeedsHost = 2, kGatePasses = 3, kGateFailsSearch = 4 };
 size_t gate_job_bytes(int n_hyp, size_t pool_bytes);
 cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_physical, const uint32_t *d_sample,
                                   const uint32_t *d_valid, const uint32_t *d_finite, const uint32_t *d_deg_mask,
                                   int n_hyp, const uint32_t *d_hyps, const int32_t *d_counts, const int32_t *d_floor,
                                   int max_words, uint8_t *d_verdict, void *d_jobs, size_t pool_bytes,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, cudaEvent_t ev_between = nullptr);
 
 inline int adjacency_row_words(int n) { return ((n + 31) / 32 + 3) & ~3; }
 

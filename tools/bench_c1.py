@@ -40,7 +40,9 @@ def main():
          "ours": {"matcher_ms": 1e3 * float(np.median(tm[2:])), "guess_ms": 1e3 * float(np.median(tg[2:])),
                   "frame_ms": 1e3 * float(np.median(np.array(tm[2:]) + np.array(tg[2:]))),
                   "k1_kernel": m.last_kernel, "k1_ms": m.last_k1_ms, "poses": int(len(res["pose_results"])),
-                  "planted_pose_recovered": bool(ok), "matches": int(out["counts"].sum())}}
+                  "planted_pose_recovered": bool(ok), "matches": int(out["counts"].sum()),
+                  "guess_stats": {k: v for k, v in g.last_stats().items() if k in ("host_ms", "gate_shape", "k2_ms",
+                                  "k3_ms", "n_hypotheses", "n_rounds", "gate_thread_ms")}}}
     try:
         import cv2
         from oracle import ref
