@@ -347,6 +347,12 @@ int32_t tod_clique_find(int32_t n_vertices, const int32_t *edges, int32_t n_edge
  *                    falls back to tod_clique_find), -2 on bad input; *steps (may be NULL) = search steps taken. */
 int32_t tod_clique_gate_small(int32_t n_vertices, const int32_t *edges, int32_t n_edges, int32_t step_cap,
                               int32_t *steps);
+/* Stage-level call of K5 (needs a B200): the same search on the device for a batch of graphs of 1..256 vertices given
+ * as concatenated edge lists (graph g = edges[edge_offsets[g] .. edge_offsets[g + 1]), pairs of vertex ids) — same
+ * kernel, job queue layout and 512-step cap as inside tod_guess_process, where K4 fills the queue.
+ * results[g] = 1 (gate passes), 0 (fails), -1 (step cap reached: left to the host search). */
+int tod_gate_search_device(int32_t device, int32_t n_graphs, const int32_t *n_vertices, const int32_t *edge_offsets,
+                           const int32_t *edges, int32_t *results);
 int tod_rigid_fit(const float *query_pts, const float *train_pts, const uint32_t *indices, int32_t m, float *R, float *T);
 /*   tod_sample_triples  getSamples (sac_model_registration_graph.h:141-168): n_hyp sample triples from the sample
  *                    graph (n x tod_adjacency_row_words(n) bit-matrix) restricted to the valid mask, consuming the

@@ -120,6 +120,7 @@ SIGNATURES = [
     ("tod_last_stage_ms", _F, []),
     ("tod_clique_find", _I32, [_I32, _P, _I32, _U32, _P, ctypes.POINTER(_I32)]),
     ("tod_clique_gate_small", _I32, [_I32, _P, _I32, _I32, ctypes.POINTER(_I32)]),
+    ("tod_gate_search_device", ctypes.c_int, [_I32, _I32, _P, _P, _P, _P]),
     ("tod_rigid_fit", ctypes.c_int, [_P, _P, _P, _I32, _P, _P]),
     ("tod_sample_triples", _I32, [_I32, _P, _P, ctypes.POINTER(_U64), _I32, _P]),
     ("tod_select_inliers", _I32, [_I32, _P, _P, _P, _P, _P]),

@@ -128,6 +128,64 @@ int32_t tod_clique_gate_small(int32_t n_vertices, const int32_t *edges, int32_t 
   return r;
 }
 
+// K5 on the device for a batch of graphs given as edge lists: the same kernel, job queue layout and step cap as inside
+// tod_guess_process (where K4 fills the queue).  results[g] = 1 passes, 0 fails, -1 left to the host (step cap).
+int tod_gate_search_device(int32_t device, int32_t n_graphs, const int32_t *n_vertices, const int32_t *edge_offsets,
+                           const int32_t *edges, int32_t *results) {
+  TOD_REQUIRE(n_graphs >= 0 && (n_graphs == 0 || (n_vertices && edge_offsets && results)), "bad argument");
+  if (n_graphs == 0) return TOD_OK;
+  if (int rc = check_device(device)) return rc;
+  size_t pool_words = 0;
+  for (int32_t g = 0; g < n_graphs; ++g) {
+    TOD_REQUIRE(n_vertices[g] >= 1 && n_vertices[g] <= tod::kSmallGraphMax, "graph %d has %d vertices (1..%d)", g,
+                n_vertices[g], tod::kSmallGraphMax);
+    const int nw = n_vertices[g] <= 64 ? 1 : (n_vertices[g] <= 128 ? 2 : 4);
+    pool_words += size_t(nw) * size_t(n_vertices[g]);
+  }
+  const size_t hdr_bytes = (2 * size_t(n_graphs) * 16 + 255) & ~size_t(255);
+  std::vector<unsigned char> host(256 + hdr_bytes + pool_words * 8, 0);
+  unsigned long long *ctl = reinterpret_cast<unsigned long long *>(host.data());
+  int32_t *hdr = reinterpret_cast<int32_t *>(host.data() + 256);
+  unsigned long long *pool = reinterpret_cast<unsigned long long *>(host.data() + 256 + hdr_bytes);
+  size_t off = 0;
+  for (int32_t g = 0; g < n_graphs; ++g) {
+    const int n = n_vertices[g];
+    const int nw = n <= 64 ? 1 : (n <= 128 ? 2 : 4);
+    unsigned long long *rows = pool + off;
+    for (int32_t e = edge_offsets[g]; e < edge_offsets[g + 1]; ++e) {
+      const int32_t a = edges[2 * e], b = edges[2 * e + 1];
+      TOD_REQUIRE(a >= 0 && a < n && b >= 0 && b < n, "edge endpoint out of range in graph %d", g);
+      if (a == b) continue;
+      rows[size_t(a) * nw + (b >> 6)] |= 1ull << (b & 63);
+      rows[size_t(b) * nw + (a >> 6)] |= 1ull << (a & 63);
+    }
+    const size_t slot = nw == 1 ? size_t(ctl[0]++) : (nw == 2 ? size_t(n_graphs) - 1 - size_t(ctl[1]++)
+                                                               : size_t(n_graphs) + size_t(ctl[3]++));
+    int32_t *h = hdr + slot * 4;
+    h[0] = g;
+    h[1] = n;
+    h[2] = int32_t(off & 0xffffffffull);
+    h[3] = int32_t(off >> 32);
+    off += size_t(nw) * size_t(n);
+  }
+  ctl[2] = off;
+  void *d_jobs = nullptr;
+  uint8_t *d_verdict = nullptr;
+  TOD_CUDA(cudaMalloc(&d_jobs, host.size()));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_verdict), size_t(n_graphs));
+  if (e == cudaSuccess) e = cudaMemcpy(d_jobs, host.data(), host.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(d_verdict, tod::kGateNeedsHost, size_t(n_graphs));
+  if (e == cudaSuccess) e = tod::launch_gate_search_jobs(n_graphs, d_jobs, d_verdict, nullptr);
+  std::vector<uint8_t> v(static_cast<size_t>(n_graphs));
+  if (e == cudaSuccess) e = cudaMemcpy(v.data(), d_verdict, size_t(n_graphs), cudaMemcpyDeviceToHost);
+  cudaFree(d_jobs);
+  if (d_verdict) cudaFree(d_verdict);
+  if (e != cudaSuccess) return tod::fail(TOD_ERR_CUDA, "K5 launch failed: %s", cudaGetErrorString(e));
+  for (int32_t g = 0; g < n_graphs; ++g)
+    results[g] = v[size_t(g)] == tod::kGatePasses ? 1 : (v[size_t(g)] == tod::kGateFailsSearch ? 0 : -1);
+  return TOD_OK;
+}
+
 int tod_rigid_fit(const float *query_pts, const float *train_pts, const uint32_t *indices, int32_t m, float *R, float *T) {
   TOD_REQUIRE(query_pts && train_pts && indices && R && T && m >= 1, "bad argument");
   tod::rigid_fit(query_pts, train_pts, indices, m, R, T);

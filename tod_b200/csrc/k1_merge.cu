@@ -24,17 +24,19 @@ __device__ __forceinline__ void topk_insert(uint32_t (&best)[K], uint32_t key) {
   }
 }
 
-// keys: n_src x nq x K.  One thread per query; reads are coalesced across the warp for every (src, slot).
-template <int K>
-__device__ __forceinline__ void reduce_query(const uint32_t *__restrict__ keys, int n_src, int nq, int q,
+// keys: n_src lists of nq x K keys, src_stride keys apart.  One thread per query; reads are coalesced across the warp
+// for every (src, slot).  kPeerWritten: the lists were stored by other GPUs over NVLink during this launch's wait —
+// read them through L2 (ld.global.cg), never through the non-coherent path.
+template <int K, bool kPeerWritten = false>
+__device__ __forceinline__ void reduce_query(const uint32_t *__restrict__ keys, int n_src, size_t src_stride, int q,
                                              uint32_t (&best)[K]) {
 #pragma unroll
   for (int i = 0; i < K; ++i) best[i] = kKeyEmpty;
   for (int s = 0; s < n_src; ++s) {
-    const uint32_t *p = keys + (size_t(s) * nq + q) * K;
+    const uint32_t *p = keys + size_t(s) * src_stride + size_t(q) * K;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      const uint32_t key = __ldg(p + i);
+      const uint32_t key = kPeerWritten ? __ldcg(p + i) : __ldg(p + i);
       if (key >= best[K - 1]) break;  // source lists are ascending
       topk_insert<K>(best, key);
     }
@@ -47,9 +49,49 @@ __global__ void __launch_bounds__(128) reduce_keys_kernel(const uint32_t *__rest
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   uint32_t best[K];
-  reduce_query<K>(keys, n_src, nq, q, best);
+  reduce_query<K>(keys, n_src, size_t(nq) * K, q, best);
 #pragma unroll
   for (int i = 0; i < K; ++i) out[size_t(q) * K + i] = best[i];
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Fused top-k reduction + all-gather over peer memory: every rank reduces its chunk lists to K keys per query and
+// stores them straight into slot `rank` of EVERY rank's exchange buffer (plain stores into CUDA-IPC-mapped peer memory:
+// NVLink writes, no copy engine, no NCCL kernel); the block that finishes last raises this rank's flag on every peer
+// with a system-scope release.  peers[r] = base of rank r's buffer for this step's parity: world slots of slot_stride
+// keys, then (at flag_offset keys) world flags.
+template <int K>
+__global__ void __launch_bounds__(128)
+reduce_push_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, uint32_t *const *__restrict__ peers, int world,
+                   int rank, size_t slot_stride, size_t flag_offset, uint32_t step, unsigned int *__restrict__ ticket) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq) {
+    uint32_t best[K];
+    reduce_query<K>(keys, n_src, size_t(nq) * K, q, best);
+    for (int r = 0; r < world; ++r) {
+      uint32_t *dst = peers[r] + size_t(rank) * slot_stride + size_t(q) * K;
+#pragma unroll
+      for (int i = 0; i < K; ++i) dst[i] = best[i];
+    }
+  }
+  __threadfence_system();   // this thread's peer stores are visible system-wide before the block takes its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *ticket = 0u;
+      __threadfence_system();
+      for (int r = 0; r < world; ++r) st_release_sys(peers[r] + flag_offset + rank, step);
+    }
+  }
 }
 
 template <int K>
@@ -57,11 +99,29 @@ __global__ void __launch_bounds__(128)
 finalize_matches_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, uint32_t radius,
                         const uint32_t *__restrict__ obj_offsets, int n_objects, const float *__restrict__ points,
                         tod_match *__restrict__ matches, int32_t *__restrict__ counts,
-                        float *__restrict__ points3d, int ratio_enabled, float ratio, uint32_t *__restrict__ rows_out) {
+                        float *__restrict__ points3d, int ratio_enabled, float ratio, uint32_t *__restrict__ rows_out,
+                        size_t src_stride, const uint32_t *__restrict__ wait_flags, uint32_t wait_step,
+                        uint32_t *__restrict__ wait_error) {
+  if (wait_flags) {
+    // peer exchange: list s was pushed by rank s; its flag reaches wait_step once all of it is visible here.  Bounded
+    // wait (~4 s): a rank that never arrives must not hang the GPU — the error word is reported by the next call.
+    if (int(threadIdx.x) < n_src) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys(wait_flags + threadIdx.x) != wait_step) {
+        if (clock64() - t0 > (1ll << 33)) {
+          atomicExch(wait_error, 1u);
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+  }
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   uint32_t best[K];
-  reduce_query<K>(keys, n_src, nq, q, best);
+  if (wait_flags) reduce_query<K, true>(keys, n_src, src_stride, q, best);
+  else reduce_query<K>(keys, n_src, src_stride, q, best);
   if (ratio_enabled && K >= 2) {
     // the ratio-test TODO of DescriptorMatcher.cpp:223-227 as Lowe's test on the two nearest neighbours (before the
     // radius cut): keep the best match only, and only if distance0 < ratio * distance1
@@ -226,12 +286,28 @@ cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k,
 cudaError_t launch_finalize_matches(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t radius,
                                     const uint32_t *d_obj_offsets, int n_objects, const float *d_points,
                                     tod_match *d_matches, int32_t *d_counts, float *d_points3d,
-                                    cudaStream_t stream, int ratio_enabled, float ratio, uint32_t *d_rows_out) {
+                                    cudaStream_t stream, int ratio_enabled, float ratio, uint32_t *d_rows_out,
+                                    size_t src_stride, const uint32_t *d_wait_flags, uint32_t wait_step,
+                                    uint32_t *d_wait_error) {
   if (nq <= 0) return cudaSuccess;
+  if (d_wait_flags && n_src > 128) return cudaErrorInvalidValue;
+  if (src_stride == 0) src_stride = size_t(nq) * size_t(k);
   const int blocks = (nq + 127) / 128;
   TOD_DISPATCH_K(k, (finalize_matches_kernel<K><<<blocks, 128, 0, stream>>>(
                         d_keys, n_src, nq, radius, d_obj_offsets, n_objects, d_points, d_matches, d_counts,
-                        d_points3d, ratio_enabled, ratio, d_rows_out)));
+                        d_points3d, ratio_enabled, ratio, d_rows_out, src_stride, d_wait_flags, wait_step,
+                        d_wait_error)));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_push(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t *const *d_peers, int world,
+                               int rank, size_t slot_stride, size_t flag_offset, uint32_t step, unsigned int *d_ticket,
+                               cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  const int blocks = (nq + 127) / 128;
+  TOD_DISPATCH_K(k, (reduce_push_kernel<K><<<blocks, 128, 0, stream>>>(d_keys, n_src, nq, d_peers, world, rank,
+                                                                        slot_stride, flag_offset, step, d_ticket)));
   count_launch();
   return cudaGetLastError();
 }

@@ -368,6 +368,19 @@ size_t gate_job_bytes(int n_hyp, size_t pool_bytes) {
   return 256 + ((2 * size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)) + pool_bytes;
 }
 
+// K5 alone on a prepared job queue (layout of gate_job_bytes): for the stage-level entry point tod_gate_search_device.
+cudaError_t launch_gate_search_jobs(int n_hyp, void *d_jobs, uint8_t *d_verdict, cudaStream_t stream) {
+  if (n_hyp <= 0) return cudaSuccess;
+  unsigned long long *job_ctl = static_cast<unsigned long long *>(d_jobs);
+  int4 *job_hdr = reinterpret_cast<int4 *>(static_cast<char *>(d_jobs) + 256);
+  unsigned long long *job_pool = reinterpret_cast<unsigned long long *>(
+      static_cast<char *>(d_jobs) + 256 + ((2 * size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)));
+  k5_search_kernel<<<(2 * n_hyp + kK5Threads - 1) / kK5Threads, kK5Threads, 0, stream>>>(job_hdr, job_pool, job_ctl, n_hyp,
+                                                                                        kK5StepCap, d_verdict);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sample_degree_mask(const void *d_clusters, const int32_t *d_active, int n_active, int max_n,
                                       const uint32_t *d_sample, const uint32_t *d_valid, uint32_t *d_deg_mask,
                                       int min_degree, cudaStream_t stream) {

@@ -132,7 +132,17 @@ cudaError_t launch_finalize_matches(const uint32_t *d_keys, int n_src, int nq, i
                                     const uint32_t *d_obj_offsets, int n_objects, const float *d_points,
                                     tod_match *d_matches, int32_t *d_counts, float *d_points3d,
                                     cudaStream_t stream, int ratio_enabled = 0, float ratio = 0.f,
-                                    uint32_t *d_rows_out = nullptr);
+                                    uint32_t *d_rows_out = nullptr, size_t src_stride = 0,
+                                    const uint32_t *d_wait_flags = nullptr, uint32_t wait_step = 0,
+                                    uint32_t *d_wait_error = nullptr);
+// Fused top-k reduction + all-gather over peer memory (k1_merge.cu: reduce_push_kernel): the reduced keys of this rank
+// go straight into slot `rank` of every rank's exchange buffer (d_peers[r] = that buffer's base for this step's parity,
+// CUDA-IPC-mapped), then this rank's flag (at d_peers[r] + flag_offset + rank) is raised to `step` on every peer.
+// The matching launch_finalize_matches call passes d_wait_flags (= own buffer + flag_offset) and wait_step = step:
+// it starts merging once every rank's flag has arrived.
+cudaError_t launch_reduce_push(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t *const *d_peers, int world,
+                               int rank, size_t slot_stride, size_t flag_offset, uint32_t step, unsigned int *d_ticket,
+                               cudaStream_t stream);
 // Duplicate-match removal inside each frame (DescriptorMatcher.cpp:229 TODO): d_rows = the global DB row of every
 // match slot (written by launch_finalize_matches); the hash tables hold table_slots (a power of two) u64 each.
 cudaError_t launch_remove_duplicates(tod_match *d_matches, int32_t *d_counts, float *d_points3d,
@@ -183,6 +193,7 @@ cudaError_t launch_sample_degree_mask(const void *d_clusters, const int32_t *d_a
 constexpr int kGateProofMax = 1024;  // K4 runs its proofs on filtered graphs of at most this many vertices
 enum { kGateNotEvaluated = 0, kGateFails = 1, kGateNeedsHost = 2, kGatePasses = 3, kGateFailsSearch = 4 };
 size_t gate_job_bytes(int n_hyp, size_t pool_bytes);
+cudaError_t launch_gate_search_jobs(int n_hyp, void *d_jobs, uint8_t *d_verdict, cudaStream_t stream);
 cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_physical, const uint32_t *d_sample,
                                   const uint32_t *d_valid, const uint32_t *d_finite, const uint32_t *d_deg_mask,
                                   int n_hyp, const uint32_t *d_hyps, const int32_t *d_counts, const int32_t *d_floor,
