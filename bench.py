@@ -53,10 +53,11 @@ def parse_args():
     ap.add_argument("--no-pipeline", action="store_true", help="skip the C4 (matcher + guess generator) leg")
     ap.add_argument("--pipeline-frames", type=int, default=64)
     ap.add_argument("--c5-objects", type=int, default=100, help="objects in the C5 RANSAC-stress leg (0 = skip)")
-    ap.add_argument("--exchange", default="library", choices=["library", "torch"],
-                    help="N > 1, device-timed loop only: 'torch' moves the key all-gather out of the library "
-                         "(stage calls + torch.distributed), for A/B comparison; the default and the e2e loop use the "
-                         "in-library ncclAllGather")
+    ap.add_argument("--exchange", default="library", choices=["library", "nccl", "torch"],
+                    help="N > 1: 'library' (default) = the exchange inside the library, over peer memory where the GPUs "
+                         "can map each other (reduce+push kernel over NVLink) else ncclAllGather; 'nccl' = force the "
+                         "in-library ncclAllGather; 'torch' = device-timed loop only, the key all-gather moved out of "
+                         "the library (stage calls + torch.distributed), for A/B comparison")
     ap.add_argument("--trace", action="store_true", help="progress lines on stderr (debugging a multi-rank run)")
     return ap.parse_args()
 
@@ -514,6 +515,8 @@ def run_ours(args):
         dist.broadcast_object_list(box, src=0)
         trace("unique id received")
         m.set_comm(box[0])
+        if args.exchange == "nccl":
+            m.set_exchange(False)
         trace("communicator up, mode %d" % m.comm_mode)
 
     stream = torch.cuda.Stream(device=dev)     # explicit, non-legacy: K1 / NCCL / merge are all ordered on it
@@ -652,6 +655,8 @@ def run_ours(args):
         m.process(q_host.numpy(), out=out)
         assert (m_np == ref_m).all() and (c_host.numpy() == ref_c).all() and (p_host.numpy() == ref_p).all()
 
+    if world > 1 and m.exchange_error != 0:
+        raise SystemExit("peer exchange timed out on rank %d" % rank)
     shard_rows, kern = m.shard_rows, m.last_kernel
     per_rank = None
     if world > 1:
@@ -752,8 +757,12 @@ def run_ours(args):
                               "buffers, copies of step i+1 / i-1 overlapped with the compute of step i")},
             "parity": parity,
             "collective": (None if world == 1 else
-                           {"where": "inside libtod_b200.so (ncclAllGather of packed top-k keys on the handle's "
-                                     "stream); no torch.distributed collective in the timed region",
+                           {"where": ("inside libtod_b200.so: the top-k reduction kernel stores every rank's packed keys "
+                                      "straight into the other GPUs' exchange buffers over NVLink (CUDA-IPC-mapped peer "
+                                      "memory) and raises a flag there; the merge kernel starts when all flags have "
+                                      "arrived — no NCCL kernel on the data path" if comm_mode == 2 else
+                                      "inside libtod_b200.so (ncclAllGather of packed top-k keys on the handle's "
+                                      "stream)") + "; no torch.distributed collective in the timed region",
                             "comm_mode": comm_mode, "device_timed_exchange": args.exchange, "per_rank": per_rank}),
             "gpu_launches": int(launches), "wall_s_timed_region": wall, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "cpu_baseline_lsh": lsh}

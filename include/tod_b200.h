@@ -158,8 +158,19 @@ int tod_matcher_reserve(tod_matcher *m, int32_t max_nq);
 #define TOD_COMM_ID_BYTES 128
 int tod_comm_unique_id(void *id_out);
 int tod_matcher_set_comm(tod_matcher *m, const void *unique_id);
-/* 0 = no communicator, 1 = NCCL communicator attached */
+/* 0 = no communicator, 1 = NCCL communicator attached (exchange = ncclAllGather of the packed keys), 2 = NCCL
+ * communicator + peer-memory exchange: at the first sharded call the ranks trade CUDA IPC handles through the
+ * communicator and map each other's exchange buffers; from then on the top-k reduction kernel stores every rank's keys
+ * straight into all the other GPUs over NVLink and raises a flag there, and the merge kernel starts as soon as every
+ * flag has arrived — no NCCL kernel, no copy engine on the data path.  If any rank cannot map a peer (no peer access,
+ * one process holding several handles) all ranks stay in mode 1.  Results are identical in both modes. */
 int32_t tod_matcher_comm_mode(const tod_matcher *m);
+/* peer_memory = 0 keeps the ncclAllGather path (A/B measurements); 1 (default) lets the next sharded call try the
+ * peer-memory exchange.  Collective in effect: call it with the same value on every rank, between steps. */
+int tod_matcher_set_exchange(tod_matcher *m, int32_t peer_memory);
+/* 1 if a merge kernel of the peer-memory exchange gave up waiting for a rank (about 4 s) since the communicator was
+ * attached — the results of that call are invalid; tod_matcher_knn checks it itself and returns TOD_ERR_STATE. */
+int32_t tod_matcher_exchange_error(const tod_matcher *m);
 /* Device time (ms, CUDA events on the launch stream) of the ncclAllGather of the last sharded call; < 0 if none.
  * The two extra event records cost a few microseconds per step, so they are off unless stage timing is switched on
  * (profiling runs); the K1 events behind tod_matcher_last_k1_ms are always recorded. */

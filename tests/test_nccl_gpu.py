@@ -1,7 +1,10 @@
 """GPU, >= 2 devices: the sharded matcher with the exchange INSIDE the library — one process per GPU, each handle holds
 one row range of the DB and an NCCL communicator (tod_matcher_set_comm); tod_matcher_knn / tod_matcher_knn_device then
-run K1 -> top-k reduction -> ncclAllGather -> merge on the handle's stream and every rank must return the complete,
-bit-exact result (oracle = exact Hamming k-NN over the whole DB), step after step with changing query sets.
+run K1 -> top-k reduction -> exchange -> merge on the handle's stream and every rank must return the complete,
+bit-exact result (oracle = exact Hamming k-NN over the whole DB), step after step with changing query sets — with the
+peer-memory exchange (reduce_push_kernel storing into the other GPUs over NVLink; comm_mode 2, the default where the
+GPUs can map each other) and with the ncclAllGather exchange (comm_mode 1), including a query set larger than the
+reserved size, which makes the ranks re-map their exchange buffers.
 
 Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_nccl_gpu.py -m gpu`."""
 import os
@@ -31,7 +34,7 @@ def _workload():
     descs[1][:, :] = 0
     descs[1][:, 9] = rng.integers(0, 4, descs[1].shape[0])            # tie-heavy object straddling a shard boundary
     steps = []
-    for s, nq in enumerate([700, 2000, 333, 2000, 1, 4096]):          # ragged, changing sizes step after step
+    for s, nq in enumerate([700, 2000, 333, 2000, 1, 4096, 5000]):    # ragged, changing sizes step after step
         q, _, _ = synth.make_queries(descs, nq, seed=400 + s)
         if s == 2:
             q[:60] = 0
@@ -62,7 +65,10 @@ def _rank_main(rank, world, uid, k, radius, out_dir):
     assert mode == 1
     dev = torch.device("cuda", rank)
     ok = True
-    for rep in range(2):
+    modes = []
+    for rep in range(3):
+        if rep == 2:
+            m.set_exchange(False)                                      # the ncclAllGather path, same results
         for q in steps:
             out = m.process(q)                                         # host buffers: H2D + K1 + all-gather + merge + D2H
             em, ec = hk.knn_c(q, descs, k, radius)
@@ -84,7 +90,9 @@ def _rank_main(rank, world, uid, k, radius, out_dir):
             same = same and (md.cpu().numpy().view(capi.MATCH_DTYPE).reshape(nq, k) == out["matches"]).all()
             same = same and (cd.cpu().numpy() == out["counts"]).all()
             ok = ok and bool(same)
-    np.save(os.path.join(out_dir, "ok_%d.npy" % rank), np.array([int(ok), mode, m.shard_rows]))
+        modes.append(m.comm_mode)
+        ok = ok and m.exchange_error == 0
+    np.save(os.path.join(out_dir, "ok_%d.npy" % rank), np.array([int(ok), mode, m.shard_rows] + modes))
     if rank == 0:
         import time
         time.sleep(2.0)            # ranks tear their handles down at different times: nobody may wait for anybody
@@ -101,5 +109,8 @@ def test_sharded_matcher_with_in_library_nccl(tmp_path, k, radius):
     mp.spawn(_rank_main, args=(world, uid, k, radius, str(tmp_path)), nprocs=world, join=True)
     res = [np.load(os.path.join(str(tmp_path), "ok_%d.npy" % r)) for r in range(world)]
     assert all(int(r[0]) == 1 for r in res), res
+    assert all(int(r[5]) == 1 for r in res), res                       # third pass ran on ncclAllGather
+    assert len(set(int(r[3]) for r in res)) == 1                       # every rank made the same choice of exchange
+    print("exchange modes per pass:", [int(x) for x in res[0][3:6]])
     descs, _, _ = _workload()
     assert sum(int(r[2]) for r in res) == sum(d.shape[0] for d in descs)

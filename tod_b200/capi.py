@@ -78,6 +78,8 @@ SIGNATURES = [
     ("tod_matcher_reserve", ctypes.c_int, [_P, _I32]),
     ("tod_comm_unique_id", ctypes.c_int, [_P]),
     ("tod_matcher_set_comm", ctypes.c_int, [_P, _P]),
+    ("tod_matcher_set_exchange", ctypes.c_int, [_P, _I32]),
+    ("tod_matcher_exchange_error", _I32, [_P]),
     ("tod_matcher_comm_mode", _I32, [_P]),
     ("tod_matcher_set_stage_timing", None, [_P, _I32]),
     ("tod_matcher_last_exchange_ms", _F, [_P]),

@@ -129,7 +129,15 @@ class DescriptorMatcher:
 
     @property
     def comm_mode(self):
+        """0 none, 1 NCCL all-gather, 2 peer-memory exchange (after the first sharded call mapped the peers)."""
         return int(self._lib.tod_matcher_comm_mode(self._h))
+
+    def set_exchange(self, peer_memory):
+        capi.check(self._lib.tod_matcher_set_exchange(self._h, 1 if peer_memory else 0))
+
+    @property
+    def exchange_error(self):
+        return int(self._lib.tod_matcher_exchange_error(self._h))
 
     def process_device(self, d_query_ptr, nq, d_matches_ptr, d_counts_ptr, d_points3d_ptr, stream=None):
         """DescriptorMatcher.process on device buffers (tod_matcher_knn_device), enqueued on `stream`."""

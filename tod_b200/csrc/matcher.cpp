@@ -51,6 +51,16 @@ struct tod_matcher {
   bool ev_x_valid = false;
   bool stage_timing = false;         // tod_matcher_set_stage_timing: also bracket the exchange with events
   int32_t reserved_nq = 0;
+  // peer-memory exchange (comm_mode 2): every rank owns one buffer of 2 parities x (world key slots + world flags),
+  // mapped into all the others with CUDA IPC; reduce_push_kernel stores into them over NVLink
+  bool peer_enabled = true;          // tod_matcher_set_exchange: 0 keeps the ncclAllGather path (A/B runs)
+  bool peer_tried = false;           // the mapping was attempted for the current communicator
+  size_t peer_cap = 0;               // keys per slot
+  size_t peer_half = 0;              // u32 words per parity half: world * peer_cap keys + flags
+  uint32_t *peer_local = nullptr;    // own buffer (cudaMalloc)
+  std::vector<void *> peer_mapped;   // bases of the other ranks' buffers (cudaIpcOpenMemHandle), own rank = peer_local
+  DeviceBuffer d_peer_tbl;           // 2 x world device pointers (one table per parity) | ticket | error word
+  uint32_t peer_step = 0;
 };
 
 namespace {
@@ -115,7 +125,8 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
 
 // Merge (+ radius cut, decode, 3-D gather) and the opt-in post-filters, from n_src key lists per query.
 int finalize(tod_matcher *m, const uint32_t *d_keys, int n_src, int nq, tod_match *d_matches, int32_t *d_counts,
-             float *d_points3d, cudaStream_t st) {
+             float *d_points3d, cudaStream_t st, size_t src_stride = 0, const uint32_t *wait_flags = nullptr,
+             uint32_t wait_step = 0, uint32_t *wait_error = nullptr) {
   const int k = m->p.k;
   const bool ratio = m->p.ratio_enabled != 0 && k >= 2;
   const bool dedupe = m->p.remove_duplicates != 0;
@@ -131,12 +142,14 @@ int finalize(tod_matcher *m, const uint32_t *d_keys, int n_src, int nq, tod_matc
   }
   TOD_CUDA(tod::launch_finalize_matches(d_keys, n_src, nq, k, m->p.radius, m->d_offsets.as<uint32_t>(),
                                         int(m->ids.size()), m->d_pts.as<float>(), d_matches, d_counts, d_points3d, st,
-                                        ratio ? 1 : 0, m->p.ratio, rows));
+                                        ratio ? 1 : 0, m->p.ratio, rows, src_stride, wait_flags, wait_step, wait_error));
   if (dedupe)
     TOD_CUDA(tod::launch_remove_duplicates(d_matches, d_counts, d_points3d, rows, nq, k, m->p.frame_keypoints,
                                            m->d_hkeys.ptr, m->d_hvals.ptr, slots, st));
   return TOD_OK;
 }
+
+int setup_peer_exchange(tod_matcher *m, size_t need_keys, cudaStream_t st);
 
 // The whole DescriptorMatcher.process on device buffers, enqueued on `st`: K1 on this shard, then (sharded) top-k
 // reduction -> ncclAllGather of the packed keys -> merge; or (one shard) merge of the chunk lists directly.
@@ -152,6 +165,27 @@ int run_process(tod_matcher *m, const void *d_query, int nq, tod_match *d_matche
     return fail(TOD_ERR_STATE, "this handle holds shard %d of %d: call tod_matcher_set_comm first (or use the "
                                "*_device stage calls with your own exchange)", m->p.shard_rank, m->p.shard_count);
   const size_t nk = size_t(nq) * k;
+  if (m->peer_enabled && (!m->peer_tried || (m->comm_mode == 2 && nk > m->peer_cap)))
+    if (int rc = setup_peer_exchange(m, nk, st)) return rc;
+  if (m->comm_mode == 2) {
+    // K1 -> [top-k reduction fused with the all-gather: stores into every rank's buffer over NVLink] -> merge, which
+    // starts as soon as every rank's flag has arrived
+    const int world = m->p.shard_count;
+    uint32_t *const *tbl = m->d_peer_tbl.as<uint32_t *>();
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(m->d_peer_tbl.as<uint64_t>() + 2 * world);
+    uint32_t *err = reinterpret_cast<uint32_t *>(m->d_peer_tbl.as<uint64_t>() + 2 * world + 1);
+    if (int rc = run_k1(m, d_query, nq, st, &plan)) return rc;
+    const uint32_t step = ++m->peer_step;
+    const int par = int(step & 1u);
+    const size_t flag_off = size_t(world) * m->peer_cap;
+    if (m->stage_timing) TOD_CUDA(cudaEventRecord(m->ev_x0, st));
+    TOD_CUDA(tod::launch_reduce_push(m->d_partial.as<uint32_t>(), plan.n_sources, nq, k, tbl + size_t(par) * world, world,
+                                     m->p.shard_rank, m->peer_cap, flag_off, step, ticket, st));
+    if (m->stage_timing) TOD_CUDA(cudaEventRecord(m->ev_x1, st));
+    m->ev_x_valid = m->stage_timing;
+    const uint32_t *mine = m->peer_local + size_t(par) * m->peer_half;
+    return finalize(m, mine, world, nq, d_matches, d_counts, d_points3d, st, m->peer_cap, mine + flag_off, step, err);
+  }
   TOD_CUDA(m->d_keys_local.reserve(nk * sizeof(uint32_t)));
   TOD_CUDA(m->d_keys_all.reserve(nk * sizeof(uint32_t) * size_t(m->p.shard_count)));
   if (int rc = run_k1(m, d_query, nq, st, &plan)) return rc;
@@ -163,7 +197,102 @@ int run_process(tod_matcher *m, const void *d_query, int nq, tod_match *d_matche
   return finalize(m, m->d_keys_all.as<uint32_t>(), m->p.shard_count, nq, d_matches, d_counts, d_points3d, st);
 }
 
+void close_peer_exchange(tod_matcher *m) {
+  for (size_t r = 0; r < m->peer_mapped.size(); ++r)
+    if (m->peer_mapped[r] && m->peer_mapped[r] != m->peer_local) cudaIpcCloseMemHandle(m->peer_mapped[r]);
+  m->peer_mapped.clear();
+  if (m->peer_local) cudaFree(m->peer_local);
+  m->peer_local = nullptr;
+  m->peer_cap = m->peer_half = 0;
+  m->peer_step = 0;
+  if (m->comm_mode == 2) m->comm_mode = 1;
+}
+
+// Collective over the ranks of the communicator (every rank reaches it in the same call, with the same nq): allocate
+// the exchange buffer, trade CUDA IPC handles through NCCL, map the peers' buffers.  Any rank that cannot map a peer
+// (no peer access, handles opened inside one process, ...) makes ALL ranks stay on the ncclAllGather path.
+int setup_peer_exchange(tod_matcher *m, size_t need_keys, cudaStream_t st) {
+  const tod::NcclApi &api = tod::nccl_api();
+  const int world = m->p.shard_count, rank = m->p.shard_rank;
+  TOD_CUDA(cudaStreamSynchronize(st));
+  close_peer_exchange(m);
+  m->peer_tried = true;
+  const size_t cap = (std::max(need_keys, size_t(std::max(m->reserved_nq, 0)) * size_t(m->p.k)) + 63) & ~size_t(63);
+  const size_t half = size_t(world) * cap + 64 * ((size_t(world) + 63) / 64);
+  bool ok = world <= 128;
+  void *local = nullptr;
+  if (ok && cudaMalloc(&local, 2 * half * sizeof(uint32_t)) != cudaSuccess) ok = false, local = nullptr, cudaGetLastError();
+  if (local) ok = cudaMemset(local, 0, 2 * half * sizeof(uint32_t)) == cudaSuccess;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok && cudaIpcGetMemHandle(&mine, local) != cudaSuccess) ok = false, cudaGetLastError();
+  // trade {handle, ok} records
+  struct Rec {
+    cudaIpcMemHandle_t h;
+    int32_t ok;
+    int32_t pad[15];
+  };
+  static_assert(sizeof(Rec) == 128, "IPC record");
+  DeviceBuffer d_rec;
+  TOD_CUDA(d_rec.reserve(sizeof(Rec) * size_t(world + 1)));
+  Rec my{};
+  my.h = mine;
+  my.ok = ok ? 1 : 0;
+  std::vector<Rec> all(static_cast<size_t>(world));
+  Rec *d_my = d_rec.as<Rec>() + world;
+  TOD_CUDA(cudaMemcpyAsync(d_my, &my, sizeof(Rec), cudaMemcpyHostToDevice, st));
+  TOD_NCCL(api.AllGather(d_my, d_rec.ptr, sizeof(Rec), tod::kNcclUint8, m->comm, st));
+  TOD_CUDA(cudaMemcpyAsync(all.data(), d_rec.ptr, sizeof(Rec) * size_t(world), cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  for (const Rec &r : all) ok = ok && r.ok == 1;
+  std::vector<void *> mapped(static_cast<size_t>(world), nullptr);
+  if (ok) {
+    for (int r = 0; r < world && ok; ++r) {
+      if (r == rank) {
+        mapped[size_t(r)] = local;
+        continue;
+      }
+      if (cudaIpcOpenMemHandle(&mapped[size_t(r)], all[size_t(r)].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        mapped[size_t(r)] = nullptr;
+        ok = false;
+        cudaGetLastError();
+      }
+    }
+  }
+  // second round: did everybody map everybody?  (also the barrier behind which every buffer is zeroed)
+  my.ok = ok ? 1 : 0;
+  TOD_CUDA(cudaMemcpyAsync(d_my, &my, sizeof(Rec), cudaMemcpyHostToDevice, st));
+  TOD_NCCL(api.AllGather(d_my, d_rec.ptr, sizeof(Rec), tod::kNcclUint8, m->comm, st));
+  TOD_CUDA(cudaMemcpyAsync(all.data(), d_rec.ptr, sizeof(Rec) * size_t(world), cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  d_rec.release();
+  for (const Rec &r : all) ok = ok && r.ok == 1;
+  if (!ok) {
+    for (int r = 0; r < world; ++r)
+      if (mapped[size_t(r)] && r != rank) cudaIpcCloseMemHandle(mapped[size_t(r)]);
+    if (local) cudaFree(local);
+    return TOD_OK;  // stay on NCCL
+  }
+  m->peer_local = static_cast<uint32_t *>(local);
+  m->peer_mapped = mapped;
+  m->peer_cap = cap;
+  m->peer_half = half;
+  m->peer_step = 0;
+  // device table: parity 0 bases, parity 1 bases, then the ticket and the error word
+  std::vector<uint64_t> tbl(size_t(2 * world) + 2, 0ull);
+  for (int par = 0; par < 2; ++par)
+    for (int r = 0; r < world; ++r)
+      tbl[size_t(par * world + r)] = uint64_t(reinterpret_cast<uintptr_t>(static_cast<uint32_t *>(mapped[size_t(r)]) + size_t(par) * half));
+  TOD_CUDA(m->d_peer_tbl.reserve(tbl.size() * 8));
+  TOD_CUDA(cudaMemcpyAsync(m->d_peer_tbl.ptr, tbl.data(), tbl.size() * 8, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  m->comm_mode = 2;
+  return TOD_OK;
+}
+
 void close_comm(tod_matcher *m) {
+  close_peer_exchange(m);
+  m->peer_tried = false;
   // ncclCommDestroy waits for the peer ranks (it hung a run whose ranks closed their handles at different times);
   // the handle's stream is idle here, so the communicator is torn down locally with ncclCommAbort instead.
   if (m->comm) {
@@ -280,7 +409,7 @@ void tod_matcher_destroy(tod_matcher *m) {
   close_comm(m);
   for (DeviceBuffer *b : {&m->d_db, &m->d_pts, &m->d_offsets, &m->d_query, &m->d_partial, &m->d_matches,
                           &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8, &m->d_gthr, &m->d_popq, &m->d_rows,
-                          &m->d_hkeys, &m->d_hvals, &m->d_keys_local, &m->d_keys_all})
+                          &m->d_hkeys, &m->d_hvals, &m->d_keys_local, &m->d_keys_all, &m->d_peer_tbl})
     b->release();
   for (int i = 0; i < tod_matcher::kEvRing; ++i) {
     if (m->ev0[i]) cudaEventDestroy(m->ev0[i]);
@@ -396,6 +525,11 @@ int tod_matcher_knn(tod_matcher *m, const uint8_t *descriptors, int32_t nq, tod_
   if (points3d)
     TOD_CUDA(cudaMemcpyAsync(points3d, m->d_pts3d.ptr, nk * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
   TOD_CUDA(cudaStreamSynchronize(m->stream));
+  if (m->comm_mode == 2) {
+    uint32_t err = 0;
+    TOD_CUDA(cudaMemcpy(&err, m->d_peer_tbl.as<uint64_t>() + 2 * m->p.shard_count + 1, 4, cudaMemcpyDeviceToHost));
+    if (err) return fail(TOD_ERR_STATE, "peer exchange timed out: a rank of the communicator did not deliver its keys");
+  }
   return TOD_OK;
 }
 
@@ -475,6 +609,24 @@ int tod_matcher_set_comm(tod_matcher *m, const void *unique_id) {
   TOD_NCCL(api.CommInitRank(&m->comm, world, id, rank));
   m->comm_mode = 1;
   return TOD_OK;
+}
+
+int tod_matcher_set_exchange(tod_matcher *m, int32_t peer_memory) {
+  TOD_REQUIRE(m, "null argument");
+  if (int rc = use_device(m)) return rc;
+  TOD_CUDA(cudaStreamSynchronize(m->stream));
+  m->peer_enabled = peer_memory != 0;
+  if (!m->peer_enabled) close_peer_exchange(m);
+  m->peer_tried = false;
+  return TOD_OK;
+}
+
+int32_t tod_matcher_exchange_error(const tod_matcher *m) {
+  if (!m || m->comm_mode != 2) return 0;
+  uint32_t err = 0;
+  if (cudaMemcpy(&err, m->d_peer_tbl.as<uint64_t>() + 2 * m->p.shard_count + 1, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  return int32_t(err);
 }
 
 void tod_matcher_set_stage_timing(tod_matcher *m, int32_t on) {
