@@ -340,6 +340,55 @@ def pipeline_leg(args, descs, points, hbm_peak, hbm_src):
             t_g.append(t2 - t1)
             k1.append(m5.last_k1_ms)
             stats = gg.last_stats()
+    # the same two calls as a stream of batches: the matcher of batch i + 1 (GPU-bound) runs on a second host thread
+    # while the guess generator of batch i (host-bound) runs on this one, two sets of pinned buffers
+    streamed = None
+    try:
+        import queue
+        import threading
+        n_batches = 6
+        outs = [out, None]
+        mt2 = torch.empty((nq, K, 4), dtype=torch.int32).pin_memory()
+        ct2 = torch.empty((nq,), dtype=torch.int32).pin_memory()
+        pt2 = torch.empty((nq, K, 3), dtype=torch.float32).pin_memory()
+        outs[1] = {"matches": mt2.numpy().view(capi.MATCH_DTYPE).reshape(nq, K), "counts": ct2.numpy(),
+                   "matches_3d": pt2.numpy()}
+        free_q, full_q = queue.Queue(), queue.Queue()
+        free_q.put(0)
+        free_q.put(1)
+        err = []
+
+        def produce():
+            try:
+                for _ in range(n_batches):
+                    b = free_q.get()
+                    m5.process(q_pin.numpy(), out=outs[b])
+                    full_q.put(b)
+            except Exception as e:          # surfaced by the consumer
+                err.append(e)
+                full_q.put(None)
+
+        th = threading.Thread(target=produce)
+        t0 = time.perf_counter()
+        th.start()
+        n_poses = 0
+        for _ in range(n_batches):
+            b = full_q.get()
+            if b is None:
+                raise err[0]
+            o = outs[b]
+            r = gg.process_batch(kps, clouds, o["matches"], o["counts"], o["matches_3d"], spans, max_poses=64 * n_frames)
+            n_poses += sum(len(x["pose_results"]) for x in r)
+            free_q.put(b)
+        th.join()
+        dt = time.perf_counter() - t0
+        streamed = {"value": n_batches * n_frames / dt, "unit": UNIT, "batches": n_batches,
+                    "ms_per_batch": 1e3 * dt / n_batches, "poses_per_batch": n_poses / n_batches,
+                    "scope": "the same two C-ABI calls on a stream of batches: DescriptorMatcher.process of batch i + 1 on "
+                             "a second host thread while GuessGenerator.process(batch) of batch i runs (two sets of "
+                             "pinned buffers); includes the pipeline fill of the first batch"}
+    except Exception as e:
+        streamed = {"unavailable": str(e)[:200]}
     want = got = 0
     for f, r in zip(frames, res):
         for o_, (R, T) in f["poses"].items():
@@ -357,7 +406,8 @@ def pipeline_leg(args, descs, points, hbm_peak, hbm_src):
            "matcher_ms_per_batch": 1e3 * tm, "guess_ms_per_batch": 1e3 * tg,
            "h2d_bytes_per_step": int(nq * 32), "d2h_bytes_per_step": int(nq * K * 16 + nq * 4 + nq * K * 12),
            "poses_found": int(sum(len(r["pose_results"]) for r in res)), "planted_objects": want,
-           "planted_recovered": got, "matches_per_frame": float(out["counts"].sum()) / n_frames}
+           "planted_recovered": got, "matches_per_frame": float(out["counts"].sum()) / n_frames,
+           "streamed": streamed}
     stages = {"k1": {"kernel_ms": k1_ms, "gcmp_per_s": nq * float(m5.num_descriptors) / (k1_ms * 1e-3) / 1e9},
               "k2": hbm_roofline("k2_adjacency_kernel", stats["k2_bytes"], stats["k2_ms"], hbm_peak, hbm_src,
                                  {"clusters": stats["n_clusters"], "correspondences": stats["n_correspondences"]}),
@@ -409,11 +459,13 @@ def feature_leg(args):
     K = np.array([[1050.0, 0, 639.5], [0, 1050.0, 479.5], [0, 0, 1]], np.float32)
     fd = FeatureDescriptor(n_features=nf)
     t_orb, t_d3 = [], []
+    import torch
+    cloud = torch.empty((h, w, 3), dtype=torch.float32).pin_memory().numpy()   # a frame loop reuses one pinned cloud
     for _ in range(6):
         t0 = time.perf_counter()
         kp, desc = fd.process(img)
         t1 = time.perf_counter()
-        depth_to_3d(zf, K)
+        depth_to_3d(zf, K, out=cloud)
         t2 = time.perf_counter()
         t_orb.append(t1 - t0)
         t_d3.append(t2 - t1)
@@ -422,7 +474,7 @@ def feature_leg(args):
            "orb_ms_per_frame": 1e3 * float(np.median(t_orb[1:])), "keypoints": int(kp.shape[0]),
            "depth_to_3d_ms_per_frame": 1e3 * float(np.median(t_d3[1:])),
            "scope": "tod_orb_detect_and_compute / tod_depth_to_3d with host buffers (H2D of the frame, D2H of keypoints, "
-                    "descriptors and the point image inside)"}
+                    "descriptors and the point image inside; the 14.7 MB point image lands in a pinned buffer)"}
     try:
         import cv2
         orb = cv2.ORB_create(nf, 1.2, 3)
@@ -608,6 +660,10 @@ def run_ours(args):
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_done = [torch.cuda.Event() for _ in range(2)]
         ev_out = [torch.cuda.Event() for _ in range(2)]
+        q_lo = (args.frames * rank // world) * args.keypoints
+        q_hi = (args.frames * (rank + 1) // world) * args.keypoints
+        own = slice(q_lo, q_hi)
+        last = [0]
 
         def e2e_run(n_steps):
             for i in range(n_steps):
@@ -621,12 +677,16 @@ def run_ours(args):
                 m.process_device(qd[b].data_ptr(), nqt, mt[b].data_ptr(), ct[b].data_ptr(), pt[b].data_ptr(), sptr)
                 ev_done[b].record(stream)
                 with torch.cuda.stream(s_out):
+                    # every rank holds the complete result in HBM; its host reads back the frames it owns (the guess
+                    # generator of a frame runs on one rank) — together the ranks deliver every frame's matches once
                     s_out.wait_event(ev_done[b])
-                    m_host.copy_(mt[b], non_blocking=True)
-                    c_host.copy_(ct[b], non_blocking=True)
-                    p_host.copy_(pt[b], non_blocking=True)
+                    m_host[own].copy_(mt[b][own], non_blocking=True)
+                    c_host[own].copy_(ct[b][own], non_blocking=True)
+                    p_host[own].copy_(pt[b][own], non_blocking=True)
                     ev_out[b].record(s_out)
             torch.cuda.synchronize()
+            if n_steps:                                   # outside the timed region's per-step work: nothing
+                last[0] = (n_steps - 1) & 1
     else:
         def e2e_run(n_steps):
             for _ in range(n_steps):
@@ -645,9 +705,16 @@ def run_ours(args):
     e2e_s = float(t.item())
     e2e_value = frames_total / e2e_s
     trace("e2e done: %.1f frames/s" % e2e_value)
-    h2d = nqt * 32
-    d2h = nqt * k * 16 + nqt * 4 + nqt * k * 12
+    h2d = nqt * 32 * world                      # the queries are replicated: every rank uploads all of them
+    d2h = nqt * k * 16 + nqt * 4 + nqt * k * 12   # every frame's result is read back once (by the rank that owns it)
     comm_mode = m.comm_mode
+    if world > 1:
+        # for the checks below: the complete result of the last timed step, read back after the timed region
+        b = last[0]
+        m_host.copy_(mt[b])
+        c_host.copy_(ct[b])
+        p_host.copy_(pt[b])
+        torch.cuda.synchronize()
 
     # ---- the sharded reference-facing call itself (tod_matcher_knn, host buffers) must agree with the streamed result
     if world > 1:
@@ -753,8 +820,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "scope": ("DescriptorMatcher.process through the C-ABI (tod_matcher_knn) with pinned host buffers"
                               if world == 1 else
-                              "tod_matcher_knn_device per step (K1 + in-library ncclAllGather + merge), pinned host "
-                              "buffers, copies of step i+1 / i-1 overlapped with the compute of step i")},
+                              "tod_matcher_knn_device per step (K1 + in-library exchange + merge), pinned host buffers: "
+                              "every rank uploads the whole query batch and reads back the results of the frames it "
+                              "owns; copies of step i+1 / i-1 overlapped with the compute of step i")},
             "parity": parity,
             "collective": (None if world == 1 else
                            {"where": ("inside libtod_b200.so: the top-k reduction kernel stores every rank's packed keys "

@@ -605,8 +605,12 @@ int tod_guess_create(const tod_guess_params *p, tod_guess **out) {
   TOD_CUDA(cudaSetDevice(p->device));
   tod_guess *g = new tod_guess();
   g->p = *p;
-  cudaError_t ce = cudaStreamCreate(&g->stream);
-  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking);
+  // highest stream priority: the guess generator's kernels are short and the host waits for each of them; when a
+  // matcher call of the next batch occupies the GPU (K1: thousands of long CTAs) they must not queue behind it
+  int prio_lo = 0, prio_hi = 0;
+  cudaError_t ce = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithPriority(&g->stream, cudaStreamDefault, prio_hi);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithPriority(&g->copy_stream, cudaStreamNonBlocking, prio_hi);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&g->ev_k2, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&g->ev_S, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&g->ev_P, cudaEventDisableTiming);

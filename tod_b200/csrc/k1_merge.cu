@@ -82,9 +82,11 @@ reduce_push_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, uint32_
       for (int i = 0; i < K; ++i) dst[i] = best[i];
     }
   }
-  __threadfence_system();   // this thread's peer stores are visible system-wide before the block takes its ticket
+  // the CTA barrier orders every thread's peer stores before thread 0's system-scope fence (cumulativity), which
+  // publishes them before the block takes its ticket — one fence per block instead of one per thread
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned int t = atomicAdd(ticket, 1u);
     if (t == gridDim.x - 1) {
       *ticket = 0u;

@@ -958,7 +958,28 @@ int tod_depth_to_3d(int32_t device, const void *depth, int32_t depth_is_u16, int
   TOD_REQUIRE(device >= 0 && device < n_dev, "device %d out of range", device);
   TOD_CUDA(cudaSetDevice(device));
   const size_t px = size_t(height) * size_t(width), in_bytes = px * (depth_is_u16 ? 2 : 4);
-  DeviceBuffer d_in, d_out;
+  // the device buffers of a calling thread are kept between calls (a frame loop calls this once per frame: no
+  // cudaMalloc / cudaFree per frame); a pinned `points3d` makes the 12-byte-per-pixel read-back run at PCIe speed
+  struct Cache {
+    int device = -1;
+    DeviceBuffer d_in, d_out;
+    ~Cache() {
+      if (device >= 0 && cudaSetDevice(device) == cudaSuccess) {
+        d_in.release();
+        d_out.release();
+      }
+    }
+  };
+  static thread_local Cache cache;
+  if (cache.device != device) {
+    if (cache.device >= 0 && cudaSetDevice(cache.device) == cudaSuccess) {
+      cache.d_in.release();
+      cache.d_out.release();
+    }
+    TOD_CUDA(cudaSetDevice(device));
+    cache.device = device;
+  }
+  DeviceBuffer &d_in = cache.d_in, &d_out = cache.d_out;
   TOD_CUDA(d_in.reserve(in_bytes));
   TOD_CUDA(d_out.reserve(px * 12));
   TOD_CUDA(cudaMemcpy(d_in.ptr, depth, in_bytes, cudaMemcpyHostToDevice));
@@ -972,8 +993,6 @@ int tod_depth_to_3d(int32_t device, const void *depth, int32_t depth_is_u16, int
   tod::count_launch();
   cudaError_t ce = cudaGetLastError();
   if (ce == cudaSuccess) ce = cudaMemcpy(points3d, d_out.ptr, px * 12, cudaMemcpyDeviceToHost);
-  d_in.release();
-  d_out.release();
   if (ce != cudaSuccess) return fail(TOD_ERR_CUDA, "depth -> 3-D failed: %s", cudaGetErrorString(ce));
   return TOD_OK;
 }
