@@ -81,3 +81,31 @@ def test_c5_full_size_objects_against_compiled_reference():
     assert len(exp) >= n_ref
     sel = [i for i, p in enumerate(res["pose_results"]) if int(p["object_index"]) < n_ref]
     compare([res["pose_results"][i] for i in sel], [res["inliers"][i] for i in sel], exp)
+
+
+def test_c1_frame_against_compiled_reference():
+    """BASELINE config C1 (the reference's own CPU-runnable case): one 640x480 frame, one object of 5000 descriptors,
+    5000 keypoints, the .ork parameters.  One frame-filling cluster of ~3500 correspondences: its filtered graph is
+    far above K4's proof limit (kGateProofMax) and K5's 256 vertices, so the gate is decided by the host search on a
+    view of the cluster's own bit-rows — same pose and inlier set as the reference's own code."""
+    descs, points = synth.make_db(1, 5000, seed=synth.BASE_SEED)
+    fr = synth.make_frame(descs, points, [0], 5000, seed=synth.BASE_SEED + 9)
+    m = DescriptorMatcher(search_json_params='{"type": "LSH", "key_size": 16, "multi_probe_level": 1, "n_tables": 10, '
+                                             '"radius": 35, "ratio": 0.8}')
+    m.add_object("object_0", descs[0], points[0])
+    m.train()
+    out = m.process(fr["descriptors"])
+    spans = m.spans_by_index
+    hist = m.k1_ms_history(1)
+    assert len(hist) == 1 and hist[0] > 0 and abs(hist[0] - m.last_k1_ms) < 1e-6     # the K1 event ring
+    m.close()
+    assert int(out["counts"].sum()) > 3000
+    gg = GuessGenerator(min_inliers=8, n_ransac_iterations=2500, sensor_error=0.01, seed=5)
+    got = gg.process(fr["keypoints_xy"], fr["cloud"], out["matches"], out["counts"], out["matches_3d"], spans)
+    st = gg.last_stats()
+    gg.close()
+    exp = ref.process(fr["keypoints_xy"], fr["cloud"], out["matches"], out["counts"], out["matches_3d"], spans, 8, 2500,
+                      0.01, seed=5)
+    assert len(exp) >= 1
+    compare(got["pose_results"], got["inliers"], exp)
+    assert st["gate_shape"]["k4_undecided_used"] >= 1 and st["gate_shape"]["k5_passes_used"] == 0

@@ -351,25 +351,29 @@ def test_sharded_db_merge_equals_unsharded(world, kernel):
         h.close()
 
 
-def test_maximum_db_size_and_limit():
-    """The packed key addresses 2^23 rows: a DB of exactly that size works (bit-exact on planted and random queries,
-    first / last rows included), one more row is refused with TOD_ERR_LIMIT."""
-    rng = np.random.default_rng(99)
-    n_obj, rows = 32, 262144                                   # 32 x 2^18 = 2^23 descriptors (268 MB packed)
+def _big_db(n_obj, rows, seed):
+    """n_obj objects of `rows` descriptors that differ from one another in byte 0 only (plus a random last byte)."""
+    rng = np.random.default_rng(seed)
     base = rng.integers(0, 256, (rows, 32), dtype=np.uint8)
     pts = rng.random((rows, 3)).astype(np.float32)
-    m = DescriptorMatcher(k=2, radius=0)
     descs = []
     for o in range(n_obj):
         d = base.copy()
         d[:, 0] ^= np.uint8(o)                                 # objects differ in a few bits of byte 0
         d[:, 31] = rng.integers(0, 256, rows, dtype=np.uint8)
         descs.append(d)
-        m.add_object("o%d" % o, d, pts)
+    return descs, pts, rng
+
+
+def test_one_segment_database_2_pow_23_rows():
+    """2^23 rows — the most one packed key addresses — in one segment: bit-exact on planted and random queries, first
+    and last rows included."""
+    n_obj, rows = 32, 262144                                   # 32 x 2^18 = 2^23 descriptors (268 MB packed)
+    descs, pts, rng = _big_db(n_obj, rows, 99)
+    m = DescriptorMatcher(k=2, radius=0)
+    for o in range(n_obj):
+        m.add_object("o%d" % o, descs[o], pts)
     assert m.num_descriptors == 1 << 23
-    with pytest.raises(capi.TodError) as e:
-        m.add_object("one_too_many", base[:1], pts[:1])
-    assert e.value.code == capi.TOD_ERR_LIMIT
     m.train()
     # queries: exact copies of chosen rows (first row of the DB, last row of the DB, random ones) + random clutter
     picks = [(0, 0), (n_obj - 1, rows - 1)] + [(int(rng.integers(0, n_obj)), int(rng.integers(0, rows)))
@@ -383,4 +387,47 @@ def test_maximum_db_size_and_limit():
         assert out["matches"]["distance"][i, 0] == 0
         # the same row of a lower-numbered object can tie at distance 0 only if byte 0 and 31 agree; the oracle decides
         assert (int(out["matches"]["imgIdx"][i, 0]), int(out["matches"]["trainIdx"][i, 0])) <= (o, r)
+    m.close()
+
+
+@pytest.mark.parametrize("kernel", ["mma", "popc"])
+def test_wide_database_is_scanned_in_segments(kernel):
+    """More than 2^23 rows: the shard is scanned in segments of 2^23 rows whose keys are local to the segment, and the
+    merge orders (distance, global row) on 64 bits.  33 x 2^18 rows = two segments; queries planted on both sides of
+    the boundary (its last and first rows included), and an object copied into BOTH segments so that equal distances
+    meet across the boundary: cv::BFMatcher's order — the lower imgIdx first — must hold, bit for bit vs the oracle."""
+    n_obj, rows = 33, 262144
+    descs, pts, rng = _big_db(n_obj, rows, 100)
+    descs[32] = descs[3].copy()                                # object 32 (second segment) == object 3 (first segment)
+    m = DescriptorMatcher(k=3, radius=0, kernel=capi.TOD_KERNEL_MMA if kernel == "mma" else capi.TOD_KERNEL_POPC)
+    for o in range(n_obj):
+        m.add_object("o%d" % o, descs[o], pts)
+    assert m.num_descriptors == (1 << 23) + rows
+    m.train()
+    picks = [(0, 0), (31, rows - 1), (32, 0), (32, rows - 1), (3, 77), (32, 77)] + \
+            [(int(rng.integers(0, n_obj)), int(rng.integers(0, rows))) for _ in range(26)]
+    nq = 64 if kernel == "mma" else 40
+    q = np.stack([descs[o][r] for o, r in picks] + [rng.integers(0, 256, 32, dtype=np.uint8)
+                                                    for _ in range(nq - len(picks))])
+    q[8, 5] ^= np.uint8(3)                                     # a near copy: distance 2 to its source row
+    out = m.process(q)
+    assert m.last_kernel == kernel
+    em, ec = hk.knn_c(q, descs, 3, 0)
+    assert_matches_equal(out["matches"], out["counts"], em["trainIdx"], em["imgIdx"], em["distance"], ec)
+    e3 = hk.gather_points3d(em, ec, [pts] * n_obj)
+    assert (out["matches_3d"] == e3).all()
+    # the twin objects: the copy of row 77 is found in object 3 first, then in object 32, both at distance 0
+    for i in (4, 5):
+        assert list(out["matches"]["imgIdx"][i, :2]) == [3, 32] and list(out["matches"]["trainIdx"][i, :2]) == [77, 77]
+        assert list(out["matches"]["distance"][i, :2]) == [0, 0]
+    # a second call with a radius and fewer queries (ragged), same handle
+    out2 = m.process(q[:17])
+    assert_matches_equal(out2["matches"], out2["counts"], em["trainIdx"][:17], em["imgIdx"][:17], em["distance"][:17],
+                         ec[:17])
+    # the stage calls carry 32-bit global keys: refused on a wide database
+    import torch
+    keys = torch.empty((17, 3), dtype=torch.int32, device="cuda")
+    with pytest.raises(capi.TodError) as e:
+        m.knn_keys_device(torch.from_numpy(q[:17]).cuda().data_ptr(), 17, keys.data_ptr())
+    assert e.value.code == capi.TOD_ERR_LIMIT
     m.close()

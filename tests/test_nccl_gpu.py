@@ -114,3 +114,57 @@ def test_sharded_matcher_with_in_library_nccl(tmp_path, k, radius):
     print("exchange modes per pass:", [int(x) for x in res[0][3:6]])
     descs, _, _ = _workload()
     assert sum(int(r[2]) for r in res) == sum(d.shape[0] for d in descs)
+
+
+def _rank_main_wide(rank, world, uid, out_dir):
+    """A database of more than 2^23 rows over `world` GPUs: keys are local to their shard's segment, the exchange
+    carries them as they are and the merge orders (distance, global row) on 64 bits."""
+    sys.path.insert(0, ROOT)
+    import torch
+    from oracle import hamming_knn as hk
+    from tod_b200 import DescriptorMatcher
+    torch.cuda.set_device(rank)
+    rng = np.random.default_rng(5)
+    n_obj, rows = 33, 262144                                    # 2^23 + 2^18 rows
+    base = rng.integers(0, 256, (rows, 32), dtype=np.uint8)
+    pts = rng.random((rows, 3)).astype(np.float32)
+    descs = []
+    for o in range(n_obj):
+        d = base.copy()
+        d[:, 0] ^= np.uint8(o)
+        d[:, 31] = rng.integers(0, 256, rows, dtype=np.uint8)
+        descs.append(d)
+    descs[32] = descs[3].copy()                                 # twins in the first and the last shard: ties across ranks
+    m = DescriptorMatcher(k=3, radius=0, device=rank, shard_rank=rank, shard_count=world)
+    for o in range(n_obj):
+        m.add_object("o%d" % o, descs[o], pts)
+    m.train()
+    m.set_comm(uid)
+    picks = [(0, 0), (32, rows - 1), (3, 77), (32, 77), (16, rows // 2)] + \
+            [(int(rng.integers(0, n_obj)), int(rng.integers(0, rows))) for _ in range(27)]
+    q = np.stack([descs[o][r] for o, r in picks] + [rng.integers(0, 256, 32, dtype=np.uint8) for _ in range(32)])
+    ok = True
+    for rep in range(2):
+        out = m.process(q)
+        em, ec = hk.knn_c(q, descs, 3, 0)
+        same = (out["counts"] == ec).all()
+        for f in ("trainIdx", "imgIdx", "distance"):
+            same = same and (out["matches"][f] == em[f]).all()
+        same = same and (out["matches_3d"] == hk.gather_points3d(em, ec, [pts] * n_obj)).all()
+        same = same and list(out["matches"]["imgIdx"][2, :2]) == [3, 32]
+        ok = ok and bool(same)
+    np.save(os.path.join(out_dir, "wide_%d.npy" % rank), np.array([int(ok), m.comm_mode, m.shard_rows]))
+    m.close()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_sharded_wide_database(tmp_path):
+    import torch.multiprocessing as mp
+    from tod_b200 import comm_unique_id
+    world = 2
+    uid = comm_unique_id()
+    mp.spawn(_rank_main_wide, args=(world, uid, str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(os.path.join(str(tmp_path), "wide_%d.npy" % r)) for r in range(world)]
+    assert all(int(r[0]) == 1 for r in res), res
+    assert all(int(r[1]) == 1 for r in res)                      # wide databases use the ncclAllGather exchange
+    assert sum(int(r[2]) for r in res) == (1 << 23) + 262144

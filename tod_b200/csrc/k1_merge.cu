@@ -10,14 +10,14 @@
 namespace tod {
 namespace {
 
-template <int K>
-__device__ __forceinline__ void topk_insert(uint32_t (&best)[K], uint32_t key) {
+template <int K, typename T>
+__device__ __forceinline__ void topk_insert(T (&best)[K], T key) {
   if (key < best[K - 1]) {
     best[K - 1] = key;
 #pragma unroll
     for (int i = K - 1; i > 0; --i) {
-      const uint32_t lo = min(best[i - 1], best[i]);
-      const uint32_t hi = max(best[i - 1], best[i]);
+      const T lo = min(best[i - 1], best[i]);
+      const T hi = max(best[i - 1], best[i]);
       best[i - 1] = lo;
       best[i] = hi;
     }
@@ -38,7 +38,31 @@ __device__ __forceinline__ void reduce_query(const uint32_t *__restrict__ keys, 
     for (int i = 0; i < K; ++i) {
       const uint32_t key = kPeerWritten ? __ldcg(p + i) : __ldg(p + i);
       if (key >= best[K - 1]) break;  // source lists are ascending
-      topk_insert<K>(best, key);
+      topk_insert<K, uint32_t>(best, key);
+    }
+  }
+}
+
+// Wide databases (more than 2^23 rows): the 23 row bits of a key count from the start of its source's row range
+// (a segment of a shard), src_base[s] = first global row of source s.  Sources are ascending, disjoint row ranges, so
+// (distance, global row) — cv::BFMatcher's order — is compared on 64-bit keys: distance << 32 | global row.
+constexpr unsigned long long kKeyEmpty64 = ~0ull;
+template <int K>
+__device__ __forceinline__ void reduce_query_wide(const uint32_t *__restrict__ keys, int n_src, size_t src_stride,
+                                                  const uint32_t *__restrict__ src_base, int q,
+                                                  unsigned long long (&best)[K]) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) best[i] = kKeyEmpty64;
+  for (int s = 0; s < n_src; ++s) {
+    const uint32_t *p = keys + size_t(s) * src_stride + size_t(q) * K;
+    const unsigned long long base = __ldg(src_base + s);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const uint32_t k32 = __ldg(p + i);
+      if (k32 == kKeyEmpty) break;
+      const unsigned long long key = ((unsigned long long)(k32 >> kKeyRowBits) << 32) | (base + (k32 & kKeyRowMask));
+      if (key >= best[K - 1]) break;  // source lists are ascending
+      topk_insert<K, unsigned long long>(best, key);
     }
   }
 }
@@ -96,14 +120,14 @@ reduce_push_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, uint32_
   }
 }
 
-template <int K>
+template <int K, bool kWide>
 __global__ void __launch_bounds__(128)
 finalize_matches_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, uint32_t radius,
                         const uint32_t *__restrict__ obj_offsets, int n_objects, const float *__restrict__ points,
                         tod_match *__restrict__ matches, int32_t *__restrict__ counts,
                         float *__restrict__ points3d, int ratio_enabled, float ratio, uint32_t *__restrict__ rows_out,
                         size_t src_stride, const uint32_t *__restrict__ wait_flags, uint32_t wait_step,
-                        uint32_t *__restrict__ wait_error) {
+                        uint32_t *__restrict__ wait_error, const uint32_t *__restrict__ src_base) {
   if (wait_flags) {
     // peer exchange: list s was pushed by rank s; its flag reaches wait_step once all of it is visible here.  Bounded
     // wait (~4 s): a rank that never arrives must not hang the GPU — the error word is reported by the next call.
@@ -121,30 +145,46 @@ finalize_matches_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, ui
   }
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
-  uint32_t best[K];
-  if (wait_flags) reduce_query<K, true>(keys, n_src, src_stride, q, best);
-  else reduce_query<K>(keys, n_src, src_stride, q, best);
+  // (distance, global row) of the K nearest, ascending; empty slots have distance 0xFFFFFFFF
+  uint32_t dist_of[K], row_of[K];
+  if (kWide) {
+    unsigned long long best[K];
+    reduce_query_wide<K>(keys, n_src, src_stride, src_base, q, best);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      dist_of[i] = uint32_t(best[i] >> 32);
+      row_of[i] = uint32_t(best[i]);
+    }
+  } else {
+    uint32_t best[K];
+    if (wait_flags) reduce_query<K, true>(keys, n_src, src_stride, q, best);
+    else reduce_query<K>(keys, n_src, src_stride, q, best);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      dist_of[i] = best[i] == kKeyEmpty ? 0xFFFFFFFFu : best[i] >> kKeyRowBits;
+      row_of[i] = best[i] & kKeyRowMask;
+    }
+  }
   if (ratio_enabled && K >= 2) {
     // the ratio-test TODO of DescriptorMatcher.cpp:223-227 as Lowe's test on the two nearest neighbours (before the
     // radius cut): keep the best match only, and only if distance0 < ratio * distance1
-    if (best[0] != kKeyEmpty && best[K >= 2 ? 1 : 0] != kKeyEmpty) {
-      const float d0 = float(best[0] >> kKeyRowBits), d1 = float(best[K >= 2 ? 1 : 0] >> kKeyRowBits);
-      if (!(d0 < __fmul_rn(ratio, d1))) best[0] = kKeyEmpty;
+    if (dist_of[0] != 0xFFFFFFFFu && dist_of[K >= 2 ? 1 : 0] != 0xFFFFFFFFu) {
+      const float d0 = float(dist_of[0]), d1 = float(dist_of[K >= 2 ? 1 : 0]);
+      if (!(d0 < __fmul_rn(ratio, d1))) dist_of[0] = 0xFFFFFFFFu;
     }
 #pragma unroll
-    for (int i = 1; i < K; ++i) best[i] = kKeyEmpty;
+    for (int i = 1; i < K; ++i) dist_of[i] = 0xFFFFFFFFu;
   }
   int n = 0;
 #pragma unroll
   for (int i = 0; i < K; ++i) {
-    const uint32_t key = best[i];
-    const uint32_t dist = key >> kKeyRowBits;
+    const uint32_t dist = dist_of[i];
     // ascending list: the first empty slot or the first distance > radius ends it (DescriptorMatcher.cpp:215-219)
-    const bool keep = (n == i) && key != kKeyEmpty && (radius == 0 || dist <= radius);
+    const bool keep = (n == i) && dist != 0xFFFFFFFFu && (radius == 0 || dist <= radius);
     tod_match m;
     float px = 0.f, py = 0.f, pz = 0.f;
     if (keep) {
-      const uint32_t row = key & kKeyRowMask;
+      const uint32_t row = row_of[i];
       int lo = 0, hi = n_objects;  // largest o with obj_offsets[o] <= row
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -164,7 +204,7 @@ finalize_matches_kernel(const uint32_t *__restrict__ keys, int n_src, int nq, ui
       m.queryIdx = -1; m.trainIdx = -1; m.imgIdx = -1; m.distance = 0.f;
     }
     matches[size_t(q) * K + i] = m;
-    if (rows_out) rows_out[size_t(q) * K + i] = keep ? (key & kKeyRowMask) : 0xFFFFFFFFu;
+    if (rows_out) rows_out[size_t(q) * K + i] = keep ? row_of[i] : 0xFFFFFFFFu;
     if (points3d) {
       float *o = points3d + (size_t(q) * K + i) * 3;
       o[0] = px; o[1] = py; o[2] = pz;
@@ -290,15 +330,21 @@ cudaError_t launch_finalize_matches(const uint32_t *d_keys, int n_src, int nq, i
                                     tod_match *d_matches, int32_t *d_counts, float *d_points3d,
                                     cudaStream_t stream, int ratio_enabled, float ratio, uint32_t *d_rows_out,
                                     size_t src_stride, const uint32_t *d_wait_flags, uint32_t wait_step,
-                                    uint32_t *d_wait_error) {
+                                    uint32_t *d_wait_error, const uint32_t *d_src_base) {
   if (nq <= 0) return cudaSuccess;
-  if (d_wait_flags && n_src > 128) return cudaErrorInvalidValue;
+  if (d_wait_flags && (n_src > 128 || d_src_base)) return cudaErrorInvalidValue;
   if (src_stride == 0) src_stride = size_t(nq) * size_t(k);
   const int blocks = (nq + 127) / 128;
-  TOD_DISPATCH_K(k, (finalize_matches_kernel<K><<<blocks, 128, 0, stream>>>(
-                        d_keys, n_src, nq, radius, d_obj_offsets, n_objects, d_points, d_matches, d_counts,
-                        d_points3d, ratio_enabled, ratio, d_rows_out, src_stride, d_wait_flags, wait_step,
-                        d_wait_error)));
+  if (d_src_base) {
+    TOD_DISPATCH_K(k, (finalize_matches_kernel<K, true><<<blocks, 128, 0, stream>>>(
+                          d_keys, n_src, nq, radius, d_obj_offsets, n_objects, d_points, d_matches, d_counts,
+                          d_points3d, ratio_enabled, ratio, d_rows_out, src_stride, nullptr, 0u, nullptr, d_src_base)));
+  } else {
+    TOD_DISPATCH_K(k, (finalize_matches_kernel<K, false><<<blocks, 128, 0, stream>>>(
+                          d_keys, n_src, nq, radius, d_obj_offsets, n_objects, d_points, d_matches, d_counts,
+                          d_points3d, ratio_enabled, ratio, d_rows_out, src_stride, d_wait_flags, wait_step,
+                          d_wait_error, nullptr)));
+  }
   count_launch();
   return cudaGetLastError();
 }

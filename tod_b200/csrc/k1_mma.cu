@@ -341,7 +341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsMma, 1)
 __global__ void __launch_bounds__(kThreadsMma, 1)
 #endif
 k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, int nq,
-              int shard_rows, uint32_t global_row_base, int rows_per_chunk, int n_chunks, int full_units,
+              int shard_rows, int seg_row0, uint32_t global_row_base, int rows_per_chunk, int n_chunks, int full_units,
               int n_sources, uint32_t thr_init, int K, uint32_t *__restrict__ partial, uint32_t *__restrict__ gthr, const uint32_t *__restrict__ popq
 #if TOD_K1_STATS
               , int debug_mode   // ablation knobs of the instrumented build only (tools/k1_stats.py)
@@ -440,7 +440,7 @@ k1_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const uint32_t full_addr = mapa_u32(ptx::smem_u32(&b_full[s]), 0);
         for (int kh = 0; kh < 2; ++kh)
           tma_load_2d_pair(b_smem + s * kBHalfBytes + kh * (kHalfN * kSwizzleBytes), &map_db, kh * kSwizzleBytes,
-                           row0 + t * kBlockN + int(rank) * kHalfN, full_addr);
+                           seg_row0 + row0 + t * kBlockN + int(rank) * kHalfN, full_addr);
       }
 #if TOD_K1_STATS
       atomicAdd(&g_k1_stats[9], st_a);
@@ -801,7 +801,7 @@ size_t tensor_map_bytes() { return sizeof(CUtensorMap); }
 
 cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
-                          const uint32_t *d_popq, cudaStream_t stream) {
+                          const uint32_t *d_popq, cudaStream_t stream, int64_t seg_row0) {
   if (k < 1 || k > TOD_MAX_K) return cudaErrorInvalidValue;
   const uint32_t thr_init = radius ? min(radius + 1u, 511u) : 511u;
   {  // per device and per context, so not cached in a static: a process may hold handles on several GPUs
@@ -818,7 +818,7 @@ cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map
   dim3 grid(unsigned(plan.full_qtiles) + unsigned(plan.n_qtiles - plan.full_qtiles) * unsigned(plan.n_chunks));
   k1_mma_kernel<<<grid, kThreadsMma, kSmemMma, stream>>>(*static_cast<const CUtensorMap *>(map_q),
                                                          *static_cast<const CUtensorMap *>(map_db), nq, int(shard_rows),
-                                                         global_row_base, plan.rows_per_chunk, plan.n_chunks,
+                                                         int(seg_row0), global_row_base, plan.rows_per_chunk, plan.n_chunks,
                                                          plan.full_qtiles / kCtas, plan.n_sources, thr_init, k, d_partial,
                                                          d_gthr, d_popq
 #if TOD_K1_STATS

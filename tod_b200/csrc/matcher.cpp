@@ -51,6 +51,11 @@ struct tod_matcher {
   bool ev_x_valid = false;
   bool stage_timing = false;         // tod_matcher_set_stage_timing: also bracket the exchange with events
   int32_t reserved_nq = 0;
+  // wide database (more than 2^23 rows in all): the shard is scanned in segments of 2^23 rows, keys count rows from
+  // their segment's start, and the merge orders (distance, global row) on 64 bits with the table d_src_base
+  bool wide = false;
+  int n_seg = 1;                     // segments per shard (the same on every rank)
+  DeviceBuffer d_src_base;           // shard_count x n_seg first global rows
   // peer-memory exchange (comm_mode 2): every rank owns one buffer of 2 parities x (world key slots + world flags),
   // mapped into all the others with CUDA IPC; reduce_push_kernel stores into them over NVLink
   bool peer_enabled = true;          // tod_matcher_set_exchange: 0 keeps the ncclAllGather path (A/B runs)
@@ -76,10 +81,15 @@ bool use_mma(const tod_matcher *m) {
   return m->p.kernel == TOD_KERNEL_MMA || (m->p.kernel == TOD_KERNEL_AUTO && m->shard_rows > 0);
 }
 
-int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1Plan *plan_out) {
+// K1 on rows [seg_row0, seg_row0 + seg_rows) of this shard; keys = distance << 23 | (key_base + row - seg_row0).
+// The whole shard with key_base = shard_begin unless the database is wide.  first / last: the first launch of a call
+// expands the queries (and resets their shared bounds, which later segments then start from), first and last bracket
+// the call's K1 time.
+int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1Plan *plan_out, int64_t seg_row0,
+           int64_t seg_rows, uint32_t key_base, bool first, bool last) {
   if (use_mma(m)) {
     if (!m->have_db8) return fail(TOD_ERR_STATE, "tensor-core K1 requested but the int8 database was not built");
-    tod::K1Plan plan = tod::k1_mma_plan(nq, m->shard_rows, m->sm_count);
+    tod::K1Plan plan = tod::k1_mma_plan(nq, seg_rows, m->sm_count);
     TOD_CUDA(m->d_partial.reserve(size_t(plan.n_sources) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
     TOD_CUDA(m->d_q8.reserve(size_t(nq) * 256));
     if (m->map_q_ptr != m->d_q8.ptr || m->map_q_rows != nq) {
@@ -90,30 +100,39 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
     }
     TOD_CUDA(m->d_gthr.reserve(size_t(nq) * sizeof(uint32_t)));
     TOD_CUDA(m->d_popq.reserve(size_t(nq) * sizeof(uint32_t)));
-    TOD_CUDA(tod::launch_expand_queries(d_query, m->d_q8.ptr, nq, m->d_popq.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
-                                        st));
+    if (first)
+      TOD_CUDA(tod::launch_expand_queries(d_query, m->d_q8.ptr, nq, m->d_popq.as<uint32_t>(),
+                                          m->d_gthr.as<uint32_t>(), st));
     const int er = int(m->k1_calls % tod_matcher::kEvRing);
-    TOD_CUDA(cudaEventRecord(m->ev0[er], st));
-    TOD_CUDA(tod::launch_k1_mma(plan, m->map_q, m->map_db, nq, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
-                                m->p.radius, m->d_partial.as<uint32_t>(), m->d_gthr.as<uint32_t>(),
-                                m->d_popq.as<uint32_t>(), st));
-    TOD_CUDA(cudaEventRecord(m->ev1[er], st));
-    ++m->k1_calls;
+    if (first) TOD_CUDA(cudaEventRecord(m->ev0[er], st));
+    TOD_CUDA(tod::launch_k1_mma(plan, m->map_q, m->map_db, nq, seg_rows, key_base, m->p.k, m->p.radius,
+                                m->d_partial.as<uint32_t>(), m->d_gthr.as<uint32_t>(), m->d_popq.as<uint32_t>(), st,
+                                seg_row0));
+    if (last) {
+      TOD_CUDA(cudaEventRecord(m->ev1[er], st));
+      ++m->k1_calls;
+    }
     m->last_kernel = "mma";
     *plan_out = plan;
     return TOD_OK;
   }
-  tod::K1Plan plan = tod::k1_popc_plan(nq, m->shard_rows, m->sm_count);
+  tod::K1Plan plan = tod::k1_popc_plan(nq, seg_rows, m->sm_count);
   TOD_CUDA(m->d_partial.reserve(size_t(plan.n_sources) * size_t(std::max(nq, 1)) * m->p.k * sizeof(uint32_t)));
   const int er = int(m->k1_calls % tod_matcher::kEvRing);
-  TOD_CUDA(cudaEventRecord(m->ev0[er], st));
-  TOD_CUDA(tod::launch_k1_popc(plan, d_query, nq, m->d_db.ptr, m->shard_rows, uint32_t(m->shard_begin), m->p.k,
-                               m->p.radius, m->d_partial.as<uint32_t>(), st));
-  TOD_CUDA(cudaEventRecord(m->ev1[er], st));
-  ++m->k1_calls;
+  if (first) TOD_CUDA(cudaEventRecord(m->ev0[er], st));
+  TOD_CUDA(tod::launch_k1_popc(plan, d_query, nq, m->d_db.as<uint8_t>() + size_t(seg_row0) * 32, seg_rows, key_base,
+                               m->p.k, m->p.radius, m->d_partial.as<uint32_t>(), st));
+  if (last) {
+    TOD_CUDA(cudaEventRecord(m->ev1[er], st));
+    ++m->k1_calls;
+  }
   m->last_kernel = "popc";
   *plan_out = plan;
   return TOD_OK;
+}
+
+int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1Plan *plan_out) {
+  return run_k1(m, d_query, nq, st, plan_out, 0, m->shard_rows, uint32_t(m->shard_begin), true, true);
 }
 
 #define TOD_NCCL(expr)                                                                                \
@@ -126,7 +145,7 @@ int run_k1(tod_matcher *m, const void *d_query, int nq, cudaStream_t st, tod::K1
 // Merge (+ radius cut, decode, 3-D gather) and the opt-in post-filters, from n_src key lists per query.
 int finalize(tod_matcher *m, const uint32_t *d_keys, int n_src, int nq, tod_match *d_matches, int32_t *d_counts,
              float *d_points3d, cudaStream_t st, size_t src_stride = 0, const uint32_t *wait_flags = nullptr,
-             uint32_t wait_step = 0, uint32_t *wait_error = nullptr) {
+             uint32_t wait_step = 0, uint32_t *wait_error = nullptr, const uint32_t *src_base = nullptr) {
   const int k = m->p.k;
   const bool ratio = m->p.ratio_enabled != 0 && k >= 2;
   const bool dedupe = m->p.remove_duplicates != 0;
@@ -142,7 +161,8 @@ int finalize(tod_matcher *m, const uint32_t *d_keys, int n_src, int nq, tod_matc
   }
   TOD_CUDA(tod::launch_finalize_matches(d_keys, n_src, nq, k, m->p.radius, m->d_offsets.as<uint32_t>(),
                                         int(m->ids.size()), m->d_pts.as<float>(), d_matches, d_counts, d_points3d, st,
-                                        ratio ? 1 : 0, m->p.ratio, rows, src_stride, wait_flags, wait_step, wait_error));
+                                        ratio ? 1 : 0, m->p.ratio, rows, src_stride, wait_flags, wait_step, wait_error,
+                                        src_base));
   if (dedupe)
     TOD_CUDA(tod::launch_remove_duplicates(d_matches, d_counts, d_points3d, rows, nq, k, m->p.frame_keypoints,
                                            m->d_hkeys.ptr, m->d_hvals.ptr, slots, st));
@@ -157,6 +177,42 @@ int run_process(tod_matcher *m, const void *d_query, int nq, tod_match *d_matche
                 float *d_points3d, cudaStream_t st) {
   const int k = m->p.k;
   tod::K1Plan plan;
+  if (m->wide) {
+    // more than 2^23 rows in all: one K1 launch + top-k reduction per segment of this shard (keys local to the
+    // segment; the shared per-query bounds carry over, so later segments start warm), then the merge over every
+    // (rank, segment) list on 64-bit (distance, global row) keys.  The exchange is the ncclAllGather one.
+    const int world = m->p.shard_count;
+    if (world > 1 && !m->comm)
+      return fail(TOD_ERR_STATE, "this handle holds shard %d of %d: call tod_matcher_set_comm first", m->p.shard_rank,
+                  world);
+    const size_t nk = size_t(nq) * k;
+    TOD_CUDA(m->d_keys_local.reserve(nk * sizeof(uint32_t) * size_t(m->n_seg)));
+    int last_seg = 0;
+    for (int sg = 0; sg < m->n_seg; ++sg)
+      if (int64_t(sg) * tod::kMaxGlobalRows < m->shard_rows) last_seg = sg;
+    for (int sg = 0; sg < m->n_seg; ++sg) {
+      const int64_t r0 = int64_t(sg) * tod::kMaxGlobalRows;
+      const int64_t rows = std::min<int64_t>(tod::kMaxGlobalRows, m->shard_rows - r0);
+      uint32_t *dst = m->d_keys_local.as<uint32_t>() + size_t(sg) * nk;
+      if (rows <= 0) {  // the last rank's shard may end before the last segment
+        TOD_CUDA(cudaMemsetAsync(dst, 0xFF, nk * sizeof(uint32_t), st));
+        continue;
+      }
+      if (int rc = run_k1(m, d_query, nq, st, &plan, r0, rows, 0u, sg == 0, sg == last_seg)) return rc;
+      TOD_CUDA(tod::launch_reduce_keys(m->d_partial.as<uint32_t>(), plan.n_sources, nq, k, dst, st));
+    }
+    if (world == 1)
+      return finalize(m, m->d_keys_local.as<uint32_t>(), m->n_seg, nq, d_matches, d_counts, d_points3d, st, 0, nullptr,
+                      0, nullptr, m->d_src_base.as<uint32_t>());
+    TOD_CUDA(m->d_keys_all.reserve(nk * sizeof(uint32_t) * size_t(m->n_seg) * size_t(world)));
+    if (m->stage_timing) TOD_CUDA(cudaEventRecord(m->ev_x0, st));
+    TOD_NCCL(tod::nccl_api().AllGather(m->d_keys_local.ptr, m->d_keys_all.ptr, nk * size_t(m->n_seg), tod::kNcclUint32,
+                                       m->comm, st));
+    if (m->stage_timing) TOD_CUDA(cudaEventRecord(m->ev_x1, st));
+    m->ev_x_valid = m->stage_timing;
+    return finalize(m, m->d_keys_all.as<uint32_t>(), world * m->n_seg, nq, d_matches, d_counts, d_points3d, st, 0,
+                    nullptr, 0, nullptr, m->d_src_base.as<uint32_t>());
+  }
   if (m->p.shard_count == 1) {
     if (int rc = run_k1(m, d_query, nq, st, &plan)) return rc;
     return finalize(m, m->d_partial.as<uint32_t>(), plan.n_sources, nq, d_matches, d_counts, d_points3d, st);
@@ -165,7 +221,7 @@ int run_process(tod_matcher *m, const void *d_query, int nq, tod_match *d_matche
     return fail(TOD_ERR_STATE, "this handle holds shard %d of %d: call tod_matcher_set_comm first (or use the "
                                "*_device stage calls with your own exchange)", m->p.shard_rank, m->p.shard_count);
   const size_t nk = size_t(nq) * k;
-  if (m->peer_enabled && (!m->peer_tried || (m->comm_mode == 2 && nk > m->peer_cap)))
+  if (m->peer_enabled && !m->wide && (!m->peer_tried || (m->comm_mode == 2 && nk > m->peer_cap)))
     if (int rc = setup_peer_exchange(m, nk, st)) return rc;
   if (m->comm_mode == 2) {
     // K1 -> [top-k reduction fused with the all-gather: stores into every rank's buffer over NVLink] -> merge, which
@@ -409,7 +465,7 @@ void tod_matcher_destroy(tod_matcher *m) {
   close_comm(m);
   for (DeviceBuffer *b : {&m->d_db, &m->d_pts, &m->d_offsets, &m->d_query, &m->d_partial, &m->d_matches,
                           &m->d_counts, &m->d_pts3d, &m->d_db8, &m->d_q8, &m->d_gthr, &m->d_popq, &m->d_rows,
-                          &m->d_hkeys, &m->d_hvals, &m->d_keys_local, &m->d_keys_all, &m->d_peer_tbl})
+                          &m->d_hkeys, &m->d_hvals, &m->d_keys_local, &m->d_keys_all, &m->d_peer_tbl, &m->d_src_base})
     b->release();
   for (int i = 0; i < tod_matcher::kEvRing; ++i) {
     if (m->ev0[i]) cudaEventDestroy(m->ev0[i]);
@@ -426,9 +482,9 @@ int tod_matcher_add_object(tod_matcher *m, const char *object_id, const uint8_t 
   TOD_REQUIRE(m && object_id, "null argument");
   TOD_REQUIRE(n >= 0 && (n == 0 || (descriptors && points)), "bad descriptor/point buffers");
   const int64_t total = int64_t(m->offsets.back()) + n;
-  if (total > tod::kMaxGlobalRows)
-    return fail(TOD_ERR_LIMIT, "DB would hold %lld descriptors; packed u32 keys address at most %lld rows",
-                (long long)total, (long long)tod::kMaxGlobalRows);
+  if (total > tod::kMaxDbRows)
+    return fail(TOD_ERR_LIMIT, "DB would hold %lld descriptors; at most %lld are supported", (long long)total,
+                (long long)tod::kMaxDbRows);
   m->ids.emplace_back(object_id);
   m->h_desc.insert(m->h_desc.end(), descriptors, descriptors + size_t(n) * 32);
   m->h_pts.insert(m->h_pts.end(), points, points + size_t(n) * 3);
@@ -477,6 +533,20 @@ int tod_matcher_train(tod_matcher *m) {
                              cudaMemcpyHostToDevice, m->stream));
   TOD_CUDA(cudaMemcpyAsync(m->d_offsets.ptr, m->offsets.data(), m->offsets.size() * sizeof(uint32_t),
                            cudaMemcpyHostToDevice, m->stream));
+  // wide database: segments of 2^23 rows per shard, the same count on every rank (shards are ceil(total / world) rows)
+  m->wide = total > tod::kMaxGlobalRows;
+  m->n_seg = 1;
+  if (m->wide) {
+    const int64_t per = (total + m->p.shard_count - 1) / m->p.shard_count;
+    m->n_seg = int((per + tod::kMaxGlobalRows - 1) / tod::kMaxGlobalRows);
+    std::vector<uint32_t> base(size_t(m->p.shard_count) * size_t(m->n_seg));
+    for (int r = 0; r < m->p.shard_count; ++r)
+      for (int sg = 0; sg < m->n_seg; ++sg)
+        base[size_t(r) * m->n_seg + sg] =
+            uint32_t(std::min<int64_t>(total, per * r) + int64_t(sg) * tod::kMaxGlobalRows);
+    TOD_CUDA(m->d_src_base.reserve(base.size() * sizeof(uint32_t)));
+    TOD_CUDA(cudaMemcpy(m->d_src_base.ptr, base.data(), base.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
   m->have_db8 = false;
   if (use_mma(m)) {
     static_assert(sizeof(m->map_db) >= 128, "CUtensorMap is 128 bytes");
@@ -554,9 +624,12 @@ int tod_matcher_reserve(tod_matcher *m, int32_t max_nq) {
   const int step = 256;
   for (int64_t q = step; q < int64_t(nq) + step; q += step) {
     const int qq = int(std::min<int64_t>(q, int64_t(nq)));
-    const tod::K1Plan pl = use_mma(m) ? tod::k1_mma_plan(qq, m->shard_rows, m->sm_count)
-                                      : tod::k1_popc_plan(qq, m->shard_rows, m->sm_count);
-    partial = std::max(partial, size_t(pl.n_sources) * size_t(qq) * k * sizeof(uint32_t));
+    for (int64_t rows : {std::min<int64_t>(m->shard_rows, tod::kMaxGlobalRows),
+                         m->shard_rows % tod::kMaxGlobalRows ? m->shard_rows % tod::kMaxGlobalRows : m->shard_rows}) {
+      const tod::K1Plan pl = use_mma(m) ? tod::k1_mma_plan(qq, rows, m->sm_count)
+                                        : tod::k1_popc_plan(qq, rows, m->sm_count);
+      partial = std::max(partial, size_t(pl.n_sources) * size_t(qq) * k * sizeof(uint32_t));
+    }
   }
   TOD_CUDA(m->d_partial.reserve(partial));
   TOD_CUDA(m->d_query.reserve(nq * 32));
@@ -568,9 +641,10 @@ int tod_matcher_reserve(tod_matcher *m, int32_t max_nq) {
     TOD_CUDA(m->d_gthr.reserve(nq * sizeof(uint32_t)));
     TOD_CUDA(m->d_popq.reserve(nq * sizeof(uint32_t)));
   }
-  if (m->p.shard_count > 1) {
-    TOD_CUDA(m->d_keys_local.reserve(nk * sizeof(uint32_t)));
-    TOD_CUDA(m->d_keys_all.reserve(nk * sizeof(uint32_t) * size_t(m->p.shard_count)));
+  if (m->p.shard_count > 1 || m->wide) {
+    TOD_CUDA(m->d_keys_local.reserve(nk * sizeof(uint32_t) * size_t(m->n_seg)));
+    if (m->p.shard_count > 1)
+      TOD_CUDA(m->d_keys_all.reserve(nk * sizeof(uint32_t) * size_t(m->n_seg) * size_t(m->p.shard_count)));
   }
   if (m->p.remove_duplicates) {
     size_t slots = 1024;
@@ -646,6 +720,9 @@ int tod_matcher_knn_keys_device(tod_matcher *m, const void *d_descriptors, int32
   TOD_REQUIRE(m && d_keys, "null argument");
   TOD_REQUIRE(nq >= 0 && (nq == 0 || d_descriptors), "bad query buffer");
   if (!m->trained) return fail(TOD_ERR_STATE, "tod_matcher_knn_keys_device called before tod_matcher_train");
+  if (m->wide)
+    return fail(TOD_ERR_LIMIT, "the stage calls carry 32-bit global keys (2^23 rows); this database is wider: use "
+                               "tod_matcher_knn / tod_matcher_knn_device");
   if (nq == 0) return TOD_OK;
   if (int rc = use_device(m)) return rc;
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : m->stream;
@@ -660,6 +737,9 @@ int tod_matcher_merge_device(tod_matcher *m, const uint32_t *d_keys_all, int32_t
   TOD_REQUIRE(m && d_keys_all && d_matches && d_counts, "null argument");
   TOD_REQUIRE(n_src >= 1 && nq >= 0, "bad sizes");
   if (!m->trained) return fail(TOD_ERR_STATE, "tod_matcher_merge_device called before tod_matcher_train");
+  if (m->wide)
+    return fail(TOD_ERR_LIMIT, "the stage calls carry 32-bit global keys (2^23 rows); this database is wider: use "
+                               "tod_matcher_knn / tod_matcher_knn_device");
   if (nq == 0) return TOD_OK;
   if (int rc = use_device(m)) return rc;
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : m->stream;

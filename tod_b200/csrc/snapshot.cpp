@@ -87,9 +87,9 @@ int tod_snapshot_write(const char *path, int32_t n_objects, const char *const *o
     total += uint64_t(rows[o]);
     id_bytes += std::strlen(object_ids[o]);
   }
-  if (int64_t(total) > tod::kMaxGlobalRows)
-    return tod::fail(TOD_ERR_LIMIT, "%llu descriptors exceed the %lld-row limit of the packed keys",
-                     (unsigned long long)total, (long long)tod::kMaxGlobalRows);
+  if (int64_t(total) > tod::kMaxDbRows)
+    return tod::fail(TOD_ERR_LIMIT, "%llu descriptors exceed the %lld-row limit", (unsigned long long)total,
+                     (long long)tod::kMaxDbRows);
   Header h{};
   std::memcpy(h.magic, kMagic, 8);
   h.version = kVersion;
@@ -148,7 +148,7 @@ int tod_snapshot_open(const char *path, tod_snapshot **out) {
   // Every bound is checked by subtraction against the file size (no u64 sum can wrap): the offsets are ordered,
   // aligned, inside the file, and each region is large enough for the counts the header claims.
   bool ok = std::memcmp(h->magic, kMagic, 8) == 0 && h->version == kVersion && h->file_bytes == size &&
-            int64_t(rows) <= tod::kMaxGlobalRows && n <= size / sizeof(Entry);
+            int64_t(rows) <= tod::kMaxDbRows && n <= size / sizeof(Entry);
   ok = ok && h->off_table >= sizeof(Header) && h->off_table <= size && h->off_table % 8 == 0 &&
        h->off_desc <= size && h->off_pts <= size && h->off_ids <= size && h->off_table <= h->off_desc &&
        h->off_desc <= h->off_pts && h->off_pts <= h->off_ids && h->off_desc % 4 == 0 && h->off_pts % 4 == 0;

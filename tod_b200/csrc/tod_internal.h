@@ -88,7 +88,8 @@ struct PinnedBuffer {
 constexpr int kKeyRowBits = 23;
 constexpr uint32_t kKeyRowMask = (1u << kKeyRowBits) - 1;
 constexpr uint32_t kKeyEmpty = 0xFFFFFFFFu;
-constexpr int64_t kMaxGlobalRows = int64_t(1) << kKeyRowBits;
+constexpr int64_t kMaxGlobalRows = int64_t(1) << kKeyRowBits;  // rows one packed key can address (a "segment")
+constexpr int64_t kMaxDbRows = (int64_t(1) << 31) - 1;        // whole database (larger ones are cut into segments)
 
 struct K1Plan {
   int q_per_thread;    // 1, 2 or 4
@@ -120,21 +121,25 @@ int k1_mma_db_box_rows();
 size_t tensor_map_bytes();
 // d_gthr: nq u32 shared per-query bounds, must hold 511 (no bound) before the launch; d_popq: nq query popcounts
 // (both written by launch_expand_queries).
+// seg_row0: the launch covers rows [seg_row0, seg_row0 + shard_rows) of the matrix behind map_db (a segment of a
+// wide database); keys count rows from global_row_base + 0 at seg_row0.
 cudaError_t launch_k1_mma(const K1Plan &plan, const void *map_q, const void *map_db, int nq, int64_t shard_rows,
                           uint32_t global_row_base, int k, uint32_t radius, uint32_t *d_partial, uint32_t *d_gthr,
-                          const uint32_t *d_popq, cudaStream_t stream);
+                          const uint32_t *d_popq, cudaStream_t stream, int64_t seg_row0 = 0);
 
 // Reduce n_src x nq x k key lists to nq x k keys (ascending).
 cudaError_t launch_reduce_keys(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t *d_out,
                                cudaStream_t stream);
-// Reduce + radius cut + decode (imgIdx, trainIdx) + matches_3d gather.
+// Reduce + radius cut + decode (imgIdx, trainIdx) + matches_3d gather.  d_src_base (wide databases, more than 2^23
+// rows): first global row of every source list, whose keys then count rows from there; the merge compares
+// (distance, global row) on 64 bits.
 cudaError_t launch_finalize_matches(const uint32_t *d_keys, int n_src, int nq, int k, uint32_t radius,
                                     const uint32_t *d_obj_offsets, int n_objects, const float *d_points,
                                     tod_match *d_matches, int32_t *d_counts, float *d_points3d,
                                     cudaStream_t stream, int ratio_enabled = 0, float ratio = 0.f,
                                     uint32_t *d_rows_out = nullptr, size_t src_stride = 0,
                                     const uint32_t *d_wait_flags = nullptr, uint32_t wait_step = 0,
-                                    uint32_t *d_wait_error = nullptr);
+                                    uint32_t *d_wait_error = nullptr, const uint32_t *d_src_base = nullptr);
 // Fused top-k reduction + all-gather over peer memory (k1_merge.cu: reduce_push_kernel): the reduced keys of this rank
 // go straight into slot `rank` of every rank's exchange buffer (d_peers[r] = that buffer's base for this step's parity,
 // CUDA-IPC-mapped), then this rank's flag (at d_peers[r] + flag_offset + rank) is raised to `step` on every peer.
