@@ -115,7 +115,8 @@ void tod_matcher_destroy(tod_matcher *m);
 
 /* parameter_callback(), one DB document per call (DescriptorMatcher.cpp:70-123): descriptors = n x 32 u8 row-major
  * (training.cpp:157), points = n x 3 f32 (the 1 x N CV_32FC3 "points" attachment, training.cpp:158). Data is copied.
- * The object's span (:106-121) is computed here.  imgIdx = order of calls. */
+ * The object's span (:106-121) is computed here.  imgIdx = order of calls.  At most 2^31 - 1 descriptors in all
+ * (TOD_ERR_LIMIT beyond); above 2^23 the database is scanned in segments of 2^23 rows, transparently. */
 int tod_matcher_add_object(tod_matcher *m, const char *object_id, const uint8_t *descriptors, const float *points,
                            int32_t n);
 /* matcher_->clear() (:127) */
@@ -179,7 +180,9 @@ float tod_matcher_last_exchange_ms(const tod_matcher *m);
 
 /* Sharding of the concatenated DB over `shard_count` GPUs (host-only, no device needed): rank r holds the contiguous
  * global rows [*begin, *begin + *rows), ceil(total/shard_count) rows each except the last ranks.  tod_matcher_train
- * uses exactly this split.  tod_pack_key builds the u32 candidate key that travels between ranks. */
+ * uses exactly this split.  tod_pack_key builds the u32 candidate key (distance << 23 | global row) that the stage
+ * calls below exchange; it addresses 2^23 rows, so those calls return TOD_ERR_LIMIT on a wider database (the
+ * whole-call entry points handle it: their keys are local to a 2^23-row segment). */
 int tod_shard_range(int64_t total_rows, int32_t shard_rank, int32_t shard_count, int64_t *begin, int64_t *rows);
 uint32_t tod_pack_key(uint32_t distance, uint32_t global_row);
 
