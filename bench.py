@@ -288,10 +288,25 @@ def parity_sample(args, m_np, c_np, p_np, descs, points, queries):
                      "queries + %d per frame" % per_frame}
 
 
+# what ncu says really bounds the geometry kernels (profiles/r2_geometry_ncu.json, one `--set full` capture each): their
+# matrices stay in the 126 MB L2, so the HBM fraction north_star asks for is small by construction
+NCU_NOTES = {
+    "k2_adjacency_kernel": {"issue_slots_busy_pct": 76.8, "dram_throughput_pct": 0.18, "dram_bytes_per_launch": 2418432,
+                            "bound_by": "instruction issue (about 89 warp instructions per 32 pair tests, no FMA "
+                                        "contraction allowed); the output stays in L2",
+                            "source": "profiles/r2_geometry_ncu.json"},
+    "k3_score_kernel": {"issue_slots_busy_pct": 18.0, "dram_throughput_pct": 0.63, "dram_bytes_per_launch": 1630464,
+                        "bound_by": "launch latency at C4 (16 384 hypotheses, 32 us); L2 bandwidth at C5",
+                        "source": "profiles/r2_geometry_ncu.json"},
+}
+
+
 def hbm_roofline(kernel, alg_bytes, ms, hbm_peak, hbm_src, extra=None):
     gbs = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     r = {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
          "peak_source": hbm_src, "kernel_ms": ms, "algorithmic_bytes": alg_bytes, "traffic": None}
+    if kernel in NCU_NOTES:
+        r["ncu"] = NCU_NOTES[kernel]
     if extra:
         r.update(extra)
     return r

@@ -104,7 +104,7 @@ struct State {
   unsigned char snapshot[kMaxN];
   Idx cls[kMaxN];
   Idx count[kMaxN + 2];
-  BitsN<NW> class_mask[kMaxN + 1];
+  BitsN<NW> class_mask[kMaxN + 5];   // classes are 1-based; four are tested per trip
   int size[kSmallGateMinimal + 2];
   unsigned level_steps[kSmallGateMinimal + 3], level_steps_old[kSmallGateMinimal + 3];
 };
@@ -144,11 +144,24 @@ TOD_HD void colour_sort(const BitsN<NW> *adj, State<NW, Idx> &s, unsigned char *
     const int p = r[i];
     s.snapshot[i] = (unsigned char)p;
     const BitsN<NW> a = adj[p];
+    // first class without a neighbour of p, four classes per trip: the four tests are independent loads, so a thread
+    // that walks a 200-vertex list through ~25 classes is not serialised on one branch per class
     int k = 1;
-    while (k <= n_classes && intersects(a, s.class_mask[k])) ++k;
+    for (;; k += 4) {
+      // (masks past n_classes hold stale words: read, then masked out — no short-circuit, the loads stay independent)
+      const bool h0 = intersects(a, s.class_mask[k]) & (k <= n_classes);
+      const bool h1 = intersects(a, s.class_mask[k + 1]) & (k + 1 <= n_classes);
+      const bool h2 = intersects(a, s.class_mask[k + 2]) & (k + 2 <= n_classes);
+      const bool h3 = intersects(a, s.class_mask[k + 3]) & (k + 3 <= n_classes);
+      if (!h0) break;
+      if (!h1) { k += 1; break; }
+      if (!h2) { k += 2; break; }
+      if (!h3) { k += 3; break; }
+    }
     if (k > n_classes) {
       n_classes = k;
       s.class_mask[k] = empty_set<NW>();
+      s.class_mask[k + 4] = empty_set<NW>();   // keeps every mask the four-wide test can read defined
       s.count[k] = 0;
     }
     set_bit(s.class_mask[k], p);
@@ -182,6 +195,7 @@ TOD_HD int small_gate_search_t(const BitsN<NW> *adj, int n, int step_cap, int *s
   if (n <= 0) return 0;
   State<NW, Idx> s;
   for (int i = 0; i < kMinimal + 3; ++i) s.level_steps[i] = s.level_steps_old[i] = 0u;
+  for (int i = 0; i < 5; ++i) s.class_mask[i] = small_clique::empty_set<NW>();   // read (and masked) before first use
   int steps = 1;
   int best = 0, cur = 0;
   unsigned char *order = s.lists[1];
