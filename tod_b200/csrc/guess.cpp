@@ -73,6 +73,8 @@ struct Cluster {
   std::vector<uint32_t> best_inliers;
   float best_R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, best_T[3] = {0, 0, 0};  // R_, T_ of the best hypothesis (finite mode)
   std::vector<uint32_t> hyps;  // triples of the current batch
+  std::vector<uint32_t> hyps_next;  // triples drawn ahead for the next batch while the GPU scores this one
+  bool drawn_ahead = false;
   int batch_begin = 0;         // offset of this cluster's hypotheses in the frame-wide batch
 };
 
@@ -515,6 +517,8 @@ struct tod_guess {
   DeviceBuffer d_jobs;                               // K5: queue of packed induced sub-graphs (<= 128 vertices each)
   int64_t k5_stats[4] = {0, 0, 0, 0};
   tod::PinnedBuffer h_P, h_S;  // host copies of the bit-matrices (read by the sampler and the gate)
+  tod::PinnedBuffer h_counts, h_verdict, h_hyps;  // per-batch K3 counts / gate verdicts / triples: pinned, so that the
+                                                  // copies are truly asynchronous and the host can draw ahead
   float k2_ms = 0, k3_ms = 0;
   double k2_bytes = 0, k3_bytes = 0;  // algorithmic bytes of the last call's K2 / K3 launches (SURVEY.md §8d units)
   int64_t n_clusters = 0, n_correspondences = 0;
@@ -646,6 +650,9 @@ void tod_guess_destroy(tod_guess *g) {
   if (g->stream) cudaStreamDestroy(g->stream);
   g->h_P.release();
   g->h_S.release();
+  g->h_counts.release();
+  g->h_verdict.release();
+  g->h_hyps.release();
   delete g->pool;
   delete g;
 }
@@ -836,7 +843,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   TOD_CUDA(g->d_floor.reserve(size_t(nc) * 4));
   std::vector<uint32_t> all_deg(all_valid.size(), 0u);
   std::vector<int32_t> floor_by_cluster(static_cast<size_t>(nc), 0);
-  std::vector<uint8_t> batch_verdict;
+  const uint8_t *batch_verdict = nullptr;
   int max_W = 0;
   for (const Cluster *c : clusters) max_W = std::max(max_W, c->W);
   long k4_fails_used = 0, k4_host_used = 0, k5_pass_used = 0, k5_fail_used = 0;
@@ -884,6 +891,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     std::vector<uint32_t> kp;
   };
   const int max_iter = int(g->p.n_ransac_iterations);
+  bool long_rounds_seen = false;  // a round of this call went past its first batch of hypotheses
   const int n_thr = pool.size();
   struct ThreadScratch {
     GateScratch gate;
@@ -895,7 +903,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   std::vector<ThreadScratch> ts(static_cast<size_t>(n_thr));
   std::vector<std::vector<Found>> found_by_cluster(clusters.size());
   std::vector<uint32_t> batch_hyps;
-  std::vector<int32_t> batch_counts;
+  const int32_t *batch_counts = nullptr;
   std::vector<float> batch_R, batch_T;
   std::vector<int> active_idx;
 
@@ -940,6 +948,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     // computeModel (ransac.h:80-143): hypotheses are drawn and scored in growing batches; the replay below consumes
     // them in order and stops exactly where the reference's loop would.
     int batch_size = 64;
+    int batches_this_round = 0;
     while (true) {
       // -- sampler (getSamples, sac_model_registration_graph.h:141-168), clusters in parallel ---------------------------
       t_phase = Clock::now();
@@ -947,6 +956,11 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         Cluster *c = clusters[size_t(active_idx[size_t(ai)])];
         c->hyps.clear();
         if (c->stopped) return;
+        if (c->drawn_ahead) {  // this batch was drawn while the GPU scored the previous one
+          c->hyps.swap(c->hyps_next);
+          c->drawn_ahead = false;
+          return;
+        }
         // the loop can run at most until iterations_ exceeds max_iterations_ (ransac.h:132-134)
         const int room = std::min(batch_size, max_iter + 1 - c->iterations);
         for (int h = 0; h < room; ++h) {
@@ -972,7 +986,8 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
       t_phase = Clock::now();
       const int H = int(batch_hyps.size() / 4);
       if (H > 0) {
-        batch_counts.resize(size_t(H));
+        TOD_CUDA(g->h_counts.reserve(size_t(H) * 4));
+        batch_counts = g->h_counts.as<int32_t>();
         TOD_CUDA(g->d_hyps.reserve(batch_hyps.size() * 4));
         TOD_CUDA(g->d_counts.reserve(size_t(H) * 4));
         if (!inf_thr) {
@@ -981,21 +996,24 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
           batch_R.resize(size_t(H) * 9);
           batch_T.resize(size_t(H) * 3);
         }
-        TOD_CUDA(cudaMemcpyAsync(g->d_hyps.ptr, batch_hyps.data(), batch_hyps.size() * 4, cudaMemcpyHostToDevice, st));
+        TOD_CUDA(g->h_hyps.reserve(batch_hyps.size() * 4));
+        std::memcpy(g->h_hyps.ptr, batch_hyps.data(), batch_hyps.size() * 4);
+        TOD_CUDA(cudaMemcpyAsync(g->d_hyps.ptr, g->h_hyps.ptr, batch_hyps.size() * 4, cudaMemcpyHostToDevice, st));
         TOD_CUDA(cudaEventRecord(g->ev0, st));
         TOD_CUDA(tod::launch_score_hypotheses_batched(
             g->d_desc.ptr, g->d_q.as<float>(), g->d_t.as<float>(), g->d_P.as<uint32_t>(), g->d_valid.as<uint32_t>(),
             g->d_finite.as<uint32_t>(), H, g->d_hyps.as<uint32_t>(), g->p.ransac_threshold, g->d_counts.as<int32_t>(),
             inf_thr ? nullptr : g->d_R.as<float>(), inf_thr ? nullptr : g->d_T.as<float>(), st));
         TOD_CUDA(cudaEventRecord(g->ev1, st));
-        TOD_CUDA(cudaMemcpyAsync(batch_counts.data(), g->d_counts.ptr, size_t(H) * 4, cudaMemcpyDeviceToHost, st));
+        TOD_CUDA(cudaMemcpyAsync(g->h_counts.ptr, g->d_counts.ptr, size_t(H) * 4, cudaMemcpyDeviceToHost, st));
         if (inf_thr) {
           // K4: the gate's exact pre-checks for every hypothesis of the batch that beats its cluster's best so far
           for (int ci : active_idx) {
             const Cluster *c = clusters[size_t(ci)];
             floor_by_cluster[size_t(ci)] = c->n_best < 0 ? 0 : c->n_best;
           }
-          batch_verdict.resize(size_t(H));
+          TOD_CUDA(g->h_verdict.reserve(size_t(H)));
+          batch_verdict = g->h_verdict.as<uint8_t>();
           TOD_CUDA(g->d_verdict.reserve(size_t(H)));
           // K5 queue: room for every hypothesis of the launch at 2 KB (128 vertices; the rare graphs of up to 256
           // take 8 KB, most take 0.5 KB), capped at 1 GiB; a hypothesis that finds the pool full goes to the host
@@ -1010,11 +1028,39 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
                                               g->d_counts.as<int32_t>(), g->d_floor.as<int32_t>(), max_W,
                                               g->d_verdict.as<uint8_t>(), g->d_jobs.ptr, pool_bytes, st, g->ev4));
           TOD_CUDA(cudaEventRecord(g->ev3, st));
-          TOD_CUDA(cudaMemcpyAsync(batch_verdict.data(), g->d_verdict.ptr, size_t(H), cudaMemcpyDeviceToHost, st));
+          TOD_CUDA(cudaMemcpyAsync(g->h_verdict.ptr, g->d_verdict.ptr, size_t(H), cudaMemcpyDeviceToHost, st));
         }
         if (!inf_thr) {
           TOD_CUDA(cudaMemcpyAsync(batch_R.data(), g->d_R.ptr, size_t(H) * 36, cudaMemcpyDeviceToHost, st));
           TOD_CUDA(cudaMemcpyAsync(batch_T.data(), g->d_T.ptr, size_t(H) * 12, cudaMemcpyDeviceToHost, st));
+        }
+        // While the GPU scores this batch: draw the NEXT batch of every cluster that can still need one.  The sampler
+        // stream of a round does not depend on the replay (the valid set is fixed during a round), so the triples are
+        // the ones the next batch would draw anyway; if the replay stops the cluster they are dropped with the round.
+        // Only in rounds that are already known to be long (this is their second batch, or an earlier round of this
+        // call needed one): short rounds — a clean object found in the first 64 hypotheses — pay nothing.
+        if (inf_thr && (batches_this_round >= 1 || long_rounds_seen)) {
+          const Clock::time_point t_ahead = Clock::now();
+          const int next_size = std::min(batch_size * 4, 4096);
+          pool.run(int(active_idx.size()), [&](int ai, int t) {
+            Cluster *c = clusters[size_t(active_idx[size_t(ai)])];
+            c->drawn_ahead = false;
+            if (c->stopped) return;
+            const int nh = int(c->hyps.size() / 3);
+            const int room_now = std::min(batch_size, max_iter + 1 - c->iterations);
+            if (nh < room_now) return;                        // the sampler ran dry: the round ends with this batch
+            const int room = std::min(next_size, max_iter + 1 - (c->iterations + nh));
+            if (room <= 0) return;
+            c->hyps_next.clear();
+            for (int h = 0; h < room; ++h) {
+              uint32_t tr[3];
+              if (!get_samples(*c, ts[size_t(t)].sampler, c->rng, tr)) break;
+              c->hyps_next.insert(c->hyps_next.end(), tr, tr + 3);
+            }
+            c->drawn_ahead = true;
+          });
+          g->prof[1] += ms_since(t_ahead);
+          t_phase += Clock::now() - t_ahead;                  // accounted under "sampler", not under "K3 launch + sync"
         }
         TOD_CUDA(cudaStreamSynchronize(st));
         float ms = 0.f;
@@ -1194,7 +1240,10 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         if (!sc.error.empty()) return fail(TOD_ERR_STATE, "%s", sc.error.c_str());
       if (!more.load()) break;
       batch_size = std::min(batch_size * 4, 4096);
+      ++batches_this_round;
+      long_rounds_seen = true;
     }
+    for (int ci : active_idx) clusters[size_t(ci)]->drawn_ahead = false;  // what was drawn ahead ends with the round
 
     // finish the round per cluster: refinement, pose, invalidation (adjacency_ransac.cpp:255-308,
     // GuessGenerator.cpp:205-230), clusters in parallel
