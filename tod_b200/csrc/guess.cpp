@@ -947,6 +947,9 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
 
     // computeModel (ransac.h:80-143): hypotheses are drawn and scored in growing batches; the replay below consumes
     // them in order and stops exactly where the reference's loop would.
+    // batches of 64, 256, 1024, 1024, ... hypotheses per cluster: while the GPU scores one the host draws the next, so
+    // only the last batch of a round is waited for in full — hence the cap (4096 left 3 ms per round exposed at C5)
+    constexpr int kMaxBatch = 1024;
     int batch_size = 64;
     int batches_this_round = 0;
     while (true) {
@@ -1041,7 +1044,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         // call needed one): short rounds — a clean object found in the first 64 hypotheses — pay nothing.
         if (inf_thr && (batches_this_round >= 1 || long_rounds_seen)) {
           const Clock::time_point t_ahead = Clock::now();
-          const int next_size = std::min(batch_size * 4, 4096);
+          const int next_size = std::min(batch_size * 4, kMaxBatch);
           pool.run(int(active_idx.size()), [&](int ai, int t) {
             Cluster *c = clusters[size_t(active_idx[size_t(ai)])];
             c->drawn_ahead = false;
@@ -1239,7 +1242,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
       for (const ThreadScratch &sc : ts)
         if (!sc.error.empty()) return fail(TOD_ERR_STATE, "%s", sc.error.c_str());
       if (!more.load()) break;
-      batch_size = std::min(batch_size * 4, 4096);
+      batch_size = std::min(batch_size * 4, kMaxBatch);
       ++batches_this_round;
       long_rounds_seen = true;
     }
