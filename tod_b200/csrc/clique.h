@@ -18,6 +18,8 @@
 #include <utility>
 #include <vector>
 
+#include "bitops.h"
+
 namespace tod {
 
 class CliqueFinder {
@@ -80,13 +82,9 @@ class CliqueFinder {
       for (int i = 0; i < n_; ++i) order[size_t(i)] = i;
     else
       for (int i = 0; i < n_; ++i) order[size_t(i)] = int(view_[size_t(i)]);
-    sort_by_degree(order);  // leaves (degree inside the graph, vertex) ascending in pairs_
-    {
-      unsigned long long twice_edges = 0;
-      for (const auto &pr : pairs_) twice_edges += pr.first;
-      dense_ = 2ull * twice_edges > (unsigned long long)(n_) * (unsigned long long)(n_ - 1);
-    }
-    const unsigned top = pairs_.back().first;
+    sort_by_degree(order);  // leaves the largest degree and the degree sum behind
+    dense_ = 2ull * last_degree_sum_ > (unsigned long long)(n_) * (unsigned long long)(n_ - 1);
+    const unsigned top = last_top_;
     colour_.assign(size_t(n_), 0u);
     for (unsigned i = 0; i < top && i < unsigned(n_); ++i) colour_[i] = i + 1;
     for (unsigned i = top; i < unsigned(n_); ++i) colour_[i] = top + 1;
@@ -99,21 +97,46 @@ class CliqueFinder {
   }
 
  private:
-  // descending by (degree inside `r`, vertex id): std::sort of (degree, vertex) pairs read backwards.
+  // descending by (degree inside `r`, vertex id): what std::sort of (degree, vertex) pairs read backwards gives the
+  // reference (DegreeSort, maximum_clique.cpp:263-284) — here a counting sort: degrees are below |r|, and walking the
+  // set's bit mask from the top yields the vertices of equal degree in descending id order.
   // degree inside r = popcount(row & mask of r) — the same numbers the reference gets from pairwise tests.
+  // Leaves the largest degree in last_top_ and the degree sum in last_degree_sum_.
   void sort_by_degree(std::vector<int> &r) {
     const size_t m = r.size();
     set_mask_.assign(size_t(words_), 0ull);
     for (int v : r) set_mask_[size_t(v) >> 6] |= 1ull << (v & 63);
-    pairs_.resize(m);
+    if (deg_of_.size() < size_t(id_space_)) deg_of_.resize(size_t(id_space_));
+    if (deg_count_.size() < m + 2) deg_count_.resize(m + 2);
+    std::fill(deg_count_.begin(), deg_count_.begin() + long(m) + 1, 0u);
+    unsigned top = 0;
+    unsigned long long sum = 0;
     for (size_t i = 0; i < m; ++i) {
       const uint64_t *row = rows_ + size_t(r[i]) * words_;
-      unsigned d = 0;
-      for (int w = 0; w < words_; ++w) d += unsigned(__builtin_popcountll(row[w] & set_mask_[size_t(w)]));
-      pairs_[i] = std::make_pair(d, r[i]);
+      const unsigned d = unsigned(bitops::and_popcount(row, set_mask_.data(), words_));
+      deg_of_[size_t(r[i])] = d;
+      ++deg_count_[d];
+      top = std::max(top, d);
+      sum += d;
     }
-    std::sort(pairs_.begin(), pairs_.end());
-    for (size_t i = 0; i < m; ++i) r[i] = pairs_[m - 1 - i].second;
+    last_top_ = top;
+    last_degree_sum_ = sum;
+    // deg_count_[d] <- first position of degree d in the descending order
+    unsigned pos = 0;
+    for (long d = long(top); d >= 0; --d) {
+      const unsigned c = deg_count_[size_t(d)];
+      deg_count_[size_t(d)] = pos;
+      pos += c;
+    }
+    for (int w = words_ - 1; w >= 0; --w) {
+      uint64_t x = set_mask_[size_t(w)];
+      while (x) {
+        const int b = 63 - __builtin_clzll(x);
+        x &= ~(1ull << b);
+        const int v = w * 64 + b;
+        r[deg_count_[deg_of_[size_t(v)]]++] = v;
+      }
+    }
   }
 
   // greedy sequential colouring; vertices whose colour cannot extend the incumbent go first with colour 0.
@@ -220,14 +243,16 @@ class CliqueFinder {
         const uint64_t *row = rows_ + size_t(v) * words_;
         uint64_t any = 0;
         if (first_member) {
-          for (int w = 0; w < words_; ++w) any |= (cand_[size_t(w)] = set_mask_[size_t(w)] & ~row[w]);
+          any = bitops::andnot_store_any(cand_.data(), set_mask_.data(), row, words_);
         } else {
           cand_[size_t(v) >> 6] &= ~(1ull << (v & 63));
-          for (int w = 0; w < words_; ++w) any |= (cand_[size_t(w)] &= ~row[w]);
+          any = bitops::andnot_store_any(cand_.data(), cand_.data(), row, words_);
         }
         if (!any) break;
         // next member = the candidate that comes first in the order of r; it lies behind the last member.  Look a few
         // positions ahead (a hit is likely while the candidate set is large), else take the minimum rank directly.
+        // (Choosing between the two by the size of the candidate set was measured and is slower: 0.145 against 0.095 ms
+        // on a 630-vertex graph.)
         more = false;
         const size_t lim = std::min(m, at + 1 + 12);
         for (size_t i = at + 1; i < lim; ++i) {
@@ -324,7 +349,9 @@ class CliqueFinder {
   bool dense_ = false;  // more than half of all vertex pairs are edges: colour_sort walks non-neighbours
   std::vector<int> class_of_;
   uint32_t stamp_ = 0u;
-  std::vector<std::pair<unsigned, int> > pairs_;
+  std::vector<unsigned> deg_of_, deg_count_;
+  unsigned last_top_ = 0;
+  unsigned long long last_degree_sum_ = 0;
   std::vector<std::vector<int> > classes_;
   std::vector<int> snapshot_;
   std::vector<uint64_t> bits_;

@@ -171,20 +171,12 @@ bool get_samples(const Cluster &c, SamplerScratch &sc, uint64_t &rng, uint32_t t
     const uint32_t r0 = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count0));
     const uint32_t s0 = copied ? select_bit64(cur0, W64, r0) : select_valid(c, W64, r0);
     const uint64_t *row0 = S + size_t(s0) * W64;
-    int count1 = 0;
-    for (int w = 0; w < W64; ++w) {
-      l1[w] = cur0[w] & row0[w];
-      count1 += popc64(l1[w]);
-    }
+    int count1 = tod::bitops::and_store_popcount(l1, cur0, row0, W64);
     while (count1 > 0) {
       const uint32_t r1 = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count1));
       const uint32_t s1 = select_bit64(l1, W64, r1);
       const uint64_t *row1 = S + size_t(s1) * W64;
-      int count2 = 0;
-      for (int w = 0; w < W64; ++w) {
-        l2[w] = l1[w] & row1[w];
-        count2 += popc64(l2[w]);
-      }
+      const int count2 = tod::bitops::and_store_popcount(l2, l1, row1, W64);
       if (count2 > 0) {
         const uint32_t r2 = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count2));
         triple[0] = select_bit64(l2, W64, r2);
