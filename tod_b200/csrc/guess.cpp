@@ -509,6 +509,7 @@ struct tod_guess {
   DeviceBuffer d_jobs;                               // K5: queue of packed induced sub-graphs (<= 128 vertices each)
   int64_t k5_stats[4] = {0, 0, 0, 0};
   tod::PinnedBuffer h_P, h_S;  // host copies of the bit-matrices (read by the sampler and the gate)
+  tod::PinnedBuffer h_pts;     // staging of the clusters' query / training points and pixels for the upload
   tod::PinnedBuffer h_counts, h_verdict, h_hyps;  // per-batch K3 counts / gate verdicts / triples: pinned, so that the
                                                   // copies are truly asynchronous and the host can draw ahead
   float k2_ms = 0, k3_ms = 0;
@@ -643,6 +644,7 @@ void tod_guess_destroy(tod_guess *g) {
   g->h_P.release();
   g->h_S.release();
   g->h_counts.release();
+  g->h_pts.release();
   g->h_verdict.release();
   g->h_hyps.release();
   delete g->pool;
@@ -783,14 +785,6 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
     c.point_offset = offsets.back();
     c.matrix_offset = mo.back();
     c.valid_offset = vo;
-    c.valid.assign(size_t(c.W), 0u);
-    c.finite.assign(size_t(c.W), 0u);
-    for (int i = 0; i < c.n; ++i) {
-      c.valid[size_t(i) >> 5] |= 1u << (i & 31);
-      bool fin = true;
-      for (int d = 0; d < 3; ++d) fin = fin && std::isfinite(c.q[size_t(i) * 3 + d]) && std::isfinite(c.t[size_t(i) * 3 + d]);
-      if (fin) c.finite[size_t(i) >> 5] |= 1u << (i & 31);
-    }
     c.n_valid = c.n;
     offsets.push_back(offsets.back() + c.n);
     mo.push_back(mo.back() + int64_t(c.n) * c.W);
@@ -807,23 +801,33 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   g->k2_bytes = 32.0 * double(N) + 2.0 * 4.0 * double(mat_words);  // 32 n in + two n x W bit-matrices out
 
   // ---- FillAdjacency for every cluster: K2 --------------------------------------------------------------------------
-  std::vector<float> all_q(size_t(N) * 3), all_t(size_t(N) * 3), all_px(size_t(N) * 2);
+  // staged in pinned memory (the uploads run at PCIe speed and do not park the host), clusters packed in parallel
+  TOD_CUDA(g->h_pts.reserve(size_t(N) * 8 * sizeof(float)));
+  float *all_q = g->h_pts.as<float>(), *all_t = all_q + size_t(N) * 3, *all_px = all_t + size_t(N) * 3;
   std::vector<uint32_t> all_valid(static_cast<size_t>(vo)), all_finite(static_cast<size_t>(vo));
   std::vector<unsigned char> desc(size_t(nc) * tod::k3_cluster_desc_size());
-  for (int ci = 0; ci < nc; ++ci) {
+  pool.run(nc, [&](int ci, int) {
     Cluster &c = *clusters[size_t(ci)];
-    std::copy(c.q.begin(), c.q.end(), all_q.begin() + c.point_offset * 3);
-    std::copy(c.t.begin(), c.t.end(), all_t.begin() + c.point_offset * 3);
-    std::copy(c.px.begin(), c.px.end(), all_px.begin() + c.point_offset * 2);
+    c.valid.assign(size_t(c.W), 0u);
+    c.finite.assign(size_t(c.W), 0u);
+    for (int i = 0; i < c.n; ++i) {
+      c.valid[size_t(i) >> 5] |= 1u << (i & 31);
+      bool fin = true;
+      for (int d = 0; d < 3; ++d) fin = fin && std::isfinite(c.q[size_t(i) * 3 + d]) && std::isfinite(c.t[size_t(i) * 3 + d]);
+      if (fin) c.finite[size_t(i) >> 5] |= 1u << (i & 31);
+    }
+    std::copy(c.q.begin(), c.q.end(), all_q + c.point_offset * 3);
+    std::copy(c.t.begin(), c.t.end(), all_t + c.point_offset * 3);
+    std::copy(c.px.begin(), c.px.end(), all_px + c.point_offset * 2);
     std::copy(c.finite.begin(), c.finite.end(), all_finite.begin() + c.valid_offset);
     tod::k3_fill_cluster_desc(desc.data() + size_t(ci) * tod::k3_cluster_desc_size(), c.n, c.W, c.point_offset,
                               c.matrix_offset, c.valid_offset);
-  }
+  });
   TOD_CUDA(g->d_off.reserve(offsets.size() * 4));
   TOD_CUDA(g->d_mo.reserve(mo.size() * 8));
-  TOD_CUDA(g->d_q.reserve(all_q.size() * 4));
-  TOD_CUDA(g->d_t.reserve(all_t.size() * 4));
-  TOD_CUDA(g->d_px.reserve(all_px.size() * 4));
+  TOD_CUDA(g->d_q.reserve(size_t(N) * 3 * 4));
+  TOD_CUDA(g->d_t.reserve(size_t(N) * 3 * 4));
+  TOD_CUDA(g->d_px.reserve(size_t(N) * 2 * 4));
   TOD_CUDA(g->d_sp.reserve(spans_c.size() * 4));
   TOD_CUDA(g->d_P.reserve(mat_words * 4));
   TOD_CUDA(g->d_S.reserve(mat_words * 4));
@@ -842,9 +846,9 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   float k4_ms = 0.f, k5_ms = 0.f;  // K4 + K5 together / K5 alone
   TOD_CUDA(cudaMemcpyAsync(g->d_off.ptr, offsets.data(), offsets.size() * 4, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(g->d_mo.ptr, mo.data(), mo.size() * 8, cudaMemcpyHostToDevice, st));
-  TOD_CUDA(cudaMemcpyAsync(g->d_q.ptr, all_q.data(), all_q.size() * 4, cudaMemcpyHostToDevice, st));
-  TOD_CUDA(cudaMemcpyAsync(g->d_t.ptr, all_t.data(), all_t.size() * 4, cudaMemcpyHostToDevice, st));
-  TOD_CUDA(cudaMemcpyAsync(g->d_px.ptr, all_px.data(), all_px.size() * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_q.ptr, all_q, size_t(N) * 3 * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_t.ptr, all_t, size_t(N) * 3 * 4, cudaMemcpyHostToDevice, st));
+  TOD_CUDA(cudaMemcpyAsync(g->d_px.ptr, all_px, size_t(N) * 2 * 4, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(g->d_sp.ptr, spans_c.data(), spans_c.size() * 4, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(g->d_desc.ptr, desc.data(), desc.size(), cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaMemcpyAsync(g->d_finite.ptr, all_finite.data(), all_finite.size() * 4, cudaMemcpyHostToDevice, st));
