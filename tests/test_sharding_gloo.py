@@ -40,7 +40,7 @@ def _workload(tie_heavy):
     return descs, q
 
 
-def _rank_main(rank, world, port, k, radius, tie_heavy, out_dir):
+def _rank_main(rank, world, port, k, radius, tie_heavy, out_dir, local_keys=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -51,6 +51,7 @@ def _rank_main(rank, world, port, k, radius, tie_heavy, out_dir):
     descs, q = _workload(tie_heavy)
     db, off = hk.concat_objects(descs)
     begin, rows = ctypes.c_int64(), ctypes.c_int64()
+    b2, r2 = ctypes.c_int64(), ctypes.c_int64()
     assert lib.tod_shard_range(db.shape[0], rank, world, ctypes.byref(begin), ctypes.byref(rows)) == capi.TOD_OK
     begin, rows = begin.value, rows.value
     # this rank's candidates: exact top-k of its row range as ONE pseudo-object, re-based to global rows
@@ -59,23 +60,45 @@ def _rank_main(rank, world, port, k, radius, tie_heavy, out_dir):
         m, c = hk.knn_c(q, [db[begin:begin + rows]], k, radius)
         for i in range(q.shape[0]):
             for j in range(int(c[i])):
-                keys[i, j] = lib.tod_pack_key(int(m["distance"][i, j]), begin + int(m["trainIdx"][i, j]))
+                # wide databases: the key counts rows from the start of the rank's segment, not from row 0 of the DB
+                keys[i, j] = lib.tod_pack_key(int(m["distance"][i, j]),
+                                              int(m["trainIdx"][i, j]) + (0 if local_keys else begin))
     mine = torch.from_numpy(keys.view(np.int32).copy())
     gathered = torch.empty((world,) + tuple(mine.shape), dtype=torch.int32)
     dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
     allk = gathered.numpy().view(np.uint32)                       # world x nq x k
-    merged = np.sort(allk.transpose(1, 0, 2).reshape(q.shape[0], -1), axis=1)[:, :k]
+    if local_keys:
+        # the merge of a wide database: (distance, first row of the source + local row) on 64 bits, empty = all ones
+        bases = []
+        for r in range(world):
+            assert lib.tod_shard_range(db.shape[0], r, world, ctypes.byref(b2), ctypes.byref(r2)) == capi.TOD_OK
+            bases.append(b2.value)
+        wide = np.full(allk.shape, np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+        for r in range(world):
+            kk = allk[r].astype(np.uint64)
+            ok = allk[r] != EMPTY
+            wide[r][ok] = ((kk[ok] >> np.uint64(KEY_ROW_BITS)) << np.uint64(32)) | \
+                          (np.uint64(bases[r]) + (kk[ok] & np.uint64((1 << KEY_ROW_BITS) - 1)))
+        m64 = np.sort(wide.transpose(1, 0, 2).reshape(q.shape[0], -1), axis=1)[:, :k]
+        merged = np.where(m64 == np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(EMPTY),
+                          ((m64 >> np.uint64(32)) << np.uint64(KEY_ROW_BITS)) | (m64 & np.uint64(0xFFFFFFFF))).astype(np.uint32)
+    else:
+        merged = np.sort(allk.transpose(1, 0, 2).reshape(q.shape[0], -1), axis=1)[:, :k]
     np.save(os.path.join(out_dir, "merged_%d.npy" % rank), merged)
     np.save(os.path.join(out_dir, "range_%d.npy" % rank), np.array([begin, rows]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,radius,tie_heavy", [(2, 0, False), (5, 35, False), (5, 0, True)])
-def test_two_rank_key_exchange_equals_single_node(tmp_path, k, radius, tie_heavy):
+@pytest.mark.parametrize("k,radius,tie_heavy,local_keys", [(2, 0, False, False), (5, 35, False, False),
+                                                           (5, 0, True, False), (5, 0, True, True), (3, 35, False, True)])
+def test_two_rank_key_exchange_equals_single_node(tmp_path, k, radius, tie_heavy, local_keys):
+    """local_keys: the protocol of a wide database (more than 2^23 rows) — keys local to the rank's segment travel
+    unchanged and the merge orders (distance, global row) on 64 bits from the table of segment bases."""
     from oracle import hamming_knn as hk
     world = 2
-    mp.spawn(_rank_main, args=(world, _free_port(), k, radius, tie_heavy, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_rank_main, args=(world, _free_port(), k, radius, tie_heavy, str(tmp_path), local_keys), nprocs=world,
+             join=True)
     descs, q = _workload(tie_heavy)
     db, off = hk.concat_objects(descs)
     em, ec = hk.knn_c(q, descs, k, radius)
