@@ -267,7 +267,9 @@ void close_peer_exchange(tod_matcher *m) {
 // Collective over the ranks of the communicator (every rank reaches it in the same call, with the same nq): allocate
 // the exchange buffer, trade CUDA IPC handles through NCCL, map the peers' buffers.  Any rank that cannot map a peer
 // (no peer access, handles opened inside one process, ...) makes ALL ranks stay on the ncclAllGather path.
-int setup_peer_exchange(tod_matcher *m, size_t need_keys, cudaStream_t st) {
+// (worker: `local` / `mapped` / `d_rec` belong to the caller, which frees them when the mapping is not adopted)
+int setup_peer_exchange_impl(tod_matcher *m, size_t need_keys, cudaStream_t st, void *&local, std::vector<void *> &mapped,
+                             DeviceBuffer &d_rec, bool &adopted) {
   const tod::NcclApi &api = tod::nccl_api();
   const int world = m->p.shard_count, rank = m->p.shard_rank;
   TOD_CUDA(cudaStreamSynchronize(st));
@@ -276,7 +278,6 @@ int setup_peer_exchange(tod_matcher *m, size_t need_keys, cudaStream_t st) {
   const size_t cap = (std::max(need_keys, size_t(std::max(m->reserved_nq, 0)) * size_t(m->p.k)) + 63) & ~size_t(63);
   const size_t half = size_t(world) * cap + 64 * ((size_t(world) + 63) / 64);
   bool ok = world <= 128;
-  void *local = nullptr;
   if (ok && cudaMalloc(&local, 2 * half * sizeof(uint32_t)) != cudaSuccess) ok = false, local = nullptr, cudaGetLastError();
   if (local) ok = cudaMemset(local, 0, 2 * half * sizeof(uint32_t)) == cudaSuccess;
   cudaIpcMemHandle_t mine;
@@ -289,7 +290,6 @@ int setup_peer_exchange(tod_matcher *m, size_t need_keys, cudaStream_t st) {
     int32_t pad[15];
   };
   static_assert(sizeof(Rec) == 128, "IPC record");
-  DeviceBuffer d_rec;
   TOD_CUDA(d_rec.reserve(sizeof(Rec) * size_t(world + 1)));
   Rec my{};
   my.h = mine;
@@ -301,7 +301,7 @@ int setup_peer_exchange(tod_matcher *m, size_t need_keys, cudaStream_t st) {
   TOD_CUDA(cudaMemcpyAsync(all.data(), d_rec.ptr, sizeof(Rec) * size_t(world), cudaMemcpyDeviceToHost, st));
   TOD_CUDA(cudaStreamSynchronize(st));
   for (const Rec &r : all) ok = ok && r.ok == 1;
-  std::vector<void *> mapped(static_cast<size_t>(world), nullptr);
+  mapped.assign(static_cast<size_t>(world), nullptr);
   if (ok) {
     for (int r = 0; r < world && ok; ++r) {
       if (r == rank) {
@@ -321,14 +321,8 @@ int setup_peer_exchange(tod_matcher *m, size_t need_keys, cudaStream_t st) {
   TOD_NCCL(api.AllGather(d_my, d_rec.ptr, sizeof(Rec), tod::kNcclUint8, m->comm, st));
   TOD_CUDA(cudaMemcpyAsync(all.data(), d_rec.ptr, sizeof(Rec) * size_t(world), cudaMemcpyDeviceToHost, st));
   TOD_CUDA(cudaStreamSynchronize(st));
-  d_rec.release();
   for (const Rec &r : all) ok = ok && r.ok == 1;
-  if (!ok) {
-    for (int r = 0; r < world; ++r)
-      if (mapped[size_t(r)] && r != rank) cudaIpcCloseMemHandle(mapped[size_t(r)]);
-    if (local) cudaFree(local);
-    return TOD_OK;  // stay on NCCL
-  }
+  if (!ok) return TOD_OK;  // stay on NCCL (the caller releases what was allocated and mapped)
   m->peer_local = static_cast<uint32_t *>(local);
   m->peer_mapped = mapped;
   m->peer_cap = cap;
@@ -343,7 +337,27 @@ int setup_peer_exchange(tod_matcher *m, size_t need_keys, cudaStream_t st) {
   TOD_CUDA(cudaMemcpyAsync(m->d_peer_tbl.ptr, tbl.data(), tbl.size() * 8, cudaMemcpyHostToDevice, st));
   TOD_CUDA(cudaStreamSynchronize(st));
   m->comm_mode = 2;
+  adopted = true;
   return TOD_OK;
+}
+
+int setup_peer_exchange(tod_matcher *m, size_t need_keys, cudaStream_t st) {
+  void *local = nullptr;
+  std::vector<void *> mapped;
+  DeviceBuffer d_rec;
+  bool adopted = false;
+  const int rc = setup_peer_exchange_impl(m, need_keys, st, local, mapped, d_rec, adopted);
+  d_rec.release();
+  if (!adopted) {  // error or "stay on NCCL": nothing of this attempt survives
+    for (size_t r = 0; r < mapped.size(); ++r)
+      if (mapped[r] && mapped[r] != local) cudaIpcCloseMemHandle(mapped[r]);
+    if (local) cudaFree(local);
+    m->peer_local = nullptr;
+    m->peer_mapped.clear();
+    m->peer_cap = m->peer_half = 0;
+    if (m->comm_mode == 2) m->comm_mode = 1;
+  }
+  return rc;
 }
 
 void close_comm(tod_matcher *m) {
