@@ -19,6 +19,7 @@
 // memory (W words per warp).  Reference-faithful (+inf threshold) mode only: the candidate set is
 // P[s0] & P[s1] & P[s2] & valid & finite, plus the three samples.
 #include "clique_small.h"
+#include "k5_warp.cuh"
 #include "tod_internal.h"
 
 namespace tod {
@@ -340,29 +341,75 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
   finish((any_found || any_overflow) ? kGateNeedsHost : kGateFails);
 }
 
-// K5: the reference's bounded clique search, stepped exactly, one thread per queued hypothesis.
+// K5, thread form: the reference's bounded clique search, stepped exactly, one THREAD per queued hypothesis whose
+// graph has at most 64 vertices (one-word rows) — the bulk of the queue, tens of steps each.
 __global__ void __launch_bounds__(kK5Threads)
 k5_search_kernel(const int4 *__restrict__ job_hdr, const unsigned long long *__restrict__ job_pool,
                  const unsigned long long *__restrict__ job_ctl, int n_hyp, int step_cap,
                  uint8_t *__restrict__ verdict) {
-  const long long j = (long long)blockIdx.x * kK5Threads + threadIdx.x;  // header slot, 2 * n_hyp of them
-  const long long n1 = (long long)job_ctl[0], n2 = (long long)job_ctl[1], n4 = (long long)job_ctl[3];
-  const bool mine = j < n1 || (j >= (long long)n_hyp - n2 && j < n_hyp) || (j >= n_hyp && j < (long long)n_hyp + n4);
-  if (!mine) return;
+  const long long j = (long long)blockIdx.x * kK5Threads + threadIdx.x;  // header slot
+  if (j >= (long long)job_ctl[0]) return;
   const int4 hd = job_hdr[j];
   if (hd.y <= 0) return;  // the pool was full: the verdict stays "host"
   const unsigned long long *rows = job_pool + ((unsigned long long)(unsigned)hd.z | ((unsigned long long)(unsigned)hd.w << 32));
-  int r;
-  if (hd.y <= 64) r = small_gate_search(reinterpret_cast<const Bits64 *>(rows), hd.y, step_cap, nullptr);
-  else if (hd.y <= 128) r = small_gate_search(reinterpret_cast<const Bits128 *>(rows), hd.y, step_cap, nullptr);
-  else r = small_gate_search(reinterpret_cast<const Bits256 *>(rows), hd.y, step_cap, nullptr);
+  const int r = small_gate_search(reinterpret_cast<const Bits64 *>(rows), hd.y, step_cap, nullptr);
   if (r == 1) verdict[hd.x] = uint8_t(kGatePasses);
   else if (r == 0) verdict[hd.x] = uint8_t(kGateFailsSearch);
 }
 
+// K5, warp form (k5_warp.cuh): one WARP per queued hypothesis of 65..256 vertices.  A fixed grid of warps pulls jobs
+// from a counter, widest graphs first (they are the slowest).
+constexpr int kK5WarpsPerCta = 4;
+constexpr int kK5WarpCtas = 296;   // two CTAs per SM
+constexpr size_t kK5WarpStateBytes = (sizeof(k5w::WarpState<4>) + 15) & ~size_t(15);
+__global__ void __launch_bounds__(kK5WarpsPerCta * 32)
+k5_warp_kernel(const int4 *__restrict__ job_hdr, const unsigned long long *__restrict__ job_pool,
+               unsigned long long *__restrict__ job_ctl, int n_hyp, int step_cap, uint8_t *__restrict__ verdict) {
+  extern __shared__ __align__(16) unsigned char k5w_smem[];
+  const int lane = threadIdx.x & 31;
+  void *state = k5w_smem + size_t(threadIdx.x >> 5) * kK5WarpStateBytes;
+  const unsigned long long n2 = job_ctl[1], n4 = job_ctl[3];
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(job_ctl + 4, 1ull);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    long long slot;
+    if (idx < n4) slot = (long long)n_hyp + (long long)idx;
+    else if (idx - n4 < n2) slot = (long long)n_hyp - 1 - (long long)(idx - n4);
+    else break;
+    const int4 hd = job_hdr[slot];
+    if (hd.y <= 0) continue;
+    const unsigned long long *rows = job_pool + ((unsigned long long)(unsigned)hd.z | ((unsigned long long)(unsigned)hd.w << 32));
+    const int r = hd.y <= 128
+                      ? k5w::warp_gate_search<2>(*static_cast<k5w::WarpState<2> *>(state), rows, hd.y, step_cap, lane)
+                      : k5w::warp_gate_search<4>(*static_cast<k5w::WarpState<4> *>(state), rows, hd.y, step_cap, lane);
+    if (lane == 0) {
+      if (r == 1) verdict[hd.x] = uint8_t(kGatePasses);
+      else if (r == 0) verdict[hd.x] = uint8_t(kGateFailsSearch);
+    }
+    __syncwarp();
+  }
+}
+
+// both forms of K5 over a filled job queue
+cudaError_t launch_k5(int4 *job_hdr, unsigned long long *job_pool, unsigned long long *job_ctl, int n_hyp,
+                      uint8_t *d_verdict, cudaStream_t stream) {
+  const size_t smem = size_t(kK5WarpsPerCta) * kK5WarpStateBytes;
+  cudaError_t e = cudaFuncSetAttribute(k5_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  // the warp form first: its jobs are the long ones, the thread form fills the machine around them
+  k5_warp_kernel<<<kK5WarpCtas, kK5WarpsPerCta * 32, smem, stream>>>(job_hdr, job_pool, job_ctl, n_hyp, kK5StepCap,
+                                                                    d_verdict);
+  k5_search_kernel<<<(n_hyp + kK5Threads - 1) / kK5Threads, kK5Threads, 0, stream>>>(job_hdr, job_pool, job_ctl, n_hyp,
+                                                                                    kK5StepCap, d_verdict);
+  count_launch(2);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
-// job queue layout: [4 x u64 control: 1-word jobs, 2-word jobs, pool words used, 4-word jobs | pad to 256 B]
+// job queue layout: [u64 control: 1-word jobs, 2-word jobs, pool words used, 4-word jobs, warp-form job cursor | pad
+// to 256 B]
 // [2 * n_hyp headers] [pool]
 size_t gate_job_bytes(int n_hyp, size_t pool_bytes) {
   return 256 + ((2 * size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)) + pool_bytes;
@@ -375,10 +422,7 @@ cudaError_t launch_gate_search_jobs(int n_hyp, void *d_jobs, uint8_t *d_verdict,
   int4 *job_hdr = reinterpret_cast<int4 *>(static_cast<char *>(d_jobs) + 256);
   unsigned long long *job_pool = reinterpret_cast<unsigned long long *>(
       static_cast<char *>(d_jobs) + 256 + ((2 * size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)));
-  k5_search_kernel<<<(2 * n_hyp + kK5Threads - 1) / kK5Threads, kK5Threads, 0, stream>>>(job_hdr, job_pool, job_ctl, n_hyp,
-                                                                                        kK5StepCap, d_verdict);
-  count_launch();
-  return cudaGetLastError();
+  return launch_k5(job_hdr, job_pool, job_ctl, n_hyp, d_verdict, stream);
 }
 
 cudaError_t launch_sample_degree_mask(const void *d_clusters, const int32_t *d_active, int n_active, int max_n,
@@ -415,7 +459,7 @@ cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_phys
     job_hdr = reinterpret_cast<int4 *>(static_cast<char *>(d_jobs) + 256);
     job_pool = reinterpret_cast<unsigned long long *>(static_cast<char *>(d_jobs) + 256 +
                                                       ((2 * size_t(n_hyp) * sizeof(int4) + 255) & ~size_t(255)));
-    e = cudaMemsetAsync(job_ctl, 0, 4 * sizeof(unsigned long long), stream);
+    e = cudaMemsetAsync(job_ctl, 0, 8 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
   }
   const int blocks = (n_hyp + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -429,9 +473,8 @@ cudaError_t launch_gate_prechecks(const void *d_clusters, const uint32_t *d_phys
     if (e != cudaSuccess) return e;
   }
   if (job_hdr) {
-    k5_search_kernel<<<(2 * n_hyp + kK5Threads - 1) / kK5Threads, kK5Threads, 0, stream>>>(job_hdr, job_pool, job_ctl,
-                                                                                          n_hyp, kK5StepCap, d_verdict);
-    count_launch();
+    e = launch_k5(job_hdr, job_pool, job_ctl, n_hyp, d_verdict, stream);
+    if (e != cudaSuccess) return e;
   }
   return cudaGetLastError();
 }
