@@ -28,6 +28,11 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 constexpr int kSmallCore = 128;   // exhaustive search limit (two 64-bit words per set)
 constexpr int kProofMax = tod::kGateProofMax;  // larger filtered graphs skip the proofs (host search)
+#ifndef TOD_K4_SEARCH_EARLY
+#define TOD_K4_SEARCH_EARLY 1      // n > 0: graphs K5 takes leave the proofs after n peeling sweeps (0: full proofs).
+                                   // Measured at C5: K4 + K5 63 -> 57 ms of device time with 1 (K5 is bound by its slowest
+                                   // search, not by the number of searches: 933 k jobs take the 24 ms that 768 k took)
+#endif
 constexpr int kSearchMax = 256;   // largest filtered graph K5 takes (four 64-bit words per row)
 constexpr int kMaxSweeps = 64;
 constexpr int kDfsBudget = 6000;  // node expansions per lane before giving the hypothesis back to the host
@@ -125,6 +130,7 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
 
   // ---- neighbourhood test (:222-238) and 7-core: Jacobi sweeps of "degree inside the live set" ------------------------
   int n_alive = nf;
+  bool search_early = false;
   for (int sweep = 0;; ++sweep) {
     if (sweep >= kMaxSweeps) return finish(kGateNeedsHost);
     int max_d = 0, removed = 0;
@@ -174,6 +180,19 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
     }
     // the reference scans for ONE filtered vertex with more than 7 sample-neighbours inside filtered
     if (sweep == 0 && max_d <= 7) return finish(kGateFails);
+#if TOD_K4_SEARCH_EARLY
+    // graphs K5 takes anyway: one peeling sweep (it settles the neighbourhood test and most of the small cores), then
+    // straight to the exact search instead of iterating to the 7-core and colouring it
+    if (job_hdr != nullptr && nf <= kSearchMax && sweep >= TOD_K4_SEARCH_EARLY - 1 && removed != 0) {
+      __syncwarp();
+      for (int w = lane; w < W; w += 32) alive[w] &= ~work[w];
+      n_alive -= removed;
+      __syncwarp();
+      if (n_alive < 8) return finish(kGateFails);
+      search_early = true;
+      break;
+    }
+#endif
     if (removed == 0) break;
     __syncwarp();
     for (int w = lane; w < W; w += 32) alive[w] &= ~work[w];
@@ -187,8 +206,8 @@ k4_gate_kernel(const K3Cluster *__restrict__ clusters, const uint32_t *__restric
   for (int w = lane; w < W; w += 32) work[w] = alive[w];  // uncoloured
   __syncwarp();
   int colours = 0;
-  bool undecided = false;
-  for (int left = n_alive; left > 0;) {
+  bool undecided = search_early;
+  for (int left = search_early ? 0 : n_alive; left > 0;) {
     if (++colours >= 8) {
       undecided = true;
       break;
