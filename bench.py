@@ -5,16 +5,21 @@ Metric (BASELINE.json): frames/sec at 2k keypoints x 1M-descriptor DB (100 objec
 Hamming k-NN k=2, on 1/2/4/8 B200; Hamming Gcmp/s vs the matching roofline.
 
 A "step" = one batch of `--frames` synthetic frames (2000 query descriptors each) through the hot path:
-  value : frames/s with the queries already resident in HBM (K1 k-NN -> [NCCL all-gather of packed top-k keys when
-          the DB is sharded] -> merge/radius/decode/3-D gather), timed with CUDA events, max over ranks;
+  value : frames/s with the queries already resident in HBM (K1 k-NN -> [when the DB is sharded: top-k reduction fused
+          with the exchange of the packed keys over peer memory, or ncclAllGather] -> merge/radius/decode/3-D gather),
+          timed with CUDA events, max over ranks;
   e2e   : the same metric through the reference-facing call with HOST buffers (pinned): H2D of the descriptors,
-          DescriptorMatcher.process, D2H of matches / counts / matches_3d, wall clock around synchronous calls.
-          (The geometry half is measured by tools/bench_geometry.py and, together with the matcher on the C4 stream
-          configuration, by tools/bench_pipeline.py.)
+          DescriptorMatcher.process, D2H of matches / counts / matches_3d, wall clock around synchronous calls
+          (N > 1: streamed, every rank uploads the batch and reads back the frames it owns).
+Beside the headline (N = 1): `parity` of the timed result against live cv2, `roofline` of K1, `cpu_baseline` (+ the
+reference's LSH matcher), `e2e_pipeline` = BASELINE config C4 through both cells (matcher + batched guess generator,
+back to back and streamed) with `stages` (K2 / K3 rooflines, host split), `stages_c5` = the RANSAC stress
+configuration, `feature_stage` = GPU ORB + DepthTo3d beside cv2.ORB.
 N > 1 shards the DB rows over the ranks (strong scaling: the 1M-descriptor DB is fixed).
 
 `--impl reference` times the reference's own CPU implementation of the path on the host cores: OpenCV's
-cv::BFMatcher(NORM_HAMMING) (the exact matcher north_star names; through cv2), on a bounded sample of each frame.
+cv::BFMatcher(NORM_HAMMING) (the exact matcher north_star names; through cv2) on all 2000 keypoints of a frame per
+step, plus the matcher the reference ships (FlannBasedMatcher + LSH) as `reference_lsh`.
 """
 import argparse
 import json
