@@ -37,9 +37,6 @@
 #endif
 
 #include "clique.h"
-#ifndef TOD_SAMPLER_PREFETCH
-#define TOD_SAMPLER_PREFETCH 0   // measured: 147 against 126 ns per triple on one core with the matrix in L2
-#endif
 #include "host_geometry.h"
 #include "tod_internal.h"
 
@@ -170,17 +167,6 @@ bool get_samples(const Cluster &c, SamplerScratch &sc, uint64_t &rng, uint32_t t
   uint64_t *own0 = sc.level[0].data(), *l1 = sc.level[1].data(), *l2 = sc.level[2].data();
   bool copied = false;
   int count0 = c.n_valid;
-#if TOD_SAMPLER_PREFETCH
-  {
-    // The row of the NEXT triple's first sample, fetched while this triple is drawn: a triple nearly always consumes
-    // three numbers of the stream, so the state three steps ahead names it (a wrong guess costs one useless prefetch).
-    uint64_t ahead = rng;
-    for (int i = 0; i < 3; ++i) (void)tod_rng_next(&ahead);
-    const uint32_t rn = uint32_t(uint64_t(tod_rng_next(&ahead)) % uint64_t(count0));
-    const char *row = reinterpret_cast<const char *>(S + size_t(select_valid(c, W64, rn)) * W64);
-    for (int b = 0; b < W64 * 8; b += 64) __builtin_prefetch(row + b, 0, 1);
-  }
-#endif
   for (;;) {
     const uint32_t r0 = uint32_t(uint64_t(tod_rng_next(&rng)) % uint64_t(count0));
     const uint32_t s0 = copied ? select_bit64(cur0, W64, r0) : select_valid(c, W64, r0);
