@@ -231,7 +231,8 @@ int run_process(tod_matcher *m, const void *d_query, int nq, tod_match *d_matche
     unsigned int *ticket = reinterpret_cast<unsigned int *>(m->d_peer_tbl.as<uint64_t>() + 2 * world);
     uint32_t *err = reinterpret_cast<uint32_t *>(m->d_peer_tbl.as<uint64_t>() + 2 * world + 1);
     if (int rc = run_k1(m, d_query, nq, st, &plan)) return rc;
-    const uint32_t step = ++m->peer_step;
+    if (++m->peer_step == 0u) m->peer_step = 2u;  // 0 is what freshly zeroed flags hold; 2 keeps the parity sequence
+    const uint32_t step = m->peer_step;
     const int par = int(step & 1u);
     const size_t flag_off = size_t(world) * m->peer_cap;
     if (m->stage_timing) TOD_CUDA(cudaEventRecord(m->ev_x0, st));
