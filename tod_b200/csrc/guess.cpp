@@ -720,20 +720,28 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
   }
   HostPool &pool = *g->pool;
 
-  // ---- ClusterPerObject (adjacency_ransac.cpp:176-205), frames in parallel: one cluster per (frame, object) --------
+  // ---- ClusterPerObject (adjacency_ransac.cpp:176-205): one cluster per (frame, object) -------------------------------
+  // Frames in parallel; when there are fewer frames than host threads (a single frame with 200 000 correspondences at
+  // C5) a frame's keypoints are cut into consecutive chunks that are clustered in parallel and then appended in chunk
+  // order — the same order of correspondences inside every cluster as one pass over the keypoints.
   std::vector<std::map<int, Cluster> > per_frame(static_cast<size_t>(n_frames));  // per frame: object -> cluster
-  std::vector<std::string> frame_error(static_cast<size_t>(n_frames));
+  const int chunks = n_frames >= pool.size() ? 1 : (pool.size() + n_frames - 1) / n_frames;
+  std::vector<std::map<int, Cluster> > partial(chunks > 1 ? size_t(n_frames) * size_t(chunks) : size_t(0));
+  std::vector<std::string> frame_error(size_t(n_frames) * size_t(chunks));
   const size_t cloud_stride = size_t(height) * size_t(width) * 3;
-  pool.run(n_frames, [&](int f, int) {
+  pool.run(n_frames * chunks, [&](int item, int) {
+    const int f = item / chunks, ch = item % chunks;
     const float *cloud = clouds + size_t(f) * cloud_stride;
-    std::map<int, Cluster> &mine = per_frame[size_t(f)];
+    std::map<int, Cluster> &mine = chunks > 1 ? partial[size_t(item)] : per_frame[size_t(f)];
+    const int64_t n_f = kp_offsets[f + 1] - kp_offsets[f];
+    const int32_t g_lo = kp_offsets[f] + int32_t(n_f * ch / chunks), g_hi = kp_offsets[f] + int32_t(n_f * (ch + 1) / chunks);
     char buf[200];
-    for (int32_t gi = kp_offsets[f]; gi < kp_offsets[f + 1]; ++gi) {
+    for (int32_t gi = g_lo; gi < g_hi; ++gi) {
       const int32_t qi = gi - kp_offsets[f];  // keypoint index inside its frame
       const int cnt = counts[gi];
       if (cnt < 0 || cnt > k) {
         snprintf(buf, sizeof(buf), "counts[%d] = %d outside [0, k=%d]", gi, cnt, k);
-        frame_error[size_t(f)] = buf;
+        frame_error[size_t(item)] = buf;
         return;
       }
       // point_cloud.at<Vec3f>(pt.y, pt.x): float -> int conversion truncates (quirk Q9)
@@ -741,7 +749,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
       if (!(y >= 0 && y < height && x >= 0 && x < width)) {
         snprintf(buf, sizeof(buf), "keypoint %d at (%g, %g) outside the %dx%d cloud", gi, keypoints[gi].x,
                  keypoints[gi].y, width, height);
-        frame_error[size_t(f)] = buf;
+        frame_error[size_t(item)] = buf;
         return;
       }
       const float *qp = cloud + (size_t(y) * width + x) * 3;
@@ -750,7 +758,7 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
         const tod_match &m = matches[size_t(gi) * k + j];
         if (m.imgIdx < 0 || m.imgIdx >= n_objects) {
           snprintf(buf, sizeof(buf), "match imgIdx %d outside [0, %d)", m.imgIdx, n_objects);
-          frame_error[size_t(f)] = buf;
+          frame_error[size_t(item)] = buf;
           return;
         }
         Cluster &c = mine[m.imgIdx];
@@ -765,6 +773,25 @@ int tod_guess_process_batch(tod_guess *g, int32_t n_frames, const int32_t *kp_of
       }
     }
   });
+  if (chunks > 1) {
+    pool.run(n_frames, [&](int f, int) {
+      std::map<int, Cluster> &dst = per_frame[size_t(f)];
+      for (int ch = 0; ch < chunks; ++ch)
+        for (auto &kv : partial[size_t(f) * size_t(chunks) + size_t(ch)]) {
+          Cluster &part = kv.second;
+          auto it = dst.find(kv.first);
+          if (it == dst.end()) {
+            dst.emplace(kv.first, std::move(part));
+            continue;
+          }
+          Cluster &c = it->second;
+          c.t.insert(c.t.end(), part.t.begin(), part.t.end());
+          c.q.insert(c.q.end(), part.q.begin(), part.q.end());
+          c.px.insert(c.px.end(), part.px.begin(), part.px.end());
+          c.qidx.insert(c.qidx.end(), part.qidx.begin(), part.qidx.end());
+        }
+    });
+  }
   for (const std::string &e : frame_error)
     if (!e.empty()) return fail(TOD_ERR_INVALID, "%s", e.c_str());
   std::vector<Cluster *> by_object;  // frames, then objects, ascending: the reference's std::map order per frame
